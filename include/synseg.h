@@ -1,0 +1,173 @@
+/*
+ * synseg.h -- C ABI of libsynseg.so, the B200 (sm_100a) raster region-detection hot path.
+ *
+ * The reference (ashr2k/synapta-image-segmentation) has no FFI of its own: it is a single Python
+ * file whose pixel arithmetic is delegated to the cv2 / PIL / numpy wheels.  Every entry point here
+ * therefore replaces one *call site* of those wheels in /root/reference/pdf_image_segmentation.py
+ * ("S:" below) or its old-algorithm twin ("O:"), or one of the north-star raster primitives that
+ * have no reference call site (oracle = the cv2 4.13.0 primitive).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; no CUDA/torch types.  `stream` is a cudaStream_t passed as void*.
+ *  - every function returns 0 on success, <0 on error (SYNSEG_E_*); synseg_last_error() gives text.
+ *    "Nothing found" (no components, empty mask) is a valid result, never an error.
+ *  - all image/result pointers are DEVICE pointers owned by the caller; calls are asynchronous on
+ *    `stream`.  The library owns only the opaque context (scratch arena, grown on demand or
+ *    pre-sized with synseg_reserve); one context per (process, GPU), not thread-safe.
+ *  - images are row-major, 8-bit unless stated, described by synseg_img: `batch` images of
+ *    height x width, `row_stride` / `batch_stride` in BYTES.  RGB images are interleaved HWC
+ *    (3 bytes per pixel; width counts pixels).  Any stride/alignment is accepted; rows whose base
+ *    and stride are 16-byte aligned take the vectorised path.
+ */
+#ifndef SYNSEG_H
+#define SYNSEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYNSEG_VERSION 100
+
+#define SYNSEG_OK 0
+#define SYNSEG_E_INVALID (-1)   /* bad argument */
+#define SYNSEG_E_CUDA (-2)      /* CUDA runtime error (text in synseg_last_error) */
+#define SYNSEG_E_NOMEM (-3)     /* scratch arena could not be grown */
+#define SYNSEG_E_CAPACITY (-4)  /* caller-provided result capacity too small */
+
+typedef struct synseg_ctx synseg_ctx;
+
+typedef struct synseg_img {
+    void *data;           /* device pointer to pixel (0,0) of image 0 */
+    int32_t width;        /* pixels */
+    int32_t height;       /* rows */
+    int64_t row_stride;   /* bytes between rows */
+    int32_t batch;        /* number of images (>= 1) */
+    int32_t _pad;
+    int64_t batch_stride; /* bytes between images */
+} synseg_img;
+
+/* Rectangular region of one image of a batch (crop given by reference, no copy). */
+typedef struct synseg_roi {
+    int32_t image;        /* index into the batch */
+    int32_t x, y;         /* top-left pixel */
+    int32_t width, height;
+} synseg_roi;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int synseg_version(void);
+const char *synseg_last_error(void);
+int synseg_create(int device, synseg_ctx **out);
+int synseg_destroy(synseg_ctx *ctx);
+/* Pre-size the scratch arena so that no call below allocates (bytes as returned by
+ * synseg_scratch_bytes for the largest batch you will submit). */
+int synseg_reserve(synseg_ctx *ctx, size_t bytes);
+size_t synseg_scratch_bytes(int32_t width, int32_t height, int32_t batch);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t synseg_launch_count(const synseg_ctx *ctx);
+
+/* ---- colour -------------------------------------------------------------------------------- */
+/* RGB -> grey.  mode 0: cv2.cvtColor(COLOR_RGB2GRAY) 15-bit fixed point (S:1348);
+ *               mode 1: PIL Image.convert('L') 16-bit fixed point (S:1323,1549,1599,1699,1758,1804,2988,3072). */
+#define SYNSEG_GRAY_CV 0
+#define SYNSEG_GRAY_PIL 1
+int synseg_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, int mode, void *stream);
+
+/* ---- threshold / edges --------------------------------------------------------------------- */
+/* cv2.adaptiveThreshold(g, 255, ADAPTIVE_THRESH_MEAN_C, invert ? THRESH_BINARY_INV : THRESH_BINARY,
+ * block_size, C): box mean over BORDER_REPLICATE.  block_size odd, 3..255.   */
+int synseg_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *out, int block_size, int C,
+                         int invert, void *stream);
+/* cv2.Canny(g, lo, hi) (aperture 3, L1 gradient): S:1324,1366,1550,1600,1700,1759.  Output {0,255}. */
+int synseg_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges, int lo, int hi, void *stream);
+
+/* ---- morphology ---------------------------------------------------------------------------- */
+#define SYNSEG_MORPH_ERODE 0
+#define SYNSEG_MORPH_DILATE 1
+#define SYNSEG_MORPH_OPEN 2   /* same values as cv2.MORPH_* */
+#define SYNSEG_MORPH_CLOSE 3
+#define SYNSEG_MORPH_BINARY 1 /* flag: caller guarantees pixels are 0 or 255 -> bit-packed fast path */
+/* cv2.erode / dilate / morphologyEx(op, getStructuringElement(MORPH_RECT,(kw,kh)), anchor=(ax,ay),
+ * iterations) with the default constant border.  ax/ay = -1 means the centre (kw/2, kh/2).
+ * Call sites: S:1370,1375 (1 x max(20,H/20), max(20,W/20) x 1, OPEN, it=2); S:1556,1557 (25x1, 1x25). */
+int synseg_morph(synseg_ctx *ctx, const synseg_img *src, const synseg_img *dst, int op, int kw, int kh, int ax, int ay,
+                 int iterations, int flags, void *stream);
+
+/* ---- connected components ------------------------------------------------------------------ */
+/* cv2.connectedComponentsWithStats(mask, connectivity=8, CV_32S) (also replaces the
+ * findContours(EXTERNAL)+boundingRect bar test at S:1403-1404).
+ *   labels     : optional int32 image (same width/height/batch; row_stride in bytes), may be NULL
+ *   n_labels   : int32[batch]   number of labels including background
+ *   stats      : int32[batch][max_labels][5]  = left, top, width, height, area  (row 0 = background)
+ *   centroids  : double[batch][max_labels][2] = mean x, mean y
+ * Component numbering is cv2's: raster order of the first 2x2 block touching each component.
+ * If an image has more than max_labels labels, n_labels is set to -(required) for that image and
+ * only the first max_labels rows are written. */
+int synseg_ccl_stats(synseg_ctx *ctx, const synseg_img *mask, const synseg_img *labels, int32_t *n_labels,
+                     int32_t *stats, double *centroids, int32_t max_labels, void *stream);
+
+/* ---- reductions ---------------------------------------------------------------------------- */
+/* Exact integer moments of 8-bit regions: out[i] = {sum, sum of squares, count of non-zero} (uint64 x 3)
+ * for each of n_rois regions.  Replaces np.sum(x > 0) (S:1371,1376,1439,1560,1561,1616) and np.var
+ * (S:1805,2989,3073; O:1007: var = (n*ss - s*s)/n^2).  rois is a DEVICE array; NULL = whole images.
+ * src_kind 0: 8-bit grey image; 1: RGB image reduced through PIL grey; 2: RGB through cv2 grey. */
+int synseg_moments(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois,
+                   uint64_t *out, void *stream);
+
+/* Dominant-colour front end (S:1571-1578): cv2 RGB2HSV S/V + mask S>30 & V>40 & V<240.
+ *   count    : uint64[n_rois]  masked-pixel count (the `< 100 -> []` decision, S:1577)
+ *   hist     : uint32[n_rois][4096] histogram of (R>>4, G>>4, B>>4) over masked pixels, may be NULL
+ *   chan_sum : uint64[n_rois][4096][3] exact per-bin channel sums, may be NULL
+ *   row_count: uint32[n_rois][max_rows] masked pixels per region row (for ordered sampling), may be NULL */
+int synseg_hsv_mask_hist(synseg_ctx *ctx, const synseg_img *rgb, const synseg_roi *rois, int32_t n_rois,
+                         uint64_t *count, uint32_t *hist, uint64_t *chan_sum, uint32_t *row_count, int32_t max_rows,
+                         void *stream);
+/* Gather the RGB of the k-th masked pixel (raster order, as numpy's img[mask]) for each rank in
+ * `ranks` (device int64[n]); row_prefix is the exclusive prefix sum of row_count for that region. */
+int synseg_hsv_mask_gather(synseg_ctx *ctx, const synseg_img *rgb, const synseg_roi *roi_host, const uint64_t *row_prefix,
+                           const int64_t *ranks, int32_t n, uint8_t *out_rgb, void *stream);
+
+/* ---- perceptual hash ----------------------------------------------------------------------- */
+/* 64-bit DCT perceptual hash of each region (PIL grey -> 32x32 cell means -> integer DCT-II ->
+ * 8x8 low frequencies -> median bits), exact integer arithmetic (oracle/synseg_oracle.c:orc_phash).
+ * Not in the reference (it has only md5(png)[:8], S:3782); SURVEY.md 8a B8.  src_kind as synseg_moments. */
+int synseg_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois,
+                 uint64_t *out, void *stream);
+/* Replicated duplicate removal after the all-gather: keep[i] = 0 iff some j with key[j] < key[i] has
+ * popcount(hash[i]^hash[j]) <= max_hamming. */
+int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t *hashes, const uint64_t *keys, int32_t n, int32_t max_hamming,
+                       uint8_t *keep, void *stream);
+
+/* ---- fused page pipeline ------------------------------------------------------------------- */
+typedef struct synseg_detect_params {
+    int32_t block_size;   /* adaptive threshold window (odd) : (dpi/6)|1      -> 51 @300 DPI */
+    int32_t C;            /* adaptive threshold offset       : 10                              */
+    int32_t canny_lo;     /* 50  (S:1324) */
+    int32_t canny_hi;     /* 150 (S:1324) */
+    int32_t k;            /* dilate / close square size     : int(10*dpi/72)|1 -> 41 @300 DPI */
+    int32_t max_labels;   /* capacity of stats / centroids per page */
+} synseg_detect_params;
+
+/* rgb pages -> component boxes:  grey(cv2) -> adaptive(INV) | Canny -> dilate(k) -> close(k) -> CCL(8)+stats.
+ * Same outputs as synseg_ccl_stats (labels omitted).  Bit-exact with the cv2 chain of SURVEY.md 8(d).
+ * gray_out may be NULL; if given it receives the cv2 grey pages (kept for downstream features). */
+int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *params,
+                        const synseg_img *gray_out, int32_t *n_labels, int32_t *stats, double *centroids, void *stream);
+
+/* Per-crop grid-line counts of _detect_grid (S:1546-1564) / _detect_chart_subtype (S:1365-1376):
+ * grey (gray_mode) -> Canny(50,150) -> OPEN(kw x 1, it=2) and OPEN(1 x kh, it=2) -> non-zero counts.
+ *   out : uint64[n_rois][3] = {h_count, v_count, edge pixel count}
+ * kw/kh <= 0 select the chart rule max(20, W/20) / max(20, H/20) per region.
+ * edges_out (optional) receives each region's Canny map in a caller buffer of batch=n_rois images
+ * of edges_out->width x height (regions larger than that are an error). */
+int synseg_grid_counts(synseg_ctx *ctx, const synseg_img *rgb_or_gray, int channels, int gray_mode,
+                       const synseg_roi *rois_host, int32_t n_rois, int kw, int kh, uint64_t *out,
+                       const synseg_img *edges_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNSEG_H */

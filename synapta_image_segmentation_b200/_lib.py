@@ -1,0 +1,79 @@
+"""ctypes binding of libsynseg.so (include/synseg.h).  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsynseg.so")
+
+
+class Img(C.Structure):
+    """synseg_img"""
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int64),
+                ("batch", C.c_int32), ("_pad", C.c_int32), ("batch_stride", C.c_int64)]
+
+
+class Roi(C.Structure):
+    """synseg_roi"""
+    _fields_ = [("image", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class DetectParams(C.Structure):
+    """synseg_detect_params"""
+    _fields_ = [("block_size", C.c_int32), ("C", C.c_int32), ("canny_lo", C.c_int32), ("canny_hi", C.c_int32),
+                ("k", C.c_int32), ("max_labels", C.c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/synseg.h declaration by declaration
+_P = C.POINTER
+SIGNATURES = {
+    "synseg_version": (C.c_int, []),
+    "synseg_last_error": (C.c_char_p, []),
+    "synseg_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
+    "synseg_destroy": (C.c_int, [C.c_void_p]),
+    "synseg_reserve": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "synseg_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "synseg_launch_count": (C.c_int64, [C.c_void_p]),
+    "synseg_rgb2gray": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_void_p]),
+    "synseg_adaptive_mean": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "synseg_canny": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_int, C.c_void_p]),
+    "synseg_morph": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "synseg_ccl_stats": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "synseg_moments": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "synseg_hsv_mask_hist": (C.c_int, [C.c_void_p, _P(Img), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "synseg_hsv_mask_gather": (C.c_int, [C.c_void_p, _P(Img), _P(Roi), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "synseg_phash": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "synseg_phash_dedup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "synseg_detect_pages": (C.c_int, [C.c_void_p, _P(Img), _P(DetectParams), _P(Img), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),
+}
+
+_lib = None
+
+
+class SynsegError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libsynseg.so.  Raises if it has not been built: the CUDA library IS the product."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m synapta_image_segmentation_b200.build` "
+                "(there is no CPU fallback for the region-detection hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().synseg_last_error().decode("utf-8", "replace")
+        raise SynsegError(f"{what or 'libsynseg'} failed (code {rc}): {msg}")

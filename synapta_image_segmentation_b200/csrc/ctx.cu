@@ -1,0 +1,132 @@
+// ctx.cu -- context, scratch arena, error reporting.
+#include <math.h>
+#include <stdarg.h>
+
+#include "internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void synseg_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int synseg_check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    synseg_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return SYNSEG_E_CUDA;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_version(void) { return SYNSEG_VERSION; }
+extern "C" SYNSEG_EXPORT const char *synseg_last_error(void) { return g_err; }
+
+extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
+{
+    if (!out) { synseg_set_error("synseg_create: out is NULL"); return SYNSEG_E_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    SS_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { synseg_set_error("synseg_create: no CUDA device %d", device); return SYNSEG_E_INVALID; }
+    SS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        synseg_set_error("synseg_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                         prop.minor);
+        return SYNSEG_E_INVALID;
+    }
+    synseg_ctx *c = new synseg_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    // integer DCT basis of the perceptual hash (same formula as oracle/synseg_oracle.c:orc_phash_basis)
+    int32_t basis[8 * 32];
+    for (int u = 0; u < 8; ++u)
+        for (int x = 0; x < 32; ++x) basis[u * 32 + x] = (int32_t)lround(16384.0 * cos(M_PI * (2 * x + 1) * u / 64.0));
+    int rc = synseg_check_cuda(cudaMalloc(&c->phash_basis, sizeof(basis)), "cudaMalloc(phash basis)");
+    if (!rc) rc = synseg_check_cuda(cudaMemcpy(c->phash_basis, basis, sizeof(basis), cudaMemcpyHostToDevice), "cudaMemcpy(basis)");
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
+{
+    if (!ctx) return SYNSEG_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->phash_basis) cudaFree(ctx->phash_basis);
+    delete ctx;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int64_t synseg_launch_count(const synseg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void arena_begin(synseg_ctx *ctx) { ctx->arena_top = 0; }
+
+int arena_ensure(synseg_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->arena_bytes) return SYNSEG_OK;
+    SS_CUDA(cudaSetDevice(ctx->device));
+    SS_CUDA(cudaDeviceSynchronize());
+    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    size_t want = align_up(bytes, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->arena, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        synseg_set_error("scratch arena: cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return SYNSEG_E_NOMEM;
+    }
+    ctx->arena_bytes = want;
+    return SYNSEG_OK;
+}
+
+int arena_alloc(synseg_ctx *ctx, size_t bytes, void **out, cudaStream_t)
+{
+    size_t off = align_up(ctx->arena_top, 256);
+    if (off + bytes > ctx->arena_bytes) {
+        synseg_set_error("scratch arena overflow: need %zu, have %zu (internal sizing error)", off + bytes, ctx->arena_bytes);
+        return SYNSEG_E_NOMEM;
+    }
+    *out = ctx->arena + off;
+    ctx->arena_top = off + bytes;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_reserve(synseg_ctx *ctx, size_t bytes)
+{
+    if (!ctx) { synseg_set_error("synseg_reserve: ctx is NULL"); return SYNSEG_E_INVALID; }
+    return arena_ensure(ctx, bytes);
+}
+
+// Upper bound of the scratch any single public call needs for a batch of width x height images:
+// class map (1 B/px) + grey (1 B/px) + 2x2-block labels (1 B/px) + a few bit planes + accumulators.
+extern "C" SYNSEG_EXPORT size_t synseg_scratch_bytes(int32_t width, int32_t height, int32_t batch)
+{
+    size_t px = (size_t)align_up((size_t)width, 128) * (size_t)(height + 2);
+    size_t per = 4 * px + 8 * ((size_t)bit_wpr(width) * 4 * height) + ((size_t)1 << 16);
+    return per * (size_t)batch + ((size_t)8 << 20);
+}
+
+int validate_img(const synseg_img *im, const char *name, int channels)
+{
+    if (!im || !im->data) { synseg_set_error("%s: image is NULL", name); return SYNSEG_E_INVALID; }
+    if (im->width <= 0 || im->height <= 0 || im->batch <= 0) {
+        synseg_set_error("%s: bad shape %d x %d x %d", name, im->batch, im->height, im->width);
+        return SYNSEG_E_INVALID;
+    }
+    if (im->row_stride < (int64_t)im->width * channels) {
+        synseg_set_error("%s: row_stride %lld < %d bytes per row", name, (long long)im->row_stride, im->width * channels);
+        return SYNSEG_E_INVALID;
+    }
+    if (im->batch > 1 && im->batch_stride < im->row_stride * (int64_t)im->height) {
+        synseg_set_error("%s: batch_stride %lld too small", name, (long long)im->batch_stride);
+        return SYNSEG_E_INVALID;
+    }
+    return SYNSEG_OK;
+}

@@ -1,0 +1,146 @@
+// internal.cuh -- shared declarations for libsynseg.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/synseg.h"
+
+#define SYNSEG_EXPORT __attribute__((visibility("default")))
+
+#ifndef __CUDA_ARCH__
+#define SYNSEG_HOST 1
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct synseg_ctx {
+    int device;
+    int sm_count;
+    uint8_t *arena;       // scratch arena (device)
+    size_t arena_bytes;
+    size_t arena_top;     // bump pointer, reset at the start of every public call
+    int64_t launches;     // kernels launched through this context
+    int32_t *phash_basis; // device int32[8*32]
+};
+
+void synseg_set_error(const char *fmt, ...);
+int synseg_check_cuda(cudaError_t e, const char *what);
+
+#define SS_CUDA(call)                                                    \
+    do {                                                                 \
+        int _rc = synseg_check_cuda((call), #call);                      \
+        if (_rc) return _rc;                                             \
+    } while (0)
+
+#define SS_TRY(call)                 \
+    do {                             \
+        int _rc = (call);            \
+        if (_rc) return _rc;         \
+    } while (0)
+
+#define SS_LAUNCH_CHECK(ctx)                                             \
+    do {                                                                 \
+        (ctx)->launches++;                                               \
+        int _rc = synseg_check_cuda(cudaGetLastError(), "kernel launch"); \
+        if (_rc) return _rc;                                             \
+    } while (0)
+
+// Scratch arena: bump allocation, 256-byte aligned.  arena_begin() at the start of a public call.
+void arena_begin(synseg_ctx *ctx);
+int arena_alloc(synseg_ctx *ctx, size_t bytes, void **out, cudaStream_t stream);
+static inline size_t arena_mark(const synseg_ctx *ctx) { return ctx->arena_top; }
+static inline void arena_release(synseg_ctx *ctx, size_t mark) { ctx->arena_top = mark; }
+// Grows the arena to hold `bytes` in total (synchronises the device when it has to reallocate).
+int arena_ensure(synseg_ctx *ctx, size_t bytes);
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+int validate_img(const synseg_img *im, const char *name, int channels);
+static inline bool same_shape(const synseg_img *a, const synseg_img *b)
+{
+    return a->width == b->width && a->height == b->height && a->batch == b->batch;
+}
+
+// A plane view used by kernels (by value).
+struct Plane {
+    uint8_t *p;
+    int64_t rs;  // row stride (bytes)
+    int64_t bs;  // batch stride (bytes)
+};
+static inline Plane plane_of(const synseg_img *im) { return Plane{(uint8_t *)im->data, im->row_stride, im->batch_stride}; }
+static inline bool plane_aligned(const synseg_img *im, int a)
+{
+    return (((uintptr_t)im->data | (uintptr_t)im->row_stride | (uintptr_t)(im->batch > 1 ? im->batch_stride : 0)) % a) == 0;
+}
+
+// Bit-packed masks: one bit per pixel, LSB = leftmost pixel, `wpr` 32-bit words per row
+// (multiple of 4 so rows are 16-byte aligned), bits at x >= width are always 0.
+struct BitPlane {
+    uint32_t *p;
+    int wpr;        // words per row
+    int64_t bs;     // words per image
+};
+static inline int bit_wpr(int width) { return (int)align_up((size_t)cdiv(width, 32), 4); }
+
+// ------------------------------------------------------------------------------------------------
+// internal launchers (one per .cu file)
+// ------------------------------------------------------------------------------------------------
+int launch_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, int mode, cudaStream_t st);
+
+int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *out_u8, BitPlane out_bits,
+                         int block_size, int C, int invert, cudaStream_t st);
+
+// Canny stage 1: grey -> class map (0 suppressed, 1 weak, 2 strong), u8 plane with W x H x batch.
+int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *cls, int lo, int hi, cudaStream_t st);
+// Full Canny.  Exactly one of edges_u8 / edges_bits receives the result (the other NULL / {nullptr}).
+// or_bits: when edges_bits is given, OR into it instead of overwriting.
+int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
+              int lo, int hi, cudaStream_t st);
+
+// bit packing
+int launch_pack_bits(synseg_ctx *ctx, const synseg_img *src, BitPlane dst, cudaStream_t st);
+int launch_unpack_bits(synseg_ctx *ctx, BitPlane src, const synseg_img *dst, cudaStream_t st);
+int launch_count_bits(synseg_ctx *ctx, BitPlane src, int width, int height, int batch, uint64_t *out, int out_stride,
+                      cudaStream_t st);
+
+// 1-D rect morphology passes on bit planes. op 0 erode, 1 dilate. Window for output i is
+// [i - anchor, i - anchor + k - 1] clipped to the image.
+int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, int height, int batch, int op, int k,
+                      int anchor, cudaStream_t st);
+int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, int height, int batch, int op, int k,
+                      int anchor, cudaStream_t st);
+// Generic 8-bit 1-D passes.
+int launch_morph_u8_h(synseg_ctx *ctx, const synseg_img *src, const synseg_img *dst, int op, int k, int anchor,
+                      cudaStream_t st);
+int launch_morph_u8_v(synseg_ctx *ctx, const synseg_img *src, const synseg_img *dst, int op, int k, int anchor,
+                      cudaStream_t st);
+// Whole rect op (erode/dilate/open/close with iterations folded) on bit planes.
+// The result is left in `cur` (the two planes are swapped as passes ping-pong).
+int run_bitmorph(synseg_ctx *ctx, BitPlane &cur, BitPlane &other, int width, int height, int batch, int op, int kw, int kh,
+                 int ax, int ay, int iterations, cudaStream_t st);
+
+// Connected components.  Mask given either as u8 plane (non-zero = foreground) or bit plane.
+struct CclMask {
+    const synseg_img *u8;  // or NULL
+    BitPlane bits;         // used when u8 == NULL
+    int width, height, batch;
+};
+// Block union-find core: fills blk_labels (int32 per 2x2 block, [batch][bh][bw]) with the root block
+// index of every block (fully compressed); background blocks hold -1.
+int run_ccl_core(synseg_ctx *ctx, const CclMask &m, int32_t *blk_labels, cudaStream_t st);
+int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, int32_t *n_labels, int32_t *stats,
+                  double *centroids, int32_t max_labels, cudaStream_t st);
+// Hysteresis: keep pixels of cls (non-zero) whose component holds a class-2 pixel.
+int run_hysteresis(synseg_ctx *ctx, const synseg_img *cls, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
+                   cudaStream_t st);
+
+size_t ccl_label_scratch_bytes(int width, int height, int batch);
+size_t canny_scratch_bytes(int width, int height, int batch);
+size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels);
+
+int launch_moments(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois,
+                   uint64_t *out, cudaStream_t st);

@@ -1,0 +1,145 @@
+// phash.cu -- 64-bit DCT perceptual hash per region + replicated Hamming dedup.
+//
+// Not in the reference: its only hash is md5(png bytes)[:8] used as a segment id
+// (pdf_image_segmentation.py:3782) and id-dedup (:3886-3887).  This is the north-star's cross-page
+// duplicate-figure key.  Defined in exact integer arithmetic so that the GPU,
+// the C oracle (oracle/synseg_oracle.c:orc_phash) and every rank agree bit for bit:
+//   grey -> 32x32 cell means q = (256*sum + cnt/2)/cnt -> F = C q C^T with C[u][x] =
+//   lround(16384 cos(pi (2x+1) u / 64)), u < 8 -> bit k = 2 F[k] > (sorted[31] + sorted[32]).
+// One CTA per region; every pixel is read once, coalesced (thread per column, 32 row groups).
+#include "internal.cuh"
+#include "pixel.cuh"
+
+namespace {
+
+constexpr int PH_MAXW = 8192;
+
+__global__ void __launch_bounds__(256) phash_kernel(Plane src, int width, int height, int src_kind, const synseg_roi *rois,
+                                                    const int32_t *basis, unsigned long long *out)
+{
+    __shared__ uint32_t colsum[PH_MAXW];
+    __shared__ int32_t q[32][33];
+    __shared__ long long T[8][33];
+    __shared__ long long F[64];
+    __shared__ int32_t cb[8 * 32];
+    __shared__ long long med2;
+    __shared__ unsigned int hbits[2];
+
+    synseg_roi r;
+    if (rois) r = rois[blockIdx.x];
+    else { r.image = blockIdx.x; r.x = 0; r.y = 0; r.width = width; r.height = height; }
+    const int tid = threadIdx.x;
+    cb[tid] = basis[tid];
+    if (tid == 0) med2 = 0;
+    const uint8_t *base = src.p + r.image * src.bs;
+    const int w = r.width, h = r.height;
+
+    for (int i = 0; i < 32; ++i) {
+        int y0 = (int)((long long)i * h / 32), y1 = (int)((long long)(i + 1) * h / 32);
+        if (y1 <= y0) y1 = y0 + 1;
+        for (int x = tid; x < w; x += 256) {
+            uint32_t s = 0;
+            for (int y = y0; y < y1; ++y) {
+                const uint8_t *row = base + (int64_t)(r.y + y) * src.rs;
+                uint32_t v;
+                if (src_kind == 0) v = __ldg(row + r.x + x);
+                else {
+                    const uint8_t *p = row + 3 * (int64_t)(r.x + x);
+                    const uint32_t rgbx = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+                    v = gray_dyn(rgbx, src_kind == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV);
+                }
+                s += v;
+            }
+            colsum[x] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int j = tid;
+            int x0 = (int)((long long)j * w / 32), x1 = (int)((long long)(j + 1) * w / 32);
+            if (x1 <= x0) x1 = x0 + 1;
+            unsigned long long s = 0;
+            for (int x = x0; x < x1; ++x) s += colsum[x];
+            const unsigned long long c = (unsigned long long)(y1 - y0) * (unsigned long long)(x1 - x0);
+            q[i][j] = (int32_t)((256ull * s + c / 2) / c);
+        }
+        __syncthreads();
+    }
+    // T[v][y] = sum_x C[v][x] q[y][x]
+    {
+        const int v = tid >> 5, y = tid & 31;
+        long long acc = 0;
+#pragma unroll
+        for (int x = 0; x < 32; ++x) acc += (long long)cb[v * 32 + x] * q[y][x];
+        T[v][y] = acc;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const int u = tid >> 3, v = tid & 7;
+        long long acc = 0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) acc += (long long)cb[u * 32 + y] * T[v][y];
+        F[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const long long f = F[tid];
+        int rank = 0;
+        for (int m = 0; m < 64; ++m) { const long long g = F[m]; rank += (g < f) || (g == f && m < tid); }
+        if (rank == 31 || rank == 32) atomicAdd((unsigned long long *)&med2, (unsigned long long)f);
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const bool bit = 2 * F[tid] > med2;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        if ((tid & 31) == 0) hbits[tid >> 5] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // bit k of the hash (MSB first) is coefficient k; ballot bit l of word wv is coefficient 32*wv + l
+        const unsigned long long hi = __brev(hbits[0]), lo = __brev(hbits[1]);
+        out[blockIdx.x] = (hi << 32) | lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) phash_dedup_kernel(const unsigned long long *hashes, const unsigned long long *keys, int n,
+                                                          int max_hamming, uint8_t *keep)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long h = hashes[i], k = keys[i];
+    uint8_t kp = 1;
+    for (int j = 0; j < n; ++j) {
+        if (keys[j] < k && __popcll(hashes[j] ^ h) <= max_hamming) { kp = 0; break; }
+    }
+    keep[i] = kp;
+}
+
+}  // namespace
+
+extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois, uint64_t *out,
+                            void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_phash: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (src_kind < 0 || src_kind > 2) { synseg_set_error("synseg_phash: bad src_kind %d", src_kind); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
+    if (!out) { synseg_set_error("synseg_phash: out is NULL"); return SYNSEG_E_INVALID; }
+    if (!rois) n_rois = src->batch;
+    if (n_rois <= 0) return SYNSEG_OK;
+    if (src->width > PH_MAXW) { synseg_set_error("synseg_phash: width > %d", PH_MAXW); return SYNSEG_E_INVALID; }
+    phash_kernel<<<n_rois, 256, 0, (cudaStream_t)stream>>>(plane_of(src), src->width, src->height, src_kind, rois, ctx->phash_basis,
+                                                           (unsigned long long *)out);
+    SS_LAUNCH_CHECK(ctx);
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t *hashes, const uint64_t *keys, int32_t n, int32_t max_hamming,
+                                  uint8_t *keep, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_phash_dedup: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (n <= 0) return SYNSEG_OK;
+    if (!hashes || !keys || !keep) { synseg_set_error("synseg_phash_dedup: NULL buffer"); return SYNSEG_E_INVALID; }
+    phash_dedup_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)hashes,
+                                                                       (const unsigned long long *)keys, n, max_hamming, keep);
+    SS_LAUNCH_CHECK(ctx);
+    return SYNSEG_OK;
+}

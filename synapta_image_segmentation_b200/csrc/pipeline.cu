@@ -1,0 +1,161 @@
+// pipeline.cu -- the fused page pipeline and the per-crop grid-line pipeline.
+//
+// synseg_detect_pages: RGB pages -> component boxes, bit-exact with the cv2 chain of SURVEY.md 8(d)
+//   grey(cv2) -> adaptiveThreshold(MEAN_C, BINARY_INV, bs, C) | Canny(lo,hi) -> dilate(k x k)
+//   -> morphologyEx(CLOSE, k x k) -> connectedComponentsWithStats(8).
+// It is the raster replacement for the inside of _detect_visual_regions / _detect_by_drawings
+// (pdf_image_segmentation.py:3105-3146, 3511-3557): the boxes it returns play the role of the
+// drawing-command rectangles and are filtered / merged on the host with the reference's own rules.
+//
+// HBM plan per page: the RGB page is read once (3 B/px) and the grey page written once (1 B/px);
+// every mask after that is a bit plane (1/8 B/px): the adaptive threshold writes bits directly, the
+// Canny hysteresis ORs its result into the same plane, the dilate (folded with the close's dilate into
+// one (2k-1) pass) and the erode run on bit planes, and the labelling reads bits.  Intermediates are
+// sized so that a sub-batch stays in the 126 MB L2.
+//
+// synseg_grid_counts: per crop, grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2)
+//   -> non-zero counts, i.e. _detect_grid (pdf_image_segmentation.py:1546-1564) and the visual part of
+//   _detect_chart_subtype (:1365-1376); the Canny map can be handed back for the host-side consumers
+//   (HoughLinesP :1327,1387,1701 and findContours :1762).
+#include "internal.cuh"
+
+static size_t detect_scratch_bytes(int W, int H, int B, int max_labels, bool need_gray)
+{
+    const size_t gray = need_gray ? (size_t)align_up((size_t)W, 16) * H * B + 256 : 0;
+    const size_t bits = 2 * ((size_t)bit_wpr(W) * H * B * 4 + 256);
+    const size_t canny = canny_scratch_bytes(W, H, B) + 512;
+    const size_t ccl = ccl_stats_scratch_bytes(W, H, B, max_labels) + 4096;
+    return gray + bits + (canny > ccl ? canny : ccl) + 4096;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
+                                   int32_t *n_labels, int32_t *stats, double *centroids, void *stream)
+{
+    if (!ctx || !prm) { synseg_set_error("synseg_detect_pages: NULL ctx/params"); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(rgb, "rgb", 3));
+    if (gray_out) {
+        SS_TRY(validate_img(gray_out, "gray_out", 1));
+        if (!same_shape(rgb, gray_out)) { synseg_set_error("synseg_detect_pages: gray_out shape mismatch"); return SYNSEG_E_INVALID; }
+    }
+    if (!n_labels || !stats || !centroids) { synseg_set_error("synseg_detect_pages: NULL result buffer"); return SYNSEG_E_INVALID; }
+    if (prm->block_size < 3 || prm->block_size > 255 || !(prm->block_size & 1) || prm->k < 1 || prm->max_labels < 1 || prm->canny_lo < 0 ||
+        prm->canny_hi < prm->canny_lo) {
+        synseg_set_error("synseg_detect_pages: bad parameters"); return SYNSEG_E_INVALID;
+    }
+    const int W = rgb->width, H = rgb->height, B = rgb->batch;
+    if (W > 32766 || H > 32766 || B > 65535) { synseg_set_error("synseg_detect_pages: image or batch too large"); return SYNSEG_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(W, H, B, prm->max_labels, gray_out == nullptr)));
+    arena_begin(ctx);
+    void *p;
+    synseg_img gray;
+    if (gray_out) gray = *gray_out;
+    else {
+        gray = *rgb;
+        gray.row_stride = (int64_t)align_up((size_t)W, 16);
+        gray.batch_stride = gray.row_stride * H;
+        SS_TRY(arena_alloc(ctx, (size_t)gray.batch_stride * B, &p, st));
+        gray.data = p;
+    }
+    const int wpr = bit_wpr(W);
+    const size_t plane_bytes = (size_t)wpr * H * B * 4;
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane cur{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane other{(uint32_t *)p, wpr, (int64_t)wpr * H};
+
+    SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
+    SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
+    const size_t mark = arena_mark(ctx);
+    SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
+    arena_release(ctx, mark);
+    // dilate(k) then close(k) = dilate(k), dilate(k), erode(k) = dilate(2k-1, anchor 2*(k/2)), erode(k)
+    const int k = prm->k;
+    SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_DILATE, k, k, k / 2, k / 2, 2, st));
+    SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_ERODE, k, k, k / 2, k / 2, 1, st));
+    CclMask m; m.u8 = nullptr; m.bits = cur; m.width = W; m.height = H; m.batch = B;
+    return run_ccl_stats(ctx, m, nullptr, n_labels, stats, centroids, prm->max_labels, st);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_grid_counts(synseg_ctx *ctx, const synseg_img *src, int channels, int gray_mode, const synseg_roi *rois_host,
+                                  int32_t n_rois, int kw, int kh, uint64_t *out, const synseg_img *edges_out, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_grid_counts: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (channels != 1 && channels != 3) { synseg_set_error("synseg_grid_counts: channels must be 1 or 3"); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(src, "src", channels));
+    if (!out) { synseg_set_error("synseg_grid_counts: out is NULL"); return SYNSEG_E_INVALID; }
+    if (edges_out) SS_TRY(validate_img(edges_out, "edges_out", 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    synseg_roi whole;
+    if (!rois_host) {
+        if (src->batch != 1) { synseg_set_error("synseg_grid_counts: rois required for batched sources"); return SYNSEG_E_INVALID; }
+        whole.image = 0; whole.x = 0; whole.y = 0; whole.width = src->width; whole.height = src->height;
+        rois_host = &whole; n_rois = 1;
+    }
+    if (n_rois <= 0) return SYNSEG_OK;
+    if (edges_out && edges_out->batch < n_rois) { synseg_set_error("synseg_grid_counts: edges_out batch < n_rois"); return SYNSEG_E_INVALID; }
+    // scratch for the largest region
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n_rois; ++i) {
+        const synseg_roi &r = rois_host[i];
+        if (r.image < 0 || r.image >= src->batch || r.x < 0 || r.y < 0 || r.width <= 0 || r.height <= 0 || r.x + r.width > src->width ||
+            r.y + r.height > src->height) {
+            synseg_set_error("synseg_grid_counts: region %d outside the image", i); return SYNSEG_E_INVALID;
+        }
+        if (edges_out && (r.width > edges_out->width || r.height > edges_out->height)) {
+            synseg_set_error("synseg_grid_counts: region %d larger than edges_out", i); return SYNSEG_E_INVALID;
+        }
+        if (r.width > mw) mw = r.width;
+        if (r.height > mh) mh = r.height;
+    }
+    const size_t gray_bytes = (size_t)align_up((size_t)mw, 16) * mh + 256;
+    const size_t plane_bytes = (size_t)bit_wpr(mw) * mh * 4 + 256;
+    SS_TRY(arena_ensure(ctx, gray_bytes + 3 * plane_bytes + canny_scratch_bytes(mw, mh, 1) + 8192));
+    SS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t) * 3 * (size_t)n_rois, st));
+    for (int i = 0; i < n_rois; ++i) {
+        const synseg_roi &r = rois_host[i];
+        arena_begin(ctx);
+        const int W = r.width, H = r.height;
+        synseg_img view = *src;
+        view.data = (uint8_t *)src->data + r.image * src->batch_stride + (int64_t)r.y * src->row_stride + (int64_t)r.x * channels;
+        view.width = W; view.height = H; view.batch = 1;
+        synseg_img gray = view;
+        void *p;
+        if (channels == 3) {
+            gray.row_stride = (int64_t)align_up((size_t)W, 16);
+            gray.batch_stride = gray.row_stride * H;
+            SS_TRY(arena_alloc(ctx, (size_t)gray.batch_stride, &p, st));
+            gray.data = p;
+            SS_TRY(launch_rgb2gray(ctx, &view, &gray, gray_mode, st));
+        }
+        const int wpr = bit_wpr(W);
+        const size_t pb = (size_t)wpr * H * 4;
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane edges{(uint32_t *)p, wpr, (int64_t)wpr * H};
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane a{(uint32_t *)p, wpr, (int64_t)wpr * H};
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane b{(uint32_t *)p, wpr, (int64_t)wpr * H};
+        SS_TRY(run_canny(ctx, &gray, nullptr, edges, false, 50, 150, st));
+        SS_TRY(launch_count_bits(ctx, edges, W, H, 1, out + 3 * (size_t)i + 2, 0, st));
+        if (edges_out) {
+            synseg_img eo = *edges_out;
+            eo.data = (uint8_t *)edges_out->data + (int64_t)i * edges_out->batch_stride;
+            eo.width = W; eo.height = H; eo.batch = 1;
+            SS_TRY(launch_unpack_bits(ctx, edges, &eo, st));
+        }
+        const int ekw = kw > 0 ? kw : (W / 20 > 20 ? W / 20 : 20);
+        const int ekh = kh > 0 ? kh : (H / 20 > 20 ? H / 20 : 20);
+        // horizontal lines: OPEN with (ekw x 1), iterations 2
+        SS_CUDA(cudaMemcpyAsync(a.p, edges.p, pb, cudaMemcpyDeviceToDevice, st));
+        {
+            BitPlane c = a, o = b;
+            SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, ekw, 1, ekw / 2, 0, 2, st));
+            SS_TRY(launch_count_bits(ctx, c, W, H, 1, out + 3 * (size_t)i + 0, 0, st));
+        }
+        // vertical lines: OPEN with (1 x ekh), iterations 2  (column passes ping-pong edges -> a -> b)
+        {
+            BitPlane c = edges, o = a;
+            SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, 1, ekh, 0, ekh / 2, 2, st));
+            SS_TRY(launch_count_bits(ctx, c, W, H, 1, out + 3 * (size_t)i + 1, 0, st));
+        }
+    }
+    return SYNSEG_OK;
+}

@@ -1,0 +1,142 @@
+"""Generates tests/golden/* by importing the reference in THIS container (never on the GPU box).
+
+    python tests/golden/make_golden.py
+
+* copies a handful of small real crops from /root/reference/investments_segmented (inputs only, data
+  not source) plus synthetic crops, and records what the reference's own functions return on them:
+  OCRProcessor._detect_grid / _count_arrows / _detect_shapes / _estimate_data_points / np.var /
+  mask counts (pdf_image_segmentation.py:1320-1341, 1546-1617, 1753-1810);
+* records the pure-geometry known answers of SURVEY.md Appendix D by calling
+  _calculate_overlap_ratio, _overlaps_with_existing, _drawing_distance, _cluster_drawings,
+  _detect_by_drawings and _validate_embedded_image on an uninitialised pipeline instance.
+"""
+import json
+import os
+import shutil
+import sys
+
+import cv2
+import numpy as np
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from synapta_image_segmentation_b200.synth import render_figure  # noqa: E402
+
+ref = ref_import.load()
+A2 = os.path.join(ref_import.REFERENCE_DIR, "investments_segmented")
+REAL = ["textbook_001_p020_2b1be7d6.png", "textbook_001_p022_3c6ac748.png", "textbook_001_p022_f96abaf9.png",
+        "textbook_001_p023_e2cf5878.png"]
+
+
+def helper_record(path):
+    img = Image.open(path)
+    g = np.array(img.convert("L"))
+    edges = cv2.Canny(g, 50, 150)
+    hk = cv2.getStructuringElement(cv2.MORPH_RECT, (25, 1)); vk = cv2.getStructuringElement(cv2.MORPH_RECT, (1, 25))
+    h_count = int(np.sum(cv2.morphologyEx(edges, cv2.MORPH_OPEN, hk, iterations=2) > 0))
+    v_count = int(np.sum(cv2.morphologyEx(edges, cv2.MORPH_OPEN, vk, iterations=2) > 0))
+    rec = dict(size=list(img.size), mode=img.mode,
+               detect_grid=bool(ref.OCRProcessor._detect_grid(img)),
+               count_arrows=int(ref.OCRProcessor._count_arrows(img)),
+               detect_shapes={k: int(v) for k, v in ref.OCRProcessor._detect_shapes(img).items()},
+               estimate_data_points=int(ref.OCRProcessor._estimate_data_points(img)),
+               connections=len(ref.OCRProcessor._extract_connections(img)),
+               image_subtype=ref.OCRProcessor._detect_image_subtype(img, None),
+               h_count=h_count, v_count=v_count, edge_px=int(np.sum(edges > 0)), variance=float(np.var(g)))
+    assert rec["detect_grid"] == (h_count > 300 and v_count > 300)
+    if img.mode == "RGB":
+        a = np.array(img)
+        hsv = cv2.cvtColor(a, cv2.COLOR_RGB2HSV)
+        rec["mask_px"] = int(((hsv[:, :, 1] > 30) & (hsv[:, :, 2] > 40) & (hsv[:, :, 2] < 240)).sum())
+        np.random.seed(7)
+        rec["dominant_colors_seed7"] = ref.OCRProcessor._extract_dominant_colors(img)
+    else:
+        rec["mask_px"] = 0
+        rec["dominant_colors_seed7"] = ref.OCRProcessor._extract_dominant_colors(img)
+    return rec
+
+
+def main():
+    crops = {}
+    for name in REAL:
+        shutil.copy(os.path.join(A2, name), os.path.join(HERE, name))
+        crops[name] = helper_record(os.path.join(HERE, name))
+    for i in range(4):       # synthetic crops at 150 DPI
+        fig = render_figure([99, i], 150, 500, 700)
+        name = f"synth_fig_{i}.png"
+        Image.fromarray(fig).save(os.path.join(HERE, name))
+        crops[name] = helper_record(os.path.join(HERE, name))
+
+    pl = ref_import.pipeline_instance(ref)
+    BB = ref.BoundingBox
+    geo = {}
+    geo["overlap_ratio"] = pl._calculate_overlap_ratio(BB(0, 0, 10, 10, 612, 792), BB(5, 5, 20, 20, 612, 792))
+    ex = [{"bbox": BB(0, 0, 100, 100, 612, 792)}]
+    geo["overlaps_existing"] = [bool(pl._overlaps_with_existing(BB(50, 0, 150, 100, 612, 792), ex)),
+                                bool(pl._overlaps_with_existing(BB(49, 0, 149, 100, 612, 792), ex))]
+    geo["drawing_distance"] = [pl._drawing_distance([0, 0, 10, 10], [10, 10, 20, 20]), pl._drawing_distance([0, 0, 10, 10], [13, 14, 20, 20])]
+    rects5 = [{"rect": [x, 0, x + 10, 10]} for x in (0, 60, 150, 240, 330)]
+    geo["cluster_5"] = [[d["rect"] for d in c] for c in pl._cluster_drawings(rects5, None)]
+    rng = np.random.default_rng(5)
+    rects = []
+    for _ in range(40):
+        x, y = float(rng.uniform(0, 500)), float(rng.uniform(0, 700))
+        rects.append([x, y, x + float(rng.uniform(2, 60)), y + float(rng.uniform(2, 60))])
+    geo["cluster_random_in"] = rects
+    geo["cluster_random_out"] = [[d["rect"] for d in c] for c in pl._cluster_drawings([{"rect": r} for r in rects], None)]
+
+    class FakeRect:
+        width, height = 612.0, 792.0
+
+    class FakePage:
+        rect = FakeRect()
+
+        def __init__(self, drawings):
+            self._d = drawings
+
+        def get_drawings(self):
+            return self._d
+
+    regs = pl._detect_by_drawings(FakePage([{"rect": [100 + 5 * i, 100, 110 + 5 * i, 300]} for i in range(6)]), FakeRect())
+    geo["detect_by_drawings"] = [dict(bbox=[r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1], caption=r["caption"],
+                                      detection_method=r["detection_method"], notes=r["notes"]) for r in regs]
+    regs = pl._detect_by_drawings(FakePage([{"rect": r} for r in rects]), FakeRect())
+    geo["detect_by_drawings_random"] = [dict(bbox=[r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1], notes=r["notes"]) for r in regs]
+
+    pl._find_caption_near_bbox = lambda page, bbox: None
+    noise = Image.fromarray(np.random.default_rng(1).integers(0, 256, (300, 400, 3), dtype=np.uint8))
+    flat = Image.fromarray(np.full((300, 300), 128, np.uint8))
+    small = Image.fromarray(np.random.default_rng(2).integers(0, 256, (40, 300, 3), dtype=np.uint8))
+    val = []
+    for nm, im, bb in [("noise", noise, (100, 200, 300, 350)), ("noise", noise, (100, 200, 150, 250)), ("flat", flat, (100, 20, 300, 350)),
+                       ("small", small, (100, 200, 400, 240)), ("noise", noise, (100, 750, 300, 790)), ("flat", flat, (10, 300, 600, 320))]:
+        score, notes = pl._validate_embedded_image(im, BB(*bb, 612, 792), FakePage([]))
+        val.append(dict(image=nm, bbox=list(bb), score=score, notes=notes))
+    geo["validate"] = val
+
+    class Seg:
+        def __init__(self, bbox, caption_text=None, extraction_method="embedded_image", confidence=1.0, image_path=None):
+            self.bbox, self.caption_text, self.extraction_method, self.confidence, self.image_path = bbox, caption_text, extraction_method, confidence, image_path
+    npath = os.path.join(HERE, "_tmp_noise.png"); noise.save(npath)
+    fpath = os.path.join(HERE, "_tmp_flat.png"); flat.save(fpath)
+    rc = []
+    for emb_bb, cap_bb, cap_text, conf, path in [((0, 0, 100, 100), (0, 0, 100, 130), "Figure 1", 0.9, npath),
+                                                 ((0, 0, 100, 100), (0, 0, 100, 100), None, 0.9, npath),
+                                                 ((0, 0, 200, 200), (0, 0, 100, 100), None, 0.5, fpath),
+                                                 ((0, 0, 100, 100), (0, 0, 100, 125), None, 0.71, fpath)]:
+        d, why = pl._resolve_conflict(Seg(BB(*emb_bb, 612, 792), confidence=conf, image_path=path),
+                                      Seg(BB(*cap_bb, 612, 792), caption_text=cap_text, extraction_method="rendered_region"), FakePage([]))
+        rc.append(dict(emb=list(emb_bb), cap=list(cap_bb), caption=cap_text, confidence=conf, image=os.path.basename(path)[5:-4], decision=d, reasons=why))
+    geo["resolve_conflict"] = rc
+    os.remove(npath); os.remove(fpath)
+
+    json.dump(dict(crops=crops, versions=dict(cv2=cv2.__version__, numpy=np.__version__)), open(os.path.join(HERE, "reference_helpers.json"), "w"), indent=1)
+    json.dump(geo, open(os.path.join(HERE, "reference_geometry.json"), "w"), indent=1)
+    print("wrote", len(crops), "crop records and geometry vectors")
+
+
+if __name__ == "__main__":
+    main()
