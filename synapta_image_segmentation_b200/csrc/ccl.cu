@@ -118,13 +118,14 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(MaskAcc m, CclGeom g, in
         uf_union(L, b, b - 1);
 }
 
-__global__ void __launch_bounds__(256) ccl_compress_kernel(int64_t n, int32_t *L, int64_t bper)
+__global__ void __launch_bounds__(256) ccl_compress_kernel(int64_t n, int32_t *L, int64_t bper, int nblk)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const int64_t img = i / bper;
     int32_t *Li = L + img * bper;
     const int32_t b = (int32_t)(i - img * bper);
+    if (b >= nblk) return;          // padding entries of the per-image stride are never initialised
     const int32_t v = Li[b];
     if (v >= 0 && v != b) Li[b] = uf_find(Li, v);
 }
@@ -450,7 +451,7 @@ int run_ccl_core(synseg_ctx *ctx, const CclMask &m, int32_t *L, cudaStream_t st)
     ccl_merge_kernel<<<grid, block, 0, st>>>(a, g, L);
     SS_LAUNCH_CHECK(ctx);
     const int64_t n = g.bper * m.batch;
-    ccl_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, L, g.bper);
+    ccl_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, L, g.bper, g.nblk);
     SS_LAUNCH_CHECK(ctx);
     return SYNSEG_OK;
 }
