@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- 300-DPI pages/sec -> region bboxes on B200 (BASELINE.json metric), with the CPU OpenCV path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dpi 300] [--batch 50]
+
+One "step" = one pass of the detection hot path over one batch of synthetic pages.  At N=1 the workload is
+BASELINE.json configs[2]: a 1,000-page synthetic textbook at 300 DPI on one B200 (20 steps x 50 pages).
+
+  value : whole-job pages/s with the batch already resident in HBM (device pipeline only), CUDA events.
+  e2e   : pages/s through the public API from PINNED HOST pages: H2D of every page, fused pipeline, D2H of the
+          component tables, host-side box filter/merge into region boxes -- all inside the timed region.
+  roofline : the dominant kernel of a step (per-kernel CUDA-event timing of profiled steps in this same run),
+          algorithmic bytes / its time / measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline : the cv2 chain (oracle/cv2_chain.py) on the box's host cores, bounded sample, rank 0, N=1.
+
+N>1 (torchrun, one rank per GPU): pages shard across ranks (weak scaling, no data-path collective); each step
+also hashes the candidate component boxes on the device, and after the K steps ONE NCCL all-gather of the
+(hash, key) pairs plus the replicated Hamming dedup runs inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "300-DPI pages/sec -> region bboxes"
+UNIT = "pages/s"
+
+# algorithmic bytes per pixel each kernel of the fused pipeline has to move
+ALG_BYTES_PER_PX = {
+    "rgb2gray": 4.0,            # 3 read + 1 written
+    "adaptive_mean": 1.125,     # grey read + bit plane written
+    "canny_classes": 2.0,       # grey read + class map written
+    "ccl_init": 2.0, "ccl_merge": 1.0, "ccl_compress": 2.0,   # u8 class map / block labels (1 B/px)
+    "hyst_flag": 2.0, "hyst_final": 2.25,
+    "bitmorph_h": 0.25, "bitmorph_v": 0.25,
+    "ccl_count": 1.0, "ccl_scan": 0.0, "ccl_assign": 1.0, "stats_init": 0.0, "ccl_final": 1.125, "stats_finalize": 0.0,
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dpi", type=int, default=300)
+    ap.add_argument("--batch", type=int, default=50, help="pages per step per GPU")
+    ap.add_argument("--unique", type=int, default=10, help="distinct synthetic pages the textbook is assembled from")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pages in the CPU baseline sample (0 = 8 x cores, capped)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def build_textbook(dpi: int, batch: int, unique: int, start_page: int, pin: bool):
+    """[batch,H,W,3] u8 host tensor: `unique` distinct seeded pages tiled to `batch` pages."""
+    import numpy as np
+    import torch
+    from synapta_image_segmentation_b200.synth import page_shape, synth_page
+    h, w = page_shape(dpi)
+    t = torch.empty((batch, h, w, 3), dtype=torch.uint8)
+    if pin:
+        t = t.pin_memory()
+    a = t.numpy()
+    uniq = min(unique, batch)
+    for i in range(uniq):
+        a[i] = synth_page(start_page + i, dpi)[0]
+    for i in range(uniq, batch):
+        a[i] = a[i % uniq]
+    return t
+
+
+def run_reference(args):
+    """--impl reference: the CPU OpenCV chain on all host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import cpu_baseline
+    from synapta_image_segmentation_b200.synth import synth_pages
+    cores = os.cpu_count() or 1
+    per_step = max(8, cores)
+    pages = synth_pages(per_step, args.dpi, start=1000)
+    best = None
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_baseline.measure_pages(pages[:max(2, cores // 2)], args.dpi)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        r = cpu_baseline.measure_pages(pages, args.dpi)
+        vals.append(r)
+        best = r if best is None or r["value"] > best["value"] else best
+        if time.perf_counter() - t0 > 150:       # keep the whole run within a few minutes
+            break
+    value = sum(v["value"] for v in vals) / len(vals)
+    ms = 1000.0 * per_step / value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"cv2 4.13 chain gray->adaptive|canny->dilate->close->CCL+stats on synthetic {args.dpi}-DPI letter pages",
+                       "pages_per_step": per_step, "dpi": args.dpi},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per_step} pages per step x {len(vals)} steps; best arrangement: {best['arrangement']}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from synapta_image_segmentation_b200.dedup import cross_page_dedup
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    from synapta_image_segmentation_b200.ops import Context
+    from synapta_image_segmentation_b200.streaming import PageStreamer
+    from synapta_image_segmentation_b200.synth import page_shape
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = Context(local)
+    det = RasterRegionDetector(DetectConfig(dpi=args.dpi, max_labels=1024), ctx=ctx)
+    h, w = page_shape(args.dpi)
+    B, K, W_ = args.batch, args.steps, args.warmup
+    npx = h * w
+
+    host_pages = build_textbook(args.dpi, B, args.unique, start_page=rank * 10_000, pin=True)
+    pages = host_pages.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    ctx.reserve(w, h, B)
+
+    ml = det.cfg.max_labels
+    out = (torch.empty(B, dtype=torch.int32, device=dev), torch.empty((B, ml, 5), dtype=torch.int32, device=dev),
+           torch.empty((B, ml, 2), dtype=torch.float64, device=dev))
+    # device-side candidate selection + hashing (used at N>1 for the dedup exchange)
+    cap = 16 * B * max(K, 1)
+    rois = torch.empty((cap, 5), dtype=torch.int32, device=dev)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    hashes = torch.empty(cap, dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = args.dpi / 72.0
+    min_area, max_area = int(5000 * s * s), int(0.8 * npx)
+    min_ext = int(50 * s)
+
+    def step(i, with_hash):
+        det.detect_components(pages, out=out)
+        if with_hash:
+            ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with_hash = world > 1
+    for i in range(W_):
+        step(i, with_hash)
+    barrier()
+    count.zero_()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(i, with_hash)
+    n_survivors = None
+    if with_hash:
+        ctx.phash_indirect(pages, 1, rois, count, hashes)      # all candidate boxes of the K steps share `pages`
+        n_valid = int(count.item())
+        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4)
+        n_survivors = int(keep.sum().item())
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * K * B / (ms_total / 1000.0)
+
+    # ---- end to end: pinned host pages -> H2D -> pipeline -> D2H -> host box filter/merge ---------------------
+    e2e = None
+    if not args.no_e2e:
+        streamer = PageStreamer(det, B, h, w, slots=2)
+        pw, ph = w * 72.0 / args.dpi, h * 72.0 / args.dpi
+        n_regions = [0]
+
+        def on_result(i, n_h, stats_h):
+            n_np, st_np = n_h.numpy(), stats_h.numpy()
+            for j in range(n_np.shape[0]):
+                n_regions[0] += len(det.candidate_regions(st_np[j], int(n_np[j]), pw, ph))
+
+        streamer.run((host_pages for _ in range(max(1, W_ // 2))), on_result)
+        barrier()
+        streamer.h2d_bytes = streamer.d2h_bytes = 0
+        t0 = time.perf_counter()
+        streamer.run((host_pages for _ in range(K)), on_result)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        e2e = {"value": world * K * B / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // K,
+               "d2h_bytes_per_step": streamer.d2h_bytes // K, "ms_per_step": 1000.0 * dt / K,
+               "includes": "pinned H2D, fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
+        del streamer
+
+    # ---- per-kernel timing of profiled steps (same run, same stream) -> roofline of the dominant kernel -------
+    peak, peak_src = load_peak()
+    PROF_STEPS = 3
+    agg = {}
+    for _ in range(PROF_STEPS):
+        torch.cuda.synchronize()
+        ctx.profile_begin()
+        det.detect_components(pages, out=out)
+        for name, ms in ctx.profile_end():
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += ms
+            a[1] += 1
+    step_ms = sum(a[0] for a in agg.values()) / PROF_STEPS
+    kernels = {name: {"ms_per_step": a[0] / PROF_STEPS, "launches_per_step": a[1] // PROF_STEPS,
+                      "share": (a[0] / PROF_STEPS) / step_ms} for name, a in agg.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    dk = kernels[dom]
+    launch_ms = dk["ms_per_step"] / max(1, dk["launches_per_step"])
+    alg_bytes = ALG_BYTES_PER_PX.get(dom, 1.0) * npx * B
+    achieved = alg_bytes / (launch_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms": launch_ms, "share_of_step": dk["share"],
+                "page_level": {"algorithmic_bytes_per_page": 19.0 * npx, "achieved": 19.0 * npx * B / (step_ms / 1000.0) / 1e9,
+                               "frac": 19.0 * npx * B / (step_ms / 1000.0) / 1e9 / peak},
+                "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "share": round(v["share"], 4),
+                                "launches": v["launches_per_step"],
+                                "GBps": round(ALG_BYTES_PER_PX.get(k, 0.0) * npx * B / max(v["ms_per_step"] / max(1, v["launches_per_step"]), 1e-9) / 1e6, 1)}
+                            for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+
+    # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_baseline
+        cores = os.cpu_count() or 1
+        n_s = args.cpu_sample or min(4 * cores, 96)
+        sample = host_pages.numpy()[:min(n_s, B)]
+        if n_s > B:
+            sample = np.concatenate([sample] * ((n_s + B - 1) // B))[:n_s]
+        r = cpu_baseline.measure_pages(sample, args.dpi)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['pages']} pages of the same textbook through the cv2 4.13 chain (oracle/cv2_chain.py); {r['arrangement']}; "
+                         f"other arrangement: {r['other']:.1f} pages/s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{K * B}-page synthetic textbook at {args.dpi} DPI ({w}x{h} RGB) per GPU, {B} pages per step, "
+                                       f"assembled from {min(args.unique, B)} unique seeded pages",
+                           "pages_per_step_per_gpu": B, "dpi": args.dpi, "parallelism": f"pages sharded over {world} GPU(s)",
+                           "l2": f"inputs larger than L2: {B * npx * 3 / 1e6:.0f} MB RGB per step vs 126 MB L2",
+                           "chain": "gray(cv2) -> adaptive(51,10,INV)|Canny(50,150) -> dilate(k) -> close(k) -> CCL8+stats" if args.dpi == 300 else "see DetectConfig"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if n_survivors is not None:
+            line["dedup"] = {"regions_hashed": int(k_all.numel()), "survivors": n_survivors, "collective": "nccl all_gather_into_tensor"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,12 @@ size_t synseg_scratch_bytes(int32_t width, int32_t height, int32_t batch);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t synseg_launch_count(const synseg_ctx *ctx);
 
+/* Per-kernel device timing for bench.py: begin records a start event on `stream`; every kernel the
+ * library launches afterwards is followed by an event; end returns (kernel name, milliseconds) pairs in
+ * launch order (value = number of launches, <0 on error). */
+int synseg_profile_begin(synseg_ctx *ctx, void *stream);
+int synseg_profile_end(synseg_ctx *ctx, const char **names, float *ms, int cap);
+
 /* ---- colour -------------------------------------------------------------------------------- */
 /* RGB -> grey.  mode 0: cv2.cvtColor(COLOR_RGB2GRAY) 15-bit fixed point (S:1348);
  *               mode 1: PIL Image.convert('L') 16-bit fixed point (S:1323,1549,1599,1699,1758,1804,2988,3072). */
@@ -156,6 +162,20 @@ typedef struct synseg_detect_params {
  * gray_out may be NULL; if given it receives the cv2 grey pages (kept for downstream features). */
 int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *params,
                         const synseg_img *gray_out, int32_t *n_labels, int32_t *stats, double *centroids, void *stream);
+
+/* Device-side selection of candidate component boxes for hashing (no host round trip): for every image,
+ * every component k >= 1 of `stats` (as written by synseg_detect_pages / synseg_ccl_stats) with
+ * min_area <= w*h <= max_area, w >= min_w, h >= min_h is appended to rois[] (image, x, y, w, h) and
+ * keys[] ((page_base + image) << 16 | k).  count: device int32 (must be zeroed by the caller before the
+ * first call; appends are cumulative, capped at capacity).  Order inside rois[] is unspecified; keys
+ * identify the entries. */
+int synseg_select_rois(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t batch, int32_t max_labels,
+                       int64_t page_base, int32_t min_area, int32_t max_area, int32_t min_w, int32_t min_h,
+                       synseg_roi *rois, uint64_t *keys, int32_t *count, int32_t capacity, void *stream);
+/* synseg_phash over a device-resident roi list whose length lives in device memory (`count`, capped at
+ * capacity): hashes[i] for i < *count. */
+int synseg_phash_indirect(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, const int32_t *count,
+                          int32_t capacity, uint64_t *out, void *stream);
 
 /* Per-crop grid-line counts of _detect_grid (S:1546-1564) / _detect_chart_subtype (S:1365-1376):
  * grey (gray_mode) -> Canny(50,150) -> OPEN(kw x 1, it=2) and OPEN(1 x kh, it=2) -> non-zero counts.

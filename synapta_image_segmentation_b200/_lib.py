@@ -35,6 +35,11 @@ SIGNATURES = {
     "synseg_reserve": (C.c_int, [C.c_void_p, C.c_size_t]),
     "synseg_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "synseg_launch_count": (C.c_int64, [C.c_void_p]),
+    "synseg_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "synseg_profile_end": (C.c_int, [C.c_void_p, _P(C.c_char_p), _P(C.c_float), C.c_int]),
+    "synseg_select_rois": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "synseg_phash_indirect": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "synseg_rgb2gray": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_void_p]),
     "synseg_adaptive_mean": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "synseg_canny": (C.c_int, [C.c_void_p, _P(Img), _P(Img), C.c_int, C.c_int, C.c_void_p]),

@@ -92,7 +92,7 @@ int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
 {
     dim3 grid(cdiv(gray->width, TW), cdiv(gray->height, TH), gray->batch);
     canny_classes_kernel<<<grid, 256, 0, st>>>(plane_of(gray), plane_of(cls), gray->width, gray->height, lo, hi);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "canny_classes", st);
     return SYNSEG_OK;
 }
 

@@ -447,12 +447,12 @@ int run_ccl_core(synseg_ctx *ctx, const CclMask &m, int32_t *L, cudaStream_t st)
     const CclGeom g = geom_of(m.width, m.height);
     dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), m.batch);
     ccl_init_kernel<<<grid, block, 0, st>>>(a, g, L);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_init", st);
     ccl_merge_kernel<<<grid, block, 0, st>>>(a, g, L);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
     const int64_t n = g.bper * m.batch;
     ccl_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, L, g.bper, g.nblk);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_compress", st);
     return SYNSEG_OK;
 }
 
@@ -482,20 +482,20 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
 
     SS_TRY(run_ccl_core(ctx, m, L, st));
     ccl_count_kernel<<<dim3(nchunks, batch), 256, 0, st>>>(L, g.bper, g.nblk, nchunks, chunk_cnt);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_count", st);
     ccl_scan_kernel<<<batch, 256, 0, st>>>(nchunks, chunk_cnt, n_roots);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_scan", st);
     ccl_assign_kernel<<<dim3(nchunks, batch), 256, 0, st>>>(L, g.bper, g.nblk, nchunks, chunk_cnt);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_assign", st);
     stats_init_kernel<<<(unsigned)cdiv(nacc, 256), 256, 0, st>>>(a, (int64_t)nacc);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "stats_init", st);
     const MaskAcc ma = mask_acc(m);
     dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), batch);
     if (labels) ccl_final_kernel<true><<<grid, block, 0, st>>>(ma, g, L, plane_of(labels), a);
     else ccl_final_kernel<false><<<grid, block, 0, st>>>(ma, g, L, Plane{nullptr, 0, 0}, a);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "ccl_final", st);
     stats_finalize_kernel<<<dim3(cdiv(max_labels, 128), batch), 128, 0, st>>>(a, n_roots, batch, n_labels, stats, centroids);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "stats_finalize", st);
     return SYNSEG_OK;
 }
 
@@ -516,10 +516,10 @@ int run_hysteresis(synseg_ctx *ctx, const synseg_img *cls, const synseg_img *edg
     SS_TRY(run_ccl_core(ctx, m, L, st));
     dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), m.batch);
     hyst_flag_kernel<<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "hyst_flag", st);
     if (edges_u8) hyst_final_kernel<false><<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L, plane_of(edges_u8), BitPlane{nullptr, 0, 0}, false);
     else hyst_final_kernel<true><<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L, Plane{nullptr, 0, 0}, edges_bits, or_bits);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "hyst_final", st);
     return SYNSEG_OK;
 }
 

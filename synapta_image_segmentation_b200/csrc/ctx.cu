@@ -40,7 +40,8 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
         return SYNSEG_E_INVALID;
     }
     synseg_ctx *c = new synseg_ctx();
-    memset(c, 0, sizeof(*c));
+    c->arena = nullptr; c->arena_bytes = 0; c->arena_top = 0; c->launches = 0; c->phash_basis = nullptr;
+    c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     // integer DCT basis of the perceptual hash (same formula as oracle/synseg_oracle.c:orc_phash_basis)
@@ -61,6 +62,8 @@ extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
     cudaDeviceSynchronize();
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->phash_basis) cudaFree(ctx->phash_basis);
+    if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     delete ctx;
     return SYNSEG_OK;
 }
@@ -129,4 +132,49 @@ int validate_img(const synseg_img *im, const char *name, int channels)
         return SYNSEG_E_INVALID;
     }
     return SYNSEG_OK;
+}
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+// All kernels of a call run back to back on one stream, so the time between the events recorded after
+// consecutive launches is the duration of the later kernel (plus any memset/memcpy issued in between).
+void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st)
+{
+    if (ctx->prof_used == ctx->prof_events.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->prof_events.push_back(e);
+        ctx->prof_names.push_back(name);
+    }
+    ctx->prof_names[ctx->prof_used] = name;
+    cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
+    ctx->prof_used++;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_profile_begin(synseg_ctx *ctx, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_profile_begin: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (!ctx->prof_start) SS_CUDA(cudaEventCreate(&ctx->prof_start));
+    ctx->prof_used = 0;
+    ctx->prof_on = true;
+    SS_CUDA(cudaEventRecord(ctx->prof_start, (cudaStream_t)stream));
+    return SYNSEG_OK;
+}
+
+// Stops profiling, waits for the last recorded event and returns up to `cap` (name, milliseconds) pairs in
+// launch order.  names[i] points to a static string.  Returns the number of launches recorded (may exceed cap).
+extern "C" SYNSEG_EXPORT int synseg_profile_end(synseg_ctx *ctx, const char **names, float *ms, int cap)
+{
+    if (!ctx) { synseg_set_error("synseg_profile_end: ctx is NULL"); return SYNSEG_E_INVALID; }
+    ctx->prof_on = false;
+    const int n = (int)ctx->prof_used;
+    if (n == 0) return 0;
+    SS_CUDA(cudaEventSynchronize(ctx->prof_events[n - 1]));
+    cudaEvent_t prev = ctx->prof_start;
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        SS_CUDA(cudaEventElapsedTime(&t, prev, ctx->prof_events[i]));
+        if (i < cap) { names[i] = ctx->prof_names[i]; ms[i] = t; }
+        prev = ctx->prof_events[i];
+    }
+    return n;
 }

@@ -117,7 +117,7 @@ int launch_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gr
         if (al) rgb2gray_kernel<SYNSEG_GRAY_PIL, true><<<grid, block, 0, st>>>(s, d, width, height, chunk_blocks);
         else rgb2gray_kernel<SYNSEG_GRAY_PIL, false><<<grid, block, 0, st>>>(s, d, width, height, chunk_blocks);
     }
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "rgb2gray", st);
     return SYNSEG_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/synseg.h"
 
 #define SYNSEG_EXPORT __attribute__((visibility("default")))
@@ -24,7 +26,15 @@ struct synseg_ctx {
     size_t arena_top;     // bump pointer, reset at the start of every public call
     int64_t launches;     // kernels launched through this context
     int32_t *phash_basis; // device int32[8*32]
+    // optional per-kernel timing (synseg_profile_*): one event after every launch on the profiled stream
+    bool prof_on;
+    cudaEvent_t prof_start;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<const char *> prof_names;
+    size_t prof_used;
 };
+
+void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st);
 
 void synseg_set_error(const char *fmt, ...);
 int synseg_check_cuda(cudaError_t e, const char *what);
@@ -41,11 +51,12 @@ int synseg_check_cuda(cudaError_t e, const char *what);
         if (_rc) return _rc;         \
     } while (0)
 
-#define SS_LAUNCH_CHECK(ctx)                                             \
+#define SS_LAUNCH_CHECK(ctx, name, stream)                               \
     do {                                                                 \
         (ctx)->launches++;                                               \
-        int _rc = synseg_check_cuda(cudaGetLastError(), "kernel launch"); \
+        int _rc = synseg_check_cuda(cudaGetLastError(), name);           \
         if (_rc) return _rc;                                             \
+        if ((ctx)->prof_on) prof_mark((ctx), name, (stream));            \
     } while (0)
 
 // Scratch arena: bump allocation, 256-byte aligned.  arena_begin() at the start of a public call.

@@ -322,7 +322,7 @@ int launch_pack_bits(synseg_ctx *ctx, const synseg_img *src, BitPlane dst, cudaS
     const int nw = cdiv(src->width, 32);
     const int64_t total = (int64_t)nw * src->height * src->batch;
     pack_bits_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(plane_of(src), dst, src->width, src->height, nw, total, plane_aligned(src, 16));
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "pack_bits", st);
     return SYNSEG_OK;
 }
 
@@ -331,7 +331,7 @@ int launch_unpack_bits(synseg_ctx *ctx, BitPlane src, const synseg_img *dst, cud
     const int nw = cdiv(dst->width, 32);
     const int64_t total = (int64_t)nw * dst->height * dst->batch;
     unpack_bits_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(src, plane_of(dst), dst->width, dst->height, nw, total, plane_aligned(dst, 16));
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "unpack_bits", st);
     return SYNSEG_OK;
 }
 
@@ -341,7 +341,7 @@ int launch_count_bits(synseg_ctx *ctx, BitPlane src, int width, int height, int 
     int gx = cdiv((int64_t)nw * height, 256 * 8);
     if (gx < 1) gx = 1;
     count_bits_kernel<<<dim3(gx, batch), 256, 0, st>>>(src, nw, height, (unsigned long long *)out, out_stride);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "count_bits", st);
     return SYNSEG_OK;
 }
 
@@ -359,7 +359,7 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
     const int maxg = ctx->sm_count * 8;
     if (grid > maxg) grid = maxg;
     bitmorph_h_kernel<<<grid, 256, smem, st>>>(src, dst, width, height, batch, nw, op == SYNSEG_MORPH_ERODE, k, anchor, padw);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "bitmorph_h", st);
     return SYNSEG_OK;
 }
 
@@ -373,7 +373,7 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
     if (!attr_set) { SS_CUDA(cudaFuncSetAttribute(bitmorph_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     dim3 grid(cdiv(nw, 32), cdiv(height, BV_TH), batch);
     bitmorph_v_kernel<<<grid, 32, smem, st>>>(src, dst, width, height, nw, op == SYNSEG_MORPH_ERODE, k, anchor);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
     return SYNSEG_OK;
 }
 
@@ -420,7 +420,7 @@ int launch_morph_u8_h(synseg_ctx *ctx, const synseg_img *src, const synseg_img *
         dim3 grid(cdiv(src->width, U8H_TW), cdiv(src->height, U8H_ROWS), 1);
         if (op == SYNSEG_MORPH_DILATE) morph_u8_h_kernel<true><<<grid, 32, smem, st>>>(s, d, src->width, src->height, k, anchor, pitch_w);
         else morph_u8_h_kernel<false><<<grid, 32, smem, st>>>(s, d, src->width, src->height, k, anchor, pitch_w);
-        SS_LAUNCH_CHECK(ctx);
+        SS_LAUNCH_CHECK(ctx, "morph_u8_h", st);
     }
     return SYNSEG_OK;
 }
@@ -438,7 +438,7 @@ int launch_morph_u8_v(synseg_ctx *ctx, const synseg_img *src, const synseg_img *
     dim3 grid(cdiv(src->width, 128), cdiv(src->height, U8V_TH), src->batch);
     if (op == SYNSEG_MORPH_DILATE) morph_u8_v_kernel<true><<<grid, 32, smem, st>>>(plane_of(src), plane_of(dst), src->width, src->height, k, anchor);
     else morph_u8_v_kernel<false><<<grid, 32, smem, st>>>(plane_of(src), plane_of(dst), src->width, src->height, k, anchor);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "morph_u8_v", st);
     return SYNSEG_OK;
 }
 

@@ -15,8 +15,9 @@ namespace {
 constexpr int PH_MAXW = 8192;
 
 __global__ void __launch_bounds__(256) phash_kernel(Plane src, int width, int height, int src_kind, const synseg_roi *rois,
-                                                    const int32_t *basis, unsigned long long *out)
+                                                    const int32_t *basis, unsigned long long *out, const int32_t *count)
 {
+    if (count && (int)blockIdx.x >= *count) return;
     __shared__ uint32_t colsum[PH_MAXW];
     __shared__ int32_t q[32][33];
     __shared__ long long T[8][33];
@@ -114,7 +115,57 @@ __global__ void __launch_bounds__(256) phash_dedup_kernel(const unsigned long lo
     keep[i] = kp;
 }
 
+__global__ void __launch_bounds__(256) select_rois_kernel(const int32_t *n_labels, const int32_t *stats, int batch, int max_labels,
+                                                          long long page_base, int min_area, int max_area, int min_w, int min_h,
+                                                          synseg_roi *rois, unsigned long long *keys, int32_t *count, int capacity)
+{
+    const int img = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    int n = n_labels[img];
+    if (n < 0) n = max_labels;           // over capacity: only the first max_labels rows exist
+    if (k < 1 || k >= n) return;
+    const int32_t *s = stats + ((int64_t)img * max_labels + k) * 5;
+    const int w = s[2], h = s[3];
+    const long long box = (long long)w * h;
+    if (box < min_area || box > max_area || w < min_w || h < min_h) return;
+    const int slot = atomicAdd(count, 1);
+    if (slot >= capacity) { atomicSub(count, 1); return; }
+    synseg_roi r; r.image = img; r.x = s[0]; r.y = s[1]; r.width = w; r.height = h;
+    rois[slot] = r;
+    keys[slot] = ((unsigned long long)(page_base + img) << 16) | (unsigned long long)k;
+}
+
 }  // namespace
+
+extern "C" SYNSEG_EXPORT int synseg_select_rois(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t batch,
+                                                int32_t max_labels, int64_t page_base, int32_t min_area, int32_t max_area, int32_t min_w,
+                                                int32_t min_h, synseg_roi *rois, uint64_t *keys, int32_t *count, int32_t capacity,
+                                                void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_select_rois: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (!n_labels || !stats || !rois || !keys || !count || batch <= 0 || max_labels < 1 || capacity < 1 || max_labels > 65535) {
+        synseg_set_error("synseg_select_rois: bad arguments"); return SYNSEG_E_INVALID;
+    }
+    select_rois_kernel<<<dim3(cdiv(max_labels, 256), batch), 256, 0, (cudaStream_t)stream>>>(
+        n_labels, stats, batch, max_labels, (long long)page_base, min_area, max_area, min_w, min_h, rois, (unsigned long long *)keys, count,
+        capacity);
+    SS_LAUNCH_CHECK(ctx, "select_rois", (cudaStream_t)stream);
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_phash_indirect(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois,
+                                                   const int32_t *count, int32_t capacity, uint64_t *out, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_phash_indirect: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (src_kind < 0 || src_kind > 2) { synseg_set_error("synseg_phash_indirect: bad src_kind %d", src_kind); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
+    if (!rois || !count || !out || capacity < 1) { synseg_set_error("synseg_phash_indirect: bad arguments"); return SYNSEG_E_INVALID; }
+    if (src->width > PH_MAXW) { synseg_set_error("synseg_phash_indirect: width > %d", PH_MAXW); return SYNSEG_E_INVALID; }
+    phash_kernel<<<capacity, 256, 0, (cudaStream_t)stream>>>(plane_of(src), src->width, src->height, src_kind, rois, ctx->phash_basis,
+                                                              (unsigned long long *)out, count);
+    SS_LAUNCH_CHECK(ctx, "phash", (cudaStream_t)stream);
+    return SYNSEG_OK;
+}
 
 extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois, uint64_t *out,
                             void *stream)
@@ -127,8 +178,8 @@ extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src
     if (n_rois <= 0) return SYNSEG_OK;
     if (src->width > PH_MAXW) { synseg_set_error("synseg_phash: width > %d", PH_MAXW); return SYNSEG_E_INVALID; }
     phash_kernel<<<n_rois, 256, 0, (cudaStream_t)stream>>>(plane_of(src), src->width, src->height, src_kind, rois, ctx->phash_basis,
-                                                           (unsigned long long *)out);
-    SS_LAUNCH_CHECK(ctx);
+                                                           (unsigned long long *)out, nullptr);
+    SS_LAUNCH_CHECK(ctx, "phash", (cudaStream_t)stream);
     return SYNSEG_OK;
 }
 
@@ -140,6 +191,6 @@ extern "C" SYNSEG_EXPORT int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t 
     if (!hashes || !keys || !keep) { synseg_set_error("synseg_phash_dedup: NULL buffer"); return SYNSEG_E_INVALID; }
     phash_dedup_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)hashes,
                                                                        (const unsigned long long *)keys, n, max_hamming, keep);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "phash_dedup", (cudaStream_t)stream);
     return SYNSEG_OK;
 }

@@ -178,7 +178,7 @@ int launch_moments(synseg_ctx *ctx, const synseg_img *src, int src_kind, const s
     if (gx < 1) gx = 1;
     if (gx > 1024) gx = 1024;
     moments_kernel<<<dim3(gx, n_rois), 256, 0, st>>>(plane_of(src), src->width, src->height, src_kind, rois, (unsigned long long *)out);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "moments", st);
     return SYNSEG_OK;
 }
 
@@ -223,7 +223,7 @@ extern "C" SYNSEG_EXPORT int synseg_hsv_mask_hist(synseg_ctx *ctx, const synseg_
     else
         hsv_hist_kernel<false><<<dim3(gx, n_rois), 256, smem, st>>>(plane_of(rgb), rgb->width, rgb->height, rois, (unsigned long long *)count,
                                                                    hist, nullptr, row_count, max_rows);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "hsv_hist", st);
     return SYNSEG_OK;
 }
 
@@ -241,6 +241,6 @@ extern "C" SYNSEG_EXPORT int synseg_hsv_mask_gather(synseg_ctx *ctx, const synse
     }
     hsv_gather_kernel<<<cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(plane_of(rgb), r, (const unsigned long long *)row_prefix,
                                                                     (const long long *)ranks, n, out_rgb);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "hsv_gather", (cudaStream_t)stream);
     return SYNSEG_OK;
 }

@@ -179,7 +179,7 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     const bool dal = to_bits ? true : plane_aligned(out_u8, 4);
     if (to_bits) adaptive_mean_kernel<true><<<(unsigned)nblocks, T, smem, st>>>(p, sal, dal);
     else adaptive_mean_kernel<false><<<(unsigned)nblocks, T, smem, st>>>(p, sal, dal);
-    SS_LAUNCH_CHECK(ctx);
+    SS_LAUNCH_CHECK(ctx, "adaptive_mean", st);
     return SYNSEG_OK;
 }
 

@@ -101,6 +101,19 @@ class Context:
     def reserve(self, width: int, height: int, batch: int):
         check(self.lib.synseg_reserve(self._h, self.lib.synseg_scratch_bytes(width, height, batch)), "synseg_reserve")
 
+    # ---- per-kernel timing ---------------------------------------------------------------------
+    def profile_begin(self):
+        check(self.lib.synseg_profile_begin(self._h, _stream()), "synseg_profile_begin")
+
+    def profile_end(self, cap: int = 4096):
+        """[(kernel name, milliseconds), ...] in launch order since profile_begin()."""
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = self.lib.synseg_profile_end(self._h, names, ms, cap)
+        if n < 0:
+            check(n, "synseg_profile_end")
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
+
     # ---- colour -------------------------------------------------------------------------------
     def rgb2gray(self, rgb: torch.Tensor, mode: int = GRAY_CV, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         r = _as3(rgb, 3)
@@ -229,6 +242,18 @@ class Context:
             check(self.lib.synseg_phash(self._h, C.byref(img_of(src, ch)), src_kind, rt.data_ptr() if rt is not None else None, n,
                                         out.data_ptr(), _stream()), "synseg_phash")
         return out
+
+    def select_rois(self, n_labels: torch.Tensor, stats: torch.Tensor, page_base: int, min_area: int, max_area: int, min_w: int,
+                    min_h: int, rois: torch.Tensor, keys: torch.Tensor, count: torch.Tensor):
+        """Device-side candidate selection: appends (image,x,y,w,h) rows to `rois` (int32 [cap,5]) and keys (int64 [cap])."""
+        b, ml = stats.shape[0], stats.shape[1]
+        check(self.lib.synseg_select_rois(self._h, n_labels.data_ptr(), stats.data_ptr(), b, ml, page_base, min_area, max_area, min_w, min_h,
+                                          rois.data_ptr(), keys.data_ptr(), count.data_ptr(), rois.shape[0], _stream()), "synseg_select_rois")
+
+    def phash_indirect(self, src: torch.Tensor, src_kind: int, rois: torch.Tensor, count: torch.Tensor, out: torch.Tensor):
+        ch = 3 if src_kind else 1
+        check(self.lib.synseg_phash_indirect(self._h, C.byref(img_of(src, ch)), src_kind, rois.data_ptr(), count.data_ptr(), rois.shape[0],
+                                             out.data_ptr(), _stream()), "synseg_phash_indirect")
 
     def phash_dedup(self, hashes: torch.Tensor, keys: torch.Tensor, max_hamming: int = 4) -> torch.Tensor:
         n = hashes.numel()

@@ -1,0 +1,166 @@
+"""GPU parity of the fused page pipeline, the detector, the hint functions, streaming and dedup.
+Checker: the cv2 chain / C oracle on the same seeded pages, and golden vectors from the imported reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import imgs
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+cv2 = pytest.importorskip("cv2")
+from PIL import Image  # noqa: E402
+
+import oracle  # noqa: E402
+from oracle import cv2_chain  # noqa: E402
+from synapta_image_segmentation_b200.synth import page_shape, synth_page, synth_pages  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _check_pages(ctx, pages, dpi, max_labels=1024):
+    bs, c, k = cv2_chain.chain_params(dpi)
+    n, stats, cent = ctx.detect_pages(torch.from_numpy(pages).cuda(), bs, c, k, max_labels=max_labels)
+    n, stats, cent = n.cpu().numpy(), stats.cpu().numpy(), cent.cpu().numpy()
+    for i in range(pages.shape[0]):
+        r = cv2_chain.page_chain(pages[i], dpi)
+        assert n[i] == r["n"], (i, n[i], r["n"])
+        assert np.array_equal(stats[i, :r["n"]], r["stats"]), i
+        assert np.array_equal(cent[i, :r["n"]], r["centroids"]), i
+
+
+def test_config1_single_300dpi_page(ctx):
+    """BASELINE.json configs[0]: one 2550x3300 page with 3 figures; boxes, areas, centroids bit-exact vs cv2."""
+    page, _ = synth_page(0, 300, n_figures=3)
+    assert page.shape == (3300, 2550, 3)
+    _check_pages(ctx, page[None], 300)
+
+
+def test_config2_256_pages_150dpi(ctx):
+    """BASELINE.json configs[1]: batch of 256 synthetic 150-DPI pages, detection + per-label stats bit-exact vs CPU."""
+    pages = synth_pages(256, 150, base_seed=77)
+    assert pages.shape[1:] == (1650, 1275, 3)
+    for s in range(0, 256, 64):
+        _check_pages(ctx, pages[s:s + 64], 150)
+
+
+def test_pipeline_odd_sizes_and_noise(ctx):
+    """Widths/heights not multiples of 2/4/32, dense noise pages (thousands of components before merging)."""
+    for (h, w, seed) in [(301, 203, 1), (257, 511, 2), (64, 33, 3)]:
+        page = imgs.rgb_noise(h, w, seed)
+        page[h // 3:h // 2] = 255
+        bs, c, k = 15, 5, 5
+        n, stats, cent = ctx.detect_pages(torch.from_numpy(page).cuda()[None], bs, c, k, max_labels=8192)
+        g = cv2.cvtColor(page, cv2.COLOR_RGB2GRAY)
+        ink = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, bs, c) | cv2.Canny(g, 50, 150)
+        se = cv2.getStructuringElement(cv2.MORPH_RECT, (k, k))
+        closed = cv2.morphologyEx(cv2.dilate(ink, se), cv2.MORPH_CLOSE, se)
+        n_w, _, st_w, ce_w = cv2.connectedComponentsWithStats(closed, 8, cv2.CV_32S)
+        assert int(n[0]) == n_w
+        assert np.array_equal(stats[0, :n_w].cpu().numpy(), st_w)
+        assert np.array_equal(cent[0, :n_w].cpu().numpy(), ce_w, equal_nan=True)
+
+
+def test_detector_regions_cover_figures(ctx):
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    det = RasterRegionDetector(DetectConfig(dpi=150), ctx=ctx)
+    pages, truths = [], []
+    for i in range(6):
+        p, t = synth_page(i, 150, n_figures=2)
+        pages.append(p); truths.append(t)
+    batch = torch.from_numpy(np.stack(pages)).cuda()
+    regions = det.detect_regions_batch(batch, page_nums=list(range(6)), with_hash=True)
+    for page, regs, truth in zip(pages, regions, truths):
+        assert regs == sorted(regs, key=lambda r: (r["bbox"].y0, r["bbox"].x0))
+        for r in regs:
+            assert set(["bbox", "caption", "detection_method", "notes", "confidence", "validation"]) <= set(r)
+            assert r["bbox"].page_width == 612.0 and r["bbox"].page_height == 792.0
+            assert r["confidence"] >= 0.5
+            x, y, w, h = r["crop_px"]
+            g = np.array(Image.fromarray(np.ascontiguousarray(page[y:y + h, x:x + w])).convert("L"))
+            assert abs(r["variance"] - float(np.var(g))) <= 1e-9 * max(1.0, r["variance"])
+            assert r["phash"] == oracle.phash(g)
+        for t in truth:         # every synthetic figure lies inside one detected region
+            x0, y0, x1, y1 = [v * 72.0 / 150 for v in t["box_px"]]
+            assert any(r["bbox"].x0 <= x0 + 1 and r["bbox"].y0 <= y0 + 1 and r["bbox"].x1 >= x1 - 1 and r["bbox"].y1 >= y1 - 1 for r in regs)
+    single = det.detect_regions(pages[0], 0)
+    assert [r["bbox"] for r in single] == [r["bbox"] for r in regions[0]]
+    segs = det.extract_segments(pages[0], 0, "textbook_001")
+    assert all(s.segment_id.startswith("textbook_001_p000_") and s.page_no == 1 and s.notes.startswith("Validation: ") for s in segs)
+    assert json.dumps(segs[0].to_dict())
+
+
+def test_hints_match_reference_golden(ctx):
+    """FeatureHints.* == what the reference's OCRProcessor.* returned on the same crops (tests/golden)."""
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    gold = json.load(open(os.path.join(GOLD, "reference_helpers.json")))["crops"]
+    for name, rec in gold.items():
+        img = Image.open(os.path.join(GOLD, name))
+        f = FeatureHints.edge_features(img)
+        assert (f["h_count"], f["v_count"], f["edge_px"]) == (rec["h_count"], rec["v_count"], rec["edge_px"]), name
+        assert FeatureHints._detect_grid(img) == rec["detect_grid"], name
+        assert FeatureHints._count_arrows(img) == rec["count_arrows"], name
+        assert FeatureHints._detect_shapes(img) == rec["detect_shapes"], name
+        assert FeatureHints._estimate_data_points(img) == rec["estimate_data_points"], name
+        assert len(FeatureHints._extract_connections(img)) == rec["connections"], name
+        assert FeatureHints._detect_image_subtype(img, None) == rec["image_subtype"], name
+        np.random.seed(7)
+        assert FeatureHints._extract_dominant_colors(img) == rec["dominant_colors_seed7"], name
+        hb = FeatureHints.hints_batch([img])[0]
+        assert hb["mask_px"] == rec["mask_px"] and hb["grid_detected"] == rec["detect_grid"]
+        assert abs(hb["variance"] - rec["variance"]) <= 1e-9 * max(1.0, rec["variance"])
+
+
+def test_chart_counts_and_subtype(ctx):
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    from synapta_image_segmentation_b200.synth import render_figure
+    for i in range(3):
+        fig = render_figure([99, i], 150, 500, 700)
+        v_px, h_px, bars = cv2_chain.chart_counts(fig)
+        t = torch.from_numpy(fig).cuda()
+        counts, _ = ctx.grid_counts(t, None, 0, 0, 0, False, channels=3)      # cv2 grey, chart kernel rule
+        assert (int(counts[0, 1]), int(counts[0, 0])) == (v_px, h_px)
+        assert FeatureHints._detect_chart_subtype(Image.fromarray(fig), None) in (None, "bar", "line", "pie")
+
+
+def test_streaming_equals_direct(ctx):
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    from synapta_image_segmentation_b200.streaming import PageStreamer
+    det = RasterRegionDetector(DetectConfig(dpi=72, max_labels=512), ctx=ctx)
+    h, w = page_shape(72)
+    batches = [torch.from_numpy(synth_pages(4, 72, base_seed=5, start=4 * i)).pin_memory() for i in range(5)]
+    got = {}
+    st = PageStreamer(det, 4, h, w, slots=2)
+    n_pages = st.run(iter(batches), lambda i, n, s: got.__setitem__(i, (n.clone(), s.clone())), stats_rows=64)
+    assert n_pages == 20 and st.h2d_bytes == 20 * h * w * 3
+    for i, hb in enumerate(batches):
+        n, stats, _ = det.detect_components(hb.cuda())
+        assert torch.equal(got[i][0], n.cpu())
+        assert torch.equal(got[i][1][:, :64], stats[:, :64].cpu())
+
+
+def test_dedup_finds_repeated_figures(ctx):
+    from synapta_image_segmentation_b200.dedup import cross_page_dedup, region_key
+    from synapta_image_segmentation_b200.synth import render_figure
+    figs = [render_figure([5, i], 150, 500, 700) for i in range(4)]
+    crops = [figs[0], figs[1], figs[0], figs[2], figs[1], figs[3]]
+    hs = torch.cat([ctx.phash(torch.from_numpy(c).cuda(), 1) for c in crops])
+    keys = torch.tensor([region_key(p, 0) for p in range(6)], dtype=torch.int64, device="cuda")
+    k_all, keep = cross_page_dedup(ctx, hs, keys, capacity=16)
+    assert keep.cpu().tolist() == [1, 1, 0, 1, 0, 1]
+    # device-side candidate selection + indirect hashing reproduces the direct hashes
+    page, _ = synth_page(1, 150, n_figures=2)
+    t = torch.from_numpy(page).cuda()[None]
+    n, stats, _ = ctx.detect_pages(t, 25, 10, 21, max_labels=256)
+    rois = torch.empty((64, 5), dtype=torch.int32, device="cuda"); keys2 = torch.empty(64, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda"); out = torch.empty(64, dtype=torch.int64, device="cuda")
+    ctx.select_rois(n, stats, 7, 21701, int(0.8 * page.shape[0] * page.shape[1]), 104, 104, rois, keys2, cnt)
+    ctx.phash_indirect(t, 1, rois, cnt, out)
+    c = int(cnt.item())
+    assert c >= 2
+    direct = ctx.phash(t, 1, [tuple(r) for r in rois[:c].cpu().tolist()])
+    assert torch.equal(direct, out[:c])
+    assert all((int(k) >> 16) == 7 for k in keys2[:c].cpu().tolist())

@@ -1,0 +1,180 @@
+"""CPU tests: host-side mirror of the reference rules vs golden vectors from the imported reference,
+the C-ABI export list vs include/synseg.h, data model, synthetic generator, and the world_size-2 gloo path."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from synapta_image_segmentation_b200 import geometry as G  # noqa: E402
+from synapta_image_segmentation_b200.datamodel import (BoundingBox, ChartSpecificData, FigureSpecificData, VisualSegment,  # noqa: E402
+                                                       VisualType)
+
+
+def BB(*a):
+    return BoundingBox(*a, 612, 792)
+
+
+@pytest.fixture(scope="module")
+def geo():
+    return json.load(open(os.path.join(GOLD, "reference_geometry.json")))
+
+
+def test_overlap_rules(geo):
+    assert G.calculate_overlap_ratio(BB(0, 0, 10, 10), BB(5, 5, 20, 20)) == geo["overlap_ratio"] == 0.25
+    ex = [{"bbox": BB(0, 0, 100, 100)}]
+    got = [G.overlaps_with_existing(BB(50, 0, 150, 100), ex), G.overlaps_with_existing(BB(49, 0, 149, 100), ex)]
+    assert got == geo["overlaps_existing"] == [False, True]
+    assert G.find_conflicting(BB(0, 0, 10, 10), [type("S", (), {"bbox": BB(5, 5, 20, 20)})()]) is None      # 0.25 <= 0.4
+    assert G.find_conflicting(BB(0, 0, 10, 10), [type("S", (), {"bbox": BB(2, 2, 20, 20)})()]) is not None  # 0.64
+
+
+def test_drawing_distance_and_clusters(geo):
+    assert [G.drawing_distance([0, 0, 10, 10], [10, 10, 20, 20]), G.drawing_distance([0, 0, 10, 10], [13, 14, 20, 20])] == geo["drawing_distance"]
+    rects5 = [[x, 0, x + 10, 10] for x in (0, 60, 150, 240, 330)]
+    assert [[rects5[i] for i in c] for c in G.cluster_rects(rects5)] == geo["cluster_5"] == []
+    rects = geo["cluster_random_in"]
+    assert [[rects[i] for i in c] for c in G.cluster_rects(rects)] == geo["cluster_random_out"]
+
+
+def test_regions_from_rects(geo):
+    regs = G.regions_from_rects([[100 + 5 * i, 100, 110 + 5 * i, 300] for i in range(6)], 612.0, 792.0)
+    got = [dict(bbox=[r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1], caption=r["caption"],
+                detection_method=r["detection_method"], notes=r["notes"]) for r in regs]
+    assert got == geo["detect_by_drawings"]
+    regs = G.regions_from_rects(geo["cluster_random_in"], 612.0, 792.0)
+    got = [dict(bbox=[r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1], notes=r["notes"]) for r in regs]
+    assert got == geo["detect_by_drawings_random"]
+
+
+def test_validate_region_bit_identical_scores(geo):
+    imgs_ = {"noise": (400, 300, float(np.var(_gray("noise")))), "flat": (300, 300, 0.0), "small": (300, 40, float(np.var(_gray("small"))))}
+    for v in geo["validate"]:
+        w, h, var = imgs_[v["image"]]
+        score, notes = G.validate_region(BB(*v["bbox"]), w, h, var, 792.0)
+        assert score == v["score"] and notes == v["notes"], v      # == on floats: same f64 operation order
+
+
+def _gray(name):
+    from PIL import Image
+    if name == "noise":
+        a = np.random.default_rng(1).integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    else:
+        a = np.random.default_rng(2).integers(0, 256, (40, 300, 3), dtype=np.uint8)
+    return np.array(Image.fromarray(a).convert("L"))
+
+
+def test_resolve_conflict(geo):
+    var = {"noise": float(np.var(_gray("noise"))), "flat": 0.0}
+    for v in geo["resolve_conflict"]:
+        d, why = G.resolve_conflict(BB(*v["emb"]), v["confidence"], var[v["image"]], BB(*v["cap"]), v["caption"])
+        assert (d, why) == (v["decision"], v["reasons"])
+
+
+def test_merge_visual_regions():
+    a = {"bbox": BB(0, 0, 100, 100), "caption_bbox": [10, 120, 90, 130]}
+    dup = {"bbox": BB(10, 10, 90, 90)}                  # 100 % of its area inside a -> dropped
+    above_caption = {"bbox": BB(0, 300, 100, 400)}
+    near_caption = {"bbox": BB(5, 20, 95, 115)}         # caption top-left within +-50 pt of its bottom edge... and duplicate
+    far = {"bbox": BB(300, 300, 400, 400)}
+    out = G.merge_visual_regions([a], [dup, above_caption, near_caption, far])
+    assert out == [a, above_caption, far]
+
+
+def test_datamodel_to_dict_schema():
+    seg = VisualSegment("textbook_001_p000_61f12f4c", VisualType.IMAGE, "textbook_001", 1, BoundingBox(106.37, 541.88, 439.38, 749.38, 651.6, 795.6),
+                        image_bytes=b"x", confidence=np.float64(1.0),
+                        notes="Validation: good_size, substantial_dimensions, good_aspect_ratio, good_position, good_content_variance")
+    seg.chart_data = ChartSpecificData(grid_detected=np.bool_(True), estimated_data_points=np.int64(23), color_scheme=["#234665"])
+    seg.figure_data = FigureSpecificData(contains_chart=True)
+    d = seg.to_dict()
+    ref = json.load(open("/root/reference/extracted_visuals_excelSS/textbook_001_visual_segments.json"))["segments"][0] \
+        if os.path.exists("/root/reference/extracted_visuals_excelSS/textbook_001_visual_segments.json") else None
+    if ref is not None:     # same key set as the reference's shipped JSON record (build container only)
+        assert set(ref) - set(d) <= {"image_details"} and set(ref["bbox"]) == set(d["bbox"])
+    assert "image_bytes" not in d and d["segment_type"] == "image" and d["bbox"]["width"] == pytest.approx(333.01)
+    assert d["chart_details"]["has_grid"] is True and d["chart_details"]["data_points"] == 23
+    assert d["figure_details"]["contains_chart"] is True
+    json.dumps(d)
+    assert BoundingBox(72, 72, 144, 216, 612, 792).to_pixels(300) == (300, 300, 300, 600)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads (no GPU needed) and exports exactly the functions include/synseg.h declares."""
+    from synapta_image_segmentation_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "synseg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(synseg_[a-z0-9_]+)\s*\(", hdr))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (synseg_\w+)", out))
+    assert exported == declared, exported ^ declared
+    assert lib.synseg_version() == 100
+    import torch
+    if not torch.cuda.is_available():      # fails loudly without a GPU: no CPU fallback
+        import ctypes as C
+        h = C.c_void_p()
+        assert lib.synseg_create(0, C.byref(h)) != 0 and lib.synseg_last_error()
+
+
+def test_synth_is_deterministic_and_shaped():
+    from synapta_image_segmentation_b200.synth import page_shape, synth_page
+    assert page_shape(300) == (3300, 2550) and page_shape(150) == (1650, 1275)
+    a, ta = synth_page(5, 72, n_figures=2)
+    b, tb = synth_page(5, 72, n_figures=2)
+    assert np.array_equal(a, b) and ta == tb and a.shape == (792, 612, 3) and len(ta) == 2
+
+
+def test_shard_and_keys():
+    from synapta_image_segmentation_b200.dedup import region_key, shard_pages
+    for n, w in [(8000, 8), (1000, 3), (5, 8)]:
+        pages = [p for r in range(w) for p in shard_pages(n, r, w)]
+        assert pages == list(range(n))
+    assert region_key(3, 2) == (3 << 16) | 2
+    with pytest.raises(ValueError):
+        region_key(1, 70000)
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from synapta_image_segmentation_b200.dedup import gather_hashes, shard_pages, region_key
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# every rank hashes "its" pages with a deterministic stand-in hash; page p and p+4 are duplicates
+pages = list(shard_pages(10, rank, world))
+h = torch.tensor([(p % 4) * 0x0101010101 + 7 for p in pages], dtype=torch.int64)
+k = torch.tensor([region_key(p, 0) for p in pages], dtype=torch.int64)
+hh, kk = gather_hashes(h, k, capacity=8)
+assert kk.tolist() == [region_key(p, 0) for p in range(10)], kk.tolist()
+assert hh.tolist() == [(p % 4) * 0x0101010101 + 7 for p in range(10)]
+# replicated decision (numpy stand-in for the CUDA Hamming kernel): identical on both ranks
+keep = [not any(kk[j] < kk[i] and bin(int(hh[i]) ^ int(hh[j])).count("1") <= 4 for j in range(len(kk))) for i in range(len(kk))]
+assert keep == [True] * 4 + [False] * 6
+out = [None] * world
+dist.all_gather_object(out, keep)
+assert all(o == keep for o in out)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world2_gather_and_replicated_dedup(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
