@@ -93,6 +93,17 @@ def test_detector_regions_cover_figures(ctx):
     assert json.dumps(segs[0].to_dict())
 
 
+def _same_colours(got, want, name):
+    """Dominant colours: the GPU hands sklearn the identical seeded sample (gather test), but KMeans' float
+    arithmetic depends on the host CPU / BLAS, so centroids are compared as sets within 1 LSB per channel
+    (the tolerance north_star states for float-derived features)."""
+    assert len(got) == len(want), name
+    a = sorted(tuple(int(c[i:i + 2], 16) for i in (1, 3, 5)) for c in got)
+    b = sorted(tuple(int(c[i:i + 2], 16) for i in (1, 3, 5)) for c in want)
+    for x in a:
+        assert any(max(abs(p - q) for p, q in zip(x, y)) <= 1 for y in b), (name, got, want)
+
+
 def test_hints_match_reference_golden(ctx):
     """FeatureHints.* == what the reference's OCRProcessor.* returned on the same crops (tests/golden)."""
     from synapta_image_segmentation_b200.hints import FeatureHints
@@ -108,7 +119,8 @@ def test_hints_match_reference_golden(ctx):
         assert len(FeatureHints._extract_connections(img)) == rec["connections"], name
         assert FeatureHints._detect_image_subtype(img, None) == rec["image_subtype"], name
         np.random.seed(7)
-        assert FeatureHints._extract_dominant_colors(img) == rec["dominant_colors_seed7"], name
+        got = FeatureHints._extract_dominant_colors(img)
+        _same_colours(got, rec["dominant_colors_seed7"], name)
         hb = FeatureHints.hints_batch([img])[0]
         assert hb["mask_px"] == rec["mask_px"] and hb["grid_detected"] == rec["detect_grid"]
         assert abs(hb["variance"] - rec["variance"]) <= 1e-9 * max(1.0, rec["variance"])
