@@ -7,11 +7,12 @@
 //   (TG22 = 13573 = tan(22.5 deg) << 15) -> kept pixels with mag > hi are strong -> the output is
 //   every kept pixel 8-connected (through kept pixels) to a strong one.
 // Stage 1 (this file): one tile kernel, grey tile + 2-pixel halo staged in shared memory, Sobel and
-//   magnitude for tile + 1 halo kept in shared memory, NMS from shared memory, class map written.
-// Stage 2 (ccl.cu): hysteresis = block union-find over the kept pixels + "component holds a strong
+//   magnitude for tile + 1 halo kept in shared memory, NMS from shared memory; the result is two bit
+//   planes (warp ballots): kept = survived NMS, strong = kept and mag > hi.
+// Stage 2 (ccl.cu): hysteresis = run-based union-find over the kept pixels + "component holds a strong
 //   pixel" flag; no host round trip, no iteration count that depends on the image.
 //
-// Roofline: HBM-bound, 2 algorithmic bytes per pixel (1 read + 1 written).
+// Roofline: HBM-bound, 1.25 algorithmic bytes per pixel (1 read + two bit planes written) for stage 1.
 #include "internal.cuh"
 
 namespace {
@@ -20,7 +21,7 @@ constexpr int TW = 128, TH = 16;           // output tile
 constexpr int GP = TW + 8;                 // grey tile pitch (TW + 4 used)
 constexpr int MP = TW + 4;                 // magnitude / gradient tile pitch (TW + 2 used)
 
-__global__ void __launch_bounds__(256) canny_classes_kernel(Plane src, Plane cls, int width, int height, int lo, int hi)
+__global__ void __launch_bounds__(256) canny_classes_kernel(Plane src, BitPlane kept, BitPlane strong, int width, int height, int lo, int hi)
 {
     __shared__ uint8_t g[(TH + 4) * GP];
     __shared__ uint16_t mag[(TH + 2) * MP];
@@ -58,14 +59,14 @@ __global__ void __launch_bounds__(256) canny_classes_kernel(Plane src, Plane cls
 
     const int lx = tid & (TW - 1);
     const int gx = tx0 + lx;
-    if (gx >= width) return;
+    if (tx0 + (lx & ~31) >= width) return;          // whole warp outside the image (warp-uniform)
     for (int ly = tid >> 7; ly < TH; ly += 2) {
         const int gy = ty0 + ly;
         if (gy >= height) break;
         const uint16_t *mc = mag + (ly + 1) * MP + (lx + 1);
         const int m = mc[0];
-        uint8_t c = 0;
-        if (m > lo) {
+        int c = 0;
+        if (m > lo && gx < width) {
             const uint32_t d = dxy[(ly + 1) * MP + (lx + 1)];
             const int xs = (int)(short)(d & 0xffffu), ys = (int)(short)(d >> 16);
             const int ax = abs(xs), ay = abs(ys) << 15;
@@ -82,36 +83,43 @@ __global__ void __launch_bounds__(256) canny_classes_kernel(Plane src, Plane cls
             }
             if (keep) c = (m > hi) ? 2 : 1;
         }
-        cls.p[img * cls.bs + gy * cls.rs + gx] = c;
+        const uint32_t kw = __ballot_sync(0xffffffffu, c != 0), sw = __ballot_sync(0xffffffffu, c == 2);
+        if ((tid & 31) == 0) {
+            const int64_t o = (int64_t)gy * kept.wpr + (gx >> 5);
+            kept.p[img * kept.bs + o] = kw;
+            strong.p[img * strong.bs + o] = sw;
+        }
     }
 }
 
 }  // namespace
 
-int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *cls, int lo, int hi, cudaStream_t st)
+int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept, BitPlane strong, int lo, int hi, cudaStream_t st)
 {
     dim3 grid(cdiv(gray->width, TW), cdiv(gray->height, TH), gray->batch);
-    canny_classes_kernel<<<grid, 256, 0, st>>>(plane_of(gray), plane_of(cls), gray->width, gray->height, lo, hi);
+    canny_classes_kernel<<<grid, 256, 0, st>>>(plane_of(gray), kept, strong, gray->width, gray->height, lo, hi);
     SS_LAUNCH_CHECK(ctx, "canny_classes", st);
     return SYNSEG_OK;
 }
 
 size_t canny_scratch_bytes(int width, int height, int batch)
 {
-    return (size_t)align_up((size_t)width, 16) * height * batch + 256 + ccl_label_scratch_bytes(width, height, batch) + 256;
+    return 2 * ((size_t)bit_wpr(width) * height * batch * 4 + 256) + hysteresis_scratch_bytes(width, height, batch) + 256;
 }
 
 int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
               int lo, int hi, cudaStream_t st)
 {
-    synseg_img cls = *gray;
-    cls.row_stride = (int64_t)align_up((size_t)gray->width, 16);
-    cls.batch_stride = cls.row_stride * gray->height;
+    const int W = gray->width, H = gray->height, B = gray->batch;
+    const int wpr = bit_wpr(W);
+    const size_t plane_bytes = (size_t)wpr * H * B * 4;
     void *p;
-    SS_TRY(arena_alloc(ctx, (size_t)cls.batch_stride * gray->batch, &p, st));
-    cls.data = p;
-    SS_TRY(launch_canny_classes(ctx, gray, &cls, lo, hi, st));
-    return run_hysteresis(ctx, &cls, edges_u8, edges_bits, or_bits, st);
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane kept{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane strong{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(launch_canny_classes(ctx, gray, kept, strong, lo, hi, st));
+    return run_hysteresis(ctx, kept, strong, W, H, B, edges_u8, edges_bits, or_bits, st);
 }
 
 extern "C" SYNSEG_EXPORT int synseg_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges, int lo, int hi, void *stream)

@@ -1,73 +1,124 @@
 // ccl.cu -- 8-connected component labelling with fused statistics, bit-exact with
-// cv2.connectedComponentsWithStats(mask, 8, CV_32S) including cv2's label numbering.
+// cv2.connectedComponentsWithStats(mask, 8, CV_32S) including cv2's label numbering, and the
+// hysteresis stage of Canny (canny.cu) on the same union-find core.
 //
 // No reference call site for the labelling itself (north-star primitive); it also
 // replaces findContours(RETR_EXTERNAL)+boundingRect at pdf_image_segmentation.py:1403-1404.
-// The same union-find core implements Canny's hysteresis (canny.cu).
 //
-// Algorithm: block-based union-find.  One thread owns a 2x2 pixel block (all foreground pixels of a
-// block are mutually 8-connected, so one label per block suffices).  init: L[b] = b (foreground) or
-// -1; merge: lock-free union (atomicMin towards the smaller block index) with the four predecessor
-// blocks whose pixels touch; compress: L[b] = root.  The root of a component is therefore its
-// smallest block index = the first block in 2x2-block raster order, which is exactly the order in
-// which cv2's block-based algorithm numbers components; final labels are 1 + (rank of the root
-// among roots), obtained with a chunked scan over the block array.
-// Statistics (bbox, area, coordinate sums) are reduced hierarchically: redux.sync over lanes that
-// share a label -> a small per-CTA shared-memory cache keyed by label -> one global atomic set per
-// CTA and label.  Centroids are sum/area in f64 like cv2.
+// Data layout: the mask is a bit plane (1 bit / pixel).  The unit of the union-find is a BLOCK RUN:
+//   * a block is a 2x2 pixel cell (all foreground pixels of a cell are mutually 8-connected);
+//   * blocks bx, bx+1 of one block row are linked iff column 2bx+1 and column 2bx+2 both hold a
+//     foreground pixel in the two pixel rows of the block row (any such pair is 8-adjacent);
+//   * a block run is a maximal chain of linked blocks; it is identified by its first block, and only
+//     that block owns an entry in the parent array L (int32 per block, touched sparsely).
+// One warp owns one block row; a lane owns a 64-pixel chunk (one 64-bit word per pixel row); runs are
+// found with bit arithmetic and a ballot-based carry across lanes.  Vertical contacts between block
+// rows are unions between runs, issued once per touching (run, run) pair:
+//   t = top pixel row of the block row, u = pixel row above it
+//   event A at x: t[x] & !t[x-1] & (u[x] | u[x-1])  -> union(run of t[x], run of u[x] or else u[x-1])
+//   event B at x: u[x] & !u[x-1] & t[x-1]           -> union(run of t[x-1], run of u[x])
+// so a solid blob costs one atomic per block row instead of four per block.  Unions are lock-free
+// (atomicMin towards the smaller block index, find with path halving); the root of a component is its
+// first block in 2x2-block raster order, which is exactly the order in which cv2's block-based
+// algorithm numbers components, so labels are 1 + rank of the root (root bit plane + per-row counts
+// + scan).  Statistics are reduced per run piece (popcounts of the 64-bit masks) -> warp redux over
+// lanes sharing a label -> per-CTA shared-memory cache -> one global atomic set per CTA and label.
+// Centroids are sum/area in f64 like cv2.
 //
-// Roofline: HBM-bound; algorithmic bytes 5 per pixel with a label image (1 read + 4 written),
-// 1 per pixel without (mask read; the block-label scratch is 1 B/px and L2-resident per page).
+// Roofline: HBM/L2-bound on the bit plane; algorithmic bytes 1/8 per pixel read (+4 per pixel when a
+// label image is requested).  The parent array is touched only at run starts.
 #include "internal.cuh"
 
 namespace {
 
-struct MaskAcc {
-    const uint8_t *p; int64_t rs; int64_t bs;      // u8 plane (p != nullptr)
-    const uint32_t *bits; int wpr; int64_t wbs;    // bit plane otherwise
+typedef unsigned long long u64;
+constexpr u64 EVEN = 0x5555555555555555ULL;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int ROWS_PER_CTA = 8;     // one warp per block row
+
+struct RowGeom {
+    const uint32_t *bits; int wpr; int64_t wbs;   // bit plane: words per row / per image
     int width, height;
+    int bw, bh;        // blocks per block row, block rows
+    int64_t bper;      // parent-array entries per image
+    int nseg;          // 2048-pixel segments per row (32 lanes x 64 pixels)
+    int cpr;           // 64-pixel chunks per row = cdiv(width, 64)
 };
 
-__device__ __forceinline__ bool fg_at(const MaskAcc &m, int img, int x, int y)
+// 64 pixels of one row; bits at x >= width (and rows outside the image) read as 0
+__device__ __forceinline__ u64 load_chunk(const uint32_t *row, int chunk, int width)
 {
-    if (m.p) return __ldg(m.p + img * m.bs + y * m.rs + x) != 0;
-    return (__ldg(m.bits + img * m.wbs + (int64_t)y * m.wpr + (x >> 5)) >> (x & 31)) & 1u;
-}
-
-// 2x2 block pixel presence: bit0 (r,c), bit1 (r,c+1), bit2 (r+1,c), bit3 (r+1,c+1); in-image only.
-__device__ __forceinline__ uint32_t block_px(const MaskAcc &m, int img, int c, int r)
-{
-    uint32_t v = 0;
-    const bool x1 = c + 1 < m.width, y1 = r + 1 < m.height;
-    if (m.p) {
-        const uint8_t *row = m.p + img * m.bs + r * m.rs + c;
-        v |= (__ldg(row) != 0) ? 1u : 0u;
-        if (x1) v |= (__ldg(row + 1) != 0) ? 2u : 0u;
-        if (y1) {
-            v |= (__ldg(row + m.rs) != 0) ? 4u : 0u;
-            if (x1) v |= (__ldg(row + m.rs + 1) != 0) ? 8u : 0u;
-        }
-    } else {
-        // c is even, so both pixels of a row live in the same word
-        const uint32_t *w = m.bits + img * m.wbs + (int64_t)r * m.wpr + (c >> 5);
-        uint32_t a = (__ldg(w) >> (c & 31)) & 3u;
-        if (!x1) a &= 1u;
-        v = a;
-        if (y1) {
-            uint32_t b = (__ldg(w + m.wpr) >> (c & 31)) & 3u;
-            if (!x1) b &= 1u;
-            v |= b << 2;
-        }
-    }
+    const int rem = width - 64 * chunk;
+    if (row == nullptr || rem <= 0) return 0;
+    const uint2 w = __ldg((const uint2 *)row + chunk);
+    u64 v = ((u64)w.y << 32) | w.x;
+    if (rem < 64) v &= (1ULL << rem) - 1ULL;
     return v;
 }
 
-__device__ __forceinline__ int32_t uf_find(const int32_t *L, int32_t i)
+// ---- run structure of one block row ---------------------------------------------------------
+struct RunCarry { uint32_t topbit; int start; };   // warp-uniform state carried from one segment to the next
+struct Runs {
+    u64 occE;      // even bit 2i: block i of this chunk holds a foreground pixel
+    u64 startE;    // even bit 2i: block i starts a run
+    int carryIn;   // first block (column index) of the run that holds the last block of the previous chunk
+};
+
+// v = OR of the two pixel rows of the block row (this lane's chunk).  All 32 lanes must call.
+__device__ __forceinline__ Runs analyze_runs(u64 v, int chunk, int lane, RunCarry &c)
 {
-    // L2-coherent loads: parents only ever decrease, so a stale value is still an ancestor
-    int32_t p = __ldcg(L + i);
-    while (p != i) { i = p; p = __ldcg(L + i); }
-    return i;
+    const uint32_t hi = (uint32_t)(v >> 63);
+    uint32_t pb = __shfl_up_sync(FULL, hi, 1);
+    if (lane == 0) pb = c.topbit;
+    const u64 vprev = (v << 1) | pb;                   // vprev[x] = v[x-1]
+    Runs r;
+    r.occE = (v | (v >> 1)) & EVEN;
+    r.startE = r.occE & ~(v & vprev);                  // not linked to the previous block
+    const unsigned has = __ballot_sync(FULL, r.startE != 0);
+    const int my_last = r.startE ? chunk * 32 + ((63 - __clzll((long long)r.startE)) >> 1) : -1;
+    const unsigned below = has & ((1u << lane) - 1u);
+    const int from_lane = __shfl_sync(FULL, my_last, below ? 31 - __clz((int)below) : 0);
+    r.carryIn = below ? from_lane : c.start;
+    const int last_all = __shfl_sync(FULL, my_last, has ? 31 - __clz((int)has) : 0);
+    if (has) c.start = last_all;
+    c.topbit = __shfl_sync(FULL, hi, 31);
+    return r;
+}
+
+// first block (column index) of the run holding the block at even bit position `pos` of this chunk
+__device__ __forceinline__ int run_start(const Runs &r, int chunk, int pos)
+{
+    const u64 m = r.startE & ((2ULL << pos) - 1ULL);
+    return m ? chunk * 32 + ((63 - __clzll((long long)m)) >> 1) : r.carryIn;
+}
+
+// Next run piece of a chunk (maximal chain of linked blocks inside the chunk).  `rem` = blocks not yet
+// visited (even bits).  Returns the pixel-column range mask of the piece and its run's first block.
+__device__ __forceinline__ u64 next_piece(const Runs &r, int chunk, u64 &rem, int &first_block)
+{
+    const int p = __ffsll((long long)rem) - 1;
+    const u64 brk = (~r.occE | r.startE) & EVEN;
+    const u64 above = (p >= 62) ? 0ULL : (brk & (~0ULL << (p + 2)));
+    const int e = above ? __ffsll((long long)above) - 1 : 64;
+    const u64 range = ((e >= 64) ? ~0ULL : ((1ULL << e) - 1ULL)) & (~0ULL << p);
+    rem &= ~range;
+    first_block = ((r.startE >> p) & 1ULL) ? chunk * 32 + (p >> 1) : r.carryIn;   // a piece that is not a start begins at p == 0
+    return range;
+}
+
+// ---- union-find -----------------------------------------------------------------------------
+// Parents only ever decrease and every value written is an ancestor, so stale reads are harmless;
+// L2-coherent loads because other SMs write concurrently.
+__device__ __forceinline__ int32_t uf_find(int32_t *L, int32_t i)
+{
+    for (;;) {
+        const int32_t p = __ldcg(L + i);
+        if (p == i) return i;
+        const int32_t gp = __ldcg(L + p);
+        if (gp == p) return p;
+        atomicMin(L + i, gp);          // path halving; only non-root entries are touched
+        i = gp;
+    }
 }
 
 __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
@@ -76,113 +127,159 @@ __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
     do {
         a = uf_find(L, a);
         b = uf_find(L, b);
-        if (a < b) { int32_t old = atomicMin(&L[b], a); done = (old == b); b = old; }
-        else if (b < a) { int32_t old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        if (a < b) { const int32_t old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int32_t old = atomicMin(&L[a], b); done = (old == a); a = old; }
         else done = true;
     } while (!done);
 }
 
-struct CclGeom { int bw, bh; int nblk; int64_t bper; };   // blocks per row / column / image; padded stride
+#define ROW_PROLOGUE(first_row)                                                             \
+    const int lane = threadIdx.x & 31;                                                       \
+    const int by = (first_row) + blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);             \
+    const int img = blockIdx.y;                                                              \
+    const bool row_ok = by < g.bh;                                                           \
+    const uint32_t *pbase = g.bits + img * g.wbs;                                            \
+    const uint32_t *r0 = pbase + (int64_t)(2 * by) * g.wpr;                                  \
+    const uint32_t *r1 = (2 * by + 1 < g.height) ? r0 + g.wpr : nullptr;
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(MaskAcc m, CclGeom g, int32_t *L)
+// every run start becomes its own parent
+__global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall)
 {
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    if (bx >= g.bw || by >= g.bh) return;
-    const int32_t b = by * g.bw + bx;
-    L[img * g.bper + b] = block_px(m, img, 2 * bx, 2 * by) ? b : -1;
+    ROW_PROLOGUE(0)
+    if (!row_ok) return;
+    int32_t *L = Lall + img * g.bper + (int64_t)by * g.bw;
+    RunCarry c{0u, -1};
+    for (int s = 0; s < g.nseg; ++s) {
+        const int chunk = s * 32 + lane;
+        const u64 v = load_chunk(r0, chunk, g.width) | load_chunk(r1, chunk, g.width);
+        const Runs r = analyze_runs(v, chunk, lane, c);
+        u64 st = r.startE;
+        while (st) {
+            const int bx = chunk * 32 + ((__ffsll((long long)st) - 1) >> 1);
+            st &= st - 1;
+            L[bx] = by * g.bw + bx;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) ccl_merge_kernel(MaskAcc m, CclGeom g, int32_t *Lall)
+// unions between the runs of block row `by` and those of block row by - 1
+__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lall)
 {
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    if (bx >= g.bw || by >= g.bh) return;
-    const int c = 2 * bx, r = 2 * by;
-    const uint32_t px = block_px(m, img, c, r);
-    if (!px) return;
-    // 4x4 window mask, bit = 4*wy + wx with window origin (r-1, c-1)
-    uint32_t P = 0;
-    if (px & 1u) P |= 0x777u;
-    if (px & 2u) P |= 0x777u << 1;
-    if (px & 4u) P |= 0x777u << 4;
-    if (px & 8u) P |= 0x777u << 5;
-    if (c == 0) P &= 0xEEEEu;
-    if (c + 1 >= m.width) P &= 0x3333u;
-    else if (c + 2 >= m.width) P &= 0x7777u;
-    if (r == 0) P &= 0xFFF0u;
+    ROW_PROLOGUE(1)
+    if (!row_ok) return;
+    const uint32_t *u1 = r0 - g.wpr, *u0 = u1 - g.wpr;    // pixel rows 2by-1, 2by-2
     int32_t *L = Lall + img * g.bper;
-    const int32_t b = by * g.bw + bx;
-    if ((P & 0x1u) && fg_at(m, img, c - 1, r - 1)) uf_union(L, b, b - g.bw - 1);
-    if (((P & 0x2u) && fg_at(m, img, c, r - 1)) || ((P & 0x4u) && fg_at(m, img, c + 1, r - 1))) uf_union(L, b, b - g.bw);
-    if ((P & 0x8u) && fg_at(m, img, c + 2, r - 1)) uf_union(L, b, b - g.bw + 1);
-    if (((P & 0x10u) && fg_at(m, img, c - 1, r)) || ((P & 0x100u) && r + 1 < m.height && fg_at(m, img, c - 1, r + 1)))
-        uf_union(L, b, b - 1);
-}
-
-__global__ void __launch_bounds__(256) ccl_compress_kernel(int64_t n, int32_t *L, int64_t bper, int nblk)
-{
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int64_t img = i / bper;
-    int32_t *Li = L + img * bper;
-    const int32_t b = (int32_t)(i - img * bper);
-    if (b >= nblk) return;          // padding entries of the per-image stride are never initialised
-    const int32_t v = Li[b];
-    if (v >= 0 && v != b) Li[b] = uf_find(Li, v);
-}
-
-// ---- numbering: chunked scan over the block array -------------------------------------------
-constexpr int CHUNK = 1024;   // block entries per CTA (256 threads x 4)
-
-__device__ __forceinline__ int count_roots4(const int32_t *L, int nblk, int base, int t, bool flag[4])
-{
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int idx = base + 4 * t + j;
-        flag[j] = (idx < nblk) && (L[idx] == idx);
-        cnt += flag[j];
-    }
-    return cnt;
-}
-
-__global__ void __launch_bounds__(256) ccl_count_kernel(const int32_t *Lall, int64_t bper, int nblk, int nchunks, int32_t *chunk_cnt)
-{
-    const int img = blockIdx.y, chunk = blockIdx.x;
-    const int32_t *L = Lall + img * bper;
-    bool f[4];
-    int c = count_roots4(L, nblk, chunk * CHUNK, threadIdx.x, f);
-    c = __reduce_add_sync(0xffffffffu, c);
-    __shared__ int ws[8];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int i = 0; i < 8; ++i) s += ws[i];
-        chunk_cnt[img * nchunks + chunk] = s;
+    const int cur_base = by * g.bw, up_base = (by - 1) * g.bw;
+    RunCarry cc{0u, -1}, cu{0u, -1};
+    uint32_t t_top = 0, u_top = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+        const int chunk = s * 32 + lane;
+        const u64 t = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
+        const u64 u = load_chunk(u1, chunk, g.width), b0 = load_chunk(u0, chunk, g.width);
+        const Runs rc = analyze_runs(t | a1, chunk, lane, cc);
+        const Runs ru = analyze_runs(u | b0, chunk, lane, cu);
+        const uint32_t th = (uint32_t)(t >> 63), uh = (uint32_t)(u >> 63);
+        uint32_t tp = __shfl_up_sync(FULL, th, 1), up = __shfl_up_sync(FULL, uh, 1);
+        if (lane == 0) { tp = t_top; up = u_top; }
+        t_top = __shfl_sync(FULL, th, 31); u_top = __shfl_sync(FULL, uh, 31);
+        const u64 tl = (t << 1) | tp, ul = (u << 1) | up;      // tl[x] = t[x-1]
+        u64 ev_a = t & ~tl & (u | ul);
+        u64 ev_b = u & ~ul & tl;
+        while (ev_a) {
+            const int x = __ffsll((long long)ev_a) - 1;
+            ev_a &= ev_a - 1;
+            const int cs = run_start(rc, chunk, x & ~1);
+            int us;
+            if ((u >> x) & 1ULL) us = run_start(ru, chunk, x & ~1);
+            else us = (x > 0) ? run_start(ru, chunk, (x - 1) & ~1) : ru.carryIn;
+            uf_union(L, cur_base + cs, up_base + us);
+        }
+        while (ev_b) {
+            const int x = __ffsll((long long)ev_b) - 1;
+            ev_b &= ev_b - 1;
+            const int us = run_start(ru, chunk, x & ~1);
+            const int cs = (x > 0) ? run_start(rc, chunk, (x - 1) & ~1) : rc.carryIn;
+            uf_union(L, cur_base + cs, up_base + us);
+        }
     }
 }
 
-// one CTA per image: exclusive scan of the chunk counts (in place), total -> n_roots[img]
-__global__ void __launch_bounds__(256) ccl_scan_kernel(int nchunks, int32_t *chunk_cnt, int32_t *n_roots)
+// Full compression of every run start.
+//  MODE 0 (labelling): the roots of the block row go to a bit plane (even-bit layout, one u64 per chunk)
+//                      and their number to row_count.
+//  MODE 1 (hysteresis): the root of every run piece that holds a strong pixel is flagged.
+template <int MODE>
+__global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g, int32_t *Lall, u64 *rootbits, int32_t *row_count,
+                                                            BitPlane strong, uint32_t *flags, int64_t fper)
+{
+    ROW_PROLOGUE(0)
+    if (!row_ok) return;
+    int32_t *L = Lall + img * g.bper;
+    const int cur_base = by * g.bw;
+    RunCarry c{0u, -1};
+    int nroots = 0;
+    const uint32_t *s0 = nullptr, *s1 = nullptr;
+    if (MODE == 1) {
+        s0 = strong.p + img * strong.bs + (int64_t)(2 * by) * strong.wpr;
+        s1 = (2 * by + 1 < g.height) ? s0 + strong.wpr : nullptr;
+    }
+    for (int s = 0; s < g.nseg; ++s) {
+        const int chunk = s * 32 + lane;
+        const u64 v = load_chunk(r0, chunk, g.width) | load_chunk(r1, chunk, g.width);
+        const Runs r = analyze_runs(v, chunk, lane, c);
+        u64 st = r.startE, rootE = 0;
+        while (st) {
+            const int p = __ffsll((long long)st) - 1;
+            st &= st - 1;
+            const int32_t b = cur_base + chunk * 32 + (p >> 1);
+            const int32_t root = uf_find(L, b);
+            if (root != b) L[b] = root; else rootE |= 1ULL << p;
+        }
+        if (MODE == 0) {
+            if (chunk < g.cpr) rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] = rootE;
+            nroots += __popcll(rootE);
+        } else {
+            const u64 sv = load_chunk(s0, chunk, g.width) | load_chunk(s1, chunk, g.width);
+            u64 rem = sv ? r.occE : 0ULL;
+            while (rem) {
+                int fb;
+                const u64 range = next_piece(r, chunk, rem, fb);
+                if (sv & range) {
+                    const int32_t root = uf_find(L, cur_base + fb);
+                    uint32_t *fw = flags + img * fper + (root >> 5);
+                    const uint32_t bit = 1u << (root & 31);
+                    if (!(__ldcg(fw) & bit)) atomicOr(fw, bit);
+                }
+            }
+        }
+    }
+    if (MODE == 0) {
+        nroots = __reduce_add_sync(FULL, nroots);
+        if (lane == 0) row_count[(int64_t)img * g.bh + by] = nroots;
+    }
+}
+
+// one CTA per image: exclusive scan of the per-row root counts (in place), total -> n_roots[img]
+__global__ void __launch_bounds__(256) ccl_scan_kernel(int n, int32_t *cnt, int32_t *n_roots)
 {
     const int img = blockIdx.x;
-    int32_t *c = chunk_cnt + (int64_t)img * nchunks;
+    int32_t *c = cnt + (int64_t)img * n;
     __shared__ int ws[8];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < nchunks; base += 256) {
+    for (int base = 0; base < n; base += 256) {
         const int i = base + threadIdx.x;
-        const int v = (i < nchunks) ? c[i] : 0;
+        const int v = (i < n) ? c[i] : 0;
         int s = v;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int nb = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += nb; }
+        for (int d = 1; d < 32; d <<= 1) { int nb = __shfl_up_sync(FULL, s, d); if ((threadIdx.x & 31) >= d) s += nb; }
         if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
         __syncthreads();
         int woff = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += ws[w];
         const int excl = carry + woff + s - v;
-        if (i < nchunks) c[i] = excl;
+        if (i < n) c[i] = excl;
         __syncthreads();
         if (threadIdx.x == 255) carry = excl + v;
         __syncthreads();
@@ -190,31 +287,36 @@ __global__ void __launch_bounds__(256) ccl_scan_kernel(int nchunks, int32_t *chu
     if (threadIdx.x == 0) n_roots[img] = carry;
 }
 
-// roots get L[root] = -(label) - 1 with label = 1 + rank
-__global__ void __launch_bounds__(256) ccl_assign_kernel(int32_t *Lall, int64_t bper, int nblk, int nchunks, const int32_t *chunk_off)
+// roots get L[root] = -(label) - 1 with label = 1 + rank in block raster order
+__global__ void __launch_bounds__(256) rccl_assign_kernel(RowGeom g, int32_t *Lall, const u64 *rootbits, const int32_t *row_off)
 {
-    const int img = blockIdx.y, chunk = blockIdx.x;
-    int32_t *L = Lall + img * bper;
-    bool f[4];
-    const int cnt = count_roots4(L, nblk, chunk * CHUNK, threadIdx.x, f);
-    int s = cnt;
+    ROW_PROLOGUE(0)
+    (void)r0; (void)r1; (void)pbase;
+    if (!row_ok) return;
+    int32_t *L = Lall + img * g.bper + (int64_t)by * g.bw;
+    int base = row_off[(int64_t)img * g.bh + by];
+    for (int s = 0; s < g.nseg; ++s) {
+        const int chunk = s * 32 + lane;
+        u64 rb = (chunk < g.cpr) ? rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] : 0ULL;
+        const int n = __popcll(rb);
+        int incl = n;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int nb = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += nb; }
-    __shared__ int ws[8];
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += ws[w];
-    int rank = chunk_off[img * nchunks + chunk] + woff + s - cnt;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (f[j]) { L[chunk * CHUNK + 4 * threadIdx.x + j] = -(rank + 1) - 1; ++rank; }
+        for (int d = 1; d < 32; d <<= 1) { int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
+        int rank = base + incl - n;
+        while (rb) {
+            const int bx = chunk * 32 + ((__ffsll((long long)rb) - 1) >> 1);
+            rb &= rb - 1;
+            L[bx] = -(rank + 1) - 1;
+            ++rank;
+        }
+        base += __shfl_sync(FULL, incl, 31);
+    }
 }
 
 // ---- statistics ---------------------------------------------------------------------------
 struct StatAcc {          // SoA accumulators, [batch][cap]
     int32_t *minx, *miny, *maxx, *maxy, *area;
-    unsigned long long *sumx, *sumy;
+    u64 *sumx, *sumy;
     int cap;
 };
 
@@ -226,14 +328,38 @@ __global__ void stats_init_kernel(StatAcc a, int64_t n)
     a.sumx[i] = 0; a.sumy[i] = 0;
 }
 
-constexpr int NSLOT = 16;
+constexpr int NSLOT = 32;
 struct SlotCache {
     int key[NSLOT];
     int minx[NSLOT], miny[NSLOT], maxx[NSLOT], maxy[NSLOT], area[NSLOT];
-    unsigned int sumx[NSLOT], sumy[NSLOT];
+    u64 sumx[NSLOT], sumy[NSLOT];
 };
 
 struct Contrib { int minx, miny, maxx, maxy, area; unsigned int sumx, sumy; };
+
+// sum of the set bit positions of a 64-bit mask
+__device__ __forceinline__ unsigned pos_sum(u64 m)
+{
+    return (unsigned)__popcll(m & 0xAAAAAAAAAAAAAAAAULL) + 2u * __popcll(m & 0xCCCCCCCCCCCCCCCCULL) +
+           4u * __popcll(m & 0xF0F0F0F0F0F0F0F0ULL) + 8u * __popcll(m & 0xFF00FF00FF00FF00ULL) +
+           16u * __popcll(m & 0xFFFF0000FFFF0000ULL) + 32u * __popcll(m & 0xFFFFFFFF00000000ULL);
+}
+
+// pixels m0 (row y) and m1 (row y + 1) of a 64-pixel chunk starting at column x0; m0 | m1 != 0
+__device__ __forceinline__ Contrib contrib_of(u64 m0, u64 m1, int x0, int y)
+{
+    Contrib v;
+    const int n0 = __popcll(m0), n1 = __popcll(m1);
+    const u64 both = m0 | m1;
+    v.area = n0 + n1;
+    v.minx = x0 + __ffsll((long long)both) - 1;
+    v.maxx = x0 + 63 - __clzll((long long)both);
+    v.miny = m0 ? y : y + 1;
+    v.maxy = m1 ? y + 1 : y;
+    v.sumx = (unsigned)v.area * (unsigned)x0 + pos_sum(m0) + pos_sum(m1);
+    v.sumy = (unsigned)v.area * (unsigned)y + (unsigned)n1;
+    return v;
+}
 
 // Lanes in `peers` share `key`: reduce their contributions; the leader adds into the CTA cache or global.
 __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contrib v, SlotCache &sc, const StatAcc &a, int64_t img_off)
@@ -242,97 +368,122 @@ __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contri
     v.maxx = __reduce_max_sync(peers, v.maxx); v.maxy = __reduce_max_sync(peers, v.maxy);
     v.area = __reduce_add_sync(peers, v.area);
     v.sumx = __reduce_add_sync(peers, v.sumx); v.sumy = __reduce_add_sync(peers, v.sumy);
-    const int lane = threadIdx.x + threadIdx.y * 32;
-    if ((lane & 31) != __ffs(peers) - 1) return;
-    if (key >= a.cap) return;                       // over capacity: reported through n_labels
+    if ((int)(threadIdx.x & 31) != __ffs((int)peers) - 1) return;
+    if (key >= a.cap || v.area == 0) return;            // over capacity: reported through n_labels
     const int slot = key & (NSLOT - 1);
     const int old = atomicCAS(&sc.key[slot], -1, key);
     if (old == -1 || old == key) {
         atomicMin(&sc.minx[slot], v.minx); atomicMin(&sc.miny[slot], v.miny);
         atomicMax(&sc.maxx[slot], v.maxx); atomicMax(&sc.maxy[slot], v.maxy);
         atomicAdd(&sc.area[slot], v.area);
-        atomicAdd(&sc.sumx[slot], v.sumx); atomicAdd(&sc.sumy[slot], v.sumy);
+        atomicAdd(&sc.sumx[slot], (u64)v.sumx); atomicAdd(&sc.sumy[slot], (u64)v.sumy);
     } else {
         const int64_t i = img_off + key;
         atomicMin(&a.minx[i], v.minx); atomicMin(&a.miny[i], v.miny);
         atomicMax(&a.maxx[i], v.maxx); atomicMax(&a.maxy[i], v.maxy);
         atomicAdd(&a.area[i], v.area);
-        atomicAdd(&a.sumx[i], (unsigned long long)v.sumx); atomicAdd(&a.sumy[i], (unsigned long long)v.sumy);
+        atomicAdd(&a.sumx[i], (u64)v.sumx); atomicAdd(&a.sumy[i], (u64)v.sumy);
     }
 }
 
-__device__ __forceinline__ Contrib contrib_of(uint32_t px, int c, int r)
-{
-    Contrib v;
-    v.area = __popc(px);
-    const int nx1 = ((px >> 1) & 1) + ((px >> 3) & 1);     // pixels in column c+1
-    const int ny1 = ((px >> 2) & 1) + ((px >> 3) & 1);     // pixels in row r+1
-    v.sumx = (unsigned)(v.area * c + nx1);
-    v.sumy = (unsigned)(v.area * r + ny1);
-    v.minx = (px & 5u) ? c : c + 1;
-    v.maxx = (px & 10u) ? c + 1 : c;
-    v.miny = (px & 3u) ? r : r + 1;
-    v.maxy = (px & 12u) ? r + 1 : r;
-    return v;
-}
+// Per-warp staging for the optional label image: block labels and pixel words of one 2048-pixel segment.
+struct LabelStage { int32_t lab[1024]; u64 px[2][32]; };
 
 template <bool WRITE_LABELS>
-__global__ void __launch_bounds__(256) ccl_final_kernel(MaskAcc m, CclGeom g, const int32_t *Lall, Plane labels, StatAcc a)
+__global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
 {
     __shared__ SlotCache sc;
-    const int tid = threadIdx.x + threadIdx.y * 32;
-    if (tid < NSLOT) {
-        sc.key[tid] = -1; sc.minx[tid] = 0x7fffffff; sc.miny[tid] = 0x7fffffff; sc.maxx[tid] = -1; sc.maxy[tid] = -1;
-        sc.area[tid] = 0; sc.sumx[tid] = 0; sc.sumy[tid] = 0;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    if (threadIdx.x < NSLOT) {
+        const int t = threadIdx.x;
+        sc.key[t] = -1; sc.minx[t] = 0x7fffffff; sc.miny[t] = 0x7fffffff; sc.maxx[t] = -1; sc.maxy[t] = -1;
+        sc.area[t] = 0; sc.sumx[t] = 0; sc.sumy[t] = 0;
     }
     __syncthreads();
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    const bool inside = bx < g.bw && by < g.bh;
-    const int c = 2 * bx, r = 2 * by;
-    uint32_t px = 0, valid = 0;
-    int label = 0;
-    if (inside) {
-        px = block_px(m, img, c, r);
-        valid = 1u | (c + 1 < m.width ? 2u : 0u);
-        if (r + 1 < m.height) valid |= valid << 2;
-        if (px) {
-            const int32_t *L = Lall + img * g.bper;
-            int32_t v = L[by * g.bw + bx];
-            if (v >= 0) v = L[v];
-            label = -v - 1;
-        }
-        if (WRITE_LABELS) {
-            int32_t *row0 = (int32_t *)(labels.p + img * labels.bs + r * labels.rs) + c;
-            const int l0 = (px & 1u) ? label : 0, l1 = (px & 2u) ? label : 0;
-            const int l2 = (px & 4u) ? label : 0, l3 = (px & 8u) ? label : 0;
-            const bool al8 = ((labels.rs | (int64_t)(uintptr_t)labels.p | labels.bs) & 7) == 0;
-            if ((valid & 2u) && al8) *(int2 *)row0 = make_int2(l0, l1);
-            else { row0[0] = l0; if (valid & 2u) row0[1] = l1; }
-            if (valid & 4u) {
-                int32_t *row1 = (int32_t *)((uint8_t *)row0 + labels.rs);
-                if ((valid & 8u) && al8) *(int2 *)row1 = make_int2(l2, l3);
-                else { row1[0] = l2; if (valid & 8u) row1[1] = l3; }
+    ROW_PROLOGUE(0)
+    const int64_t img_off = (int64_t)img * a.cap;
+    if (row_ok) {
+        const int32_t *L = Lall + img * g.bper;
+        const int cur_base = by * g.bw;
+        const int y = 2 * by;
+        const bool has_row1 = y + 1 < g.height;
+        LabelStage *stage = WRITE_LABELS ? (LabelStage *)dyn_smem + (threadIdx.x >> 5) : nullptr;
+        RunCarry c{0u, -1};
+        for (int s = 0; s < g.nseg; ++s) {
+            const int chunk = s * 32 + lane;
+            const int x0 = 64 * chunk;
+            const u64 a0 = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
+            const Runs r = analyze_runs(a0 | a1, chunk, lane, c);
+            // background (label 0): all lanes reduce together
+            {
+                const int remw = g.width - x0;
+                const u64 vm = remw >= 64 ? ~0ULL : (remw <= 0 ? 0ULL : ((1ULL << remw) - 1ULL));
+                const u64 b0 = ~a0 & vm, b1 = has_row1 ? (~a1 & vm) : 0ULL;
+                Contrib v;
+                if (b0 | b1) v = contrib_of(b0, b1, x0, y);
+                else { v.minx = 0x7fffffff; v.miny = 0x7fffffff; v.maxx = -1; v.maxy = -1; v.area = 0; v.sumx = 0; v.sumy = 0; }
+                accumulate_group(FULL, 0, v, sc, a, img_off);
+            }
+            if (WRITE_LABELS) {
+                int4 *z = (int4 *)(stage->lab + lane * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = make_int4(0, 0, 0, 0);
+                stage->px[0][lane] = a0; stage->px[1][lane] = a1;
+            }
+            u64 rem = r.occE;
+            for (;;) {
+                const bool has = rem != 0;
+                const unsigned active = __ballot_sync(FULL, has);
+                if (!active) break;
+                if (has) {
+                    int fb;
+                    const int p = __ffsll((long long)rem) - 1;
+                    const u64 range = next_piece(r, chunk, rem, fb);
+                    int32_t v = L[cur_base + fb];
+                    if (v >= 0) v = L[v];
+                    const int label = -v - 1;
+                    if (WRITE_LABELS) {
+                        const int e = 64 - __clzll((long long)range);     // one past the last column of the piece
+                        for (int q = p; q < e; q += 2) stage->lab[lane * 32 + (q >> 1)] = label;
+                    }
+                    const unsigned peers = __match_any_sync(active, label);
+                    accumulate_group(peers, label, contrib_of(a0 & range, a1 & range, x0, y), sc, a, img_off);
+                }
+            }
+            if (WRITE_LABELS) {
+                __syncwarp();
+                const int seg_x = s * 2048;
+                for (int rr = 0; rr < (has_row1 ? 2 : 1); ++rr) {
+                    int32_t *lrow = (int32_t *)(labels.p + img * labels.bs + (int64_t)(y + rr) * labels.rs);
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int xx = 128 * i + 4 * lane;
+                        const int x = seg_x + xx;
+                        if (x >= g.width) continue;
+                        const uint32_t bits = (uint32_t)(stage->px[rr][xx >> 6] >> (xx & 63)) & 0xFu;
+                        const int l01 = stage->lab[xx >> 1], l23 = stage->lab[(xx >> 1) + 1];
+                        const int4 o = make_int4((bits & 1u) ? l01 : 0, (bits & 2u) ? l01 : 0, (bits & 4u) ? l23 : 0, (bits & 8u) ? l23 : 0);
+                        if (labels_al16 && x + 3 < g.width) *(int4 *)(lrow + x) = o;
+                        else {
+                            lrow[x] = o.x;
+                            if (x + 1 < g.width) lrow[x + 1] = o.y;
+                            if (x + 2 < g.width) lrow[x + 2] = o.z;
+                            if (x + 3 < g.width) lrow[x + 3] = o.w;
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
     }
-    const int64_t img_off = (int64_t)img * a.cap;
-    // foreground contribution, grouped by label
-    const unsigned fgm = __ballot_sync(0xffffffffu, px != 0);
-    if (px) {
-        const unsigned peers = __match_any_sync(fgm, label);
-        accumulate_group(peers, label, contrib_of(px, c, r), sc, a, img_off);
-    }
-    // background contribution (label 0)
-    const uint32_t bgpx = valid & ~px;
-    const unsigned bgm = __ballot_sync(0xffffffffu, bgpx != 0);
-    if (bgpx) accumulate_group(bgm, 0, contrib_of(bgpx, c, r), sc, a, img_off);
     __syncthreads();
-    if (tid < NSLOT && sc.key[tid] >= 0 && sc.area[tid] > 0) {
-        const int64_t i = img_off + sc.key[tid];
-        atomicMin(&a.minx[i], sc.minx[tid]); atomicMin(&a.miny[i], sc.miny[tid]);
-        atomicMax(&a.maxx[i], sc.maxx[tid]); atomicMax(&a.maxy[i], sc.maxy[tid]);
-        atomicAdd(&a.area[i], sc.area[tid]);
-        atomicAdd(&a.sumx[i], (unsigned long long)sc.sumx[tid]); atomicAdd(&a.sumy[i], (unsigned long long)sc.sumy[tid]);
+    if (threadIdx.x < NSLOT && sc.key[threadIdx.x] >= 0 && sc.area[threadIdx.x] > 0) {
+        const int t = threadIdx.x;
+        const int64_t i = img_off + sc.key[t];
+        atomicMin(&a.minx[i], sc.minx[t]); atomicMin(&a.miny[i], sc.miny[t]);
+        atomicMax(&a.maxx[i], sc.maxx[t]); atomicMax(&a.maxy[i], sc.maxy[t]);
+        atomicAdd(&a.area[i], sc.area[t]);
+        atomicAdd(&a.sumx[i], sc.sumx[t]); atomicAdd(&a.sumy[i], sc.sumy[t]);
     }
 }
 
@@ -357,116 +508,134 @@ __global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int bat
     }
 }
 
-// ---- hysteresis kernels ----------------------------------------------------------------------
-// mark the root of every block that holds a strong (class 2) pixel: L[root] = -(root) - 2
-__global__ void __launch_bounds__(256) hyst_flag_kernel(Plane cls, int width, int height, CclGeom g, int32_t *Lall)
-{
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    if (bx >= g.bw || by >= g.bh) return;
-    const int c = 2 * bx, r = 2 * by;
-    const uint8_t *row = cls.p + img * cls.bs + r * cls.rs + c;
-    bool strong = row[0] == 2;
-    if (c + 1 < width) strong |= row[1] == 2;
-    if (r + 1 < height) { strong |= row[cls.rs] == 2; if (c + 1 < width) strong |= row[cls.rs + 1] == 2; }
-    if (!strong) return;
-    int32_t *L = Lall + img * g.bper;
-    const int32_t b = by * g.bw + bx;
-    const int32_t v = L[b];
-    if (v < -1) return;              // this block is a root already marked
-    L[v] = -v - 2;                   // v is the (compressed) root index; benign race, same value
-}
+// ---- hysteresis output -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
+// keep the pixels of every run piece whose component was flagged (holds a strong pixel)
 template <bool OUT_BITS>
-__global__ void __launch_bounds__(256) hyst_final_kernel(Plane cls, int width, int height, CclGeom g, const int32_t *Lall,
-                                                         Plane out, BitPlane obits, bool or_bits)
+__global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const int32_t *Lall, const uint32_t *flags, int64_t fper,
+                                                              Plane out, bool out_al16, BitPlane obits, bool or_bits)
 {
-    // thread per block as elsewhere; for bit output a half-warp of 16 blocks forms one 32-bit word per row
-    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    const bool inside = bx < g.bw && by < g.bh;
-    const int c = 2 * bx, r = 2 * by;
-    uint32_t keep = 0;    // bit0 (r,c), bit1 (r,c+1), bit2 (r+1,c), bit3 (r+1,c+1)
-    if (inside) {
-        const uint8_t *row = cls.p + img * cls.bs + r * cls.rs + c;
-        uint32_t px = row[0] != 0;
-        if (c + 1 < width) px |= (row[1] != 0) << 1;
-        if (r + 1 < height) { px |= (row[cls.rs] != 0) << 2; if (c + 1 < width) px |= (row[cls.rs + 1] != 0) << 3; }
-        if (px) {
-            const int32_t *L = Lall + img * g.bper;
-            int32_t v = L[by * g.bw + bx];
-            if (v >= 0) v = L[v];
-            if (v < -1) keep = px;
+    ROW_PROLOGUE(0)
+    if (!row_ok) return;
+    const int32_t *L = Lall + img * g.bper;
+    const uint32_t *F = flags + img * fper;
+    const int cur_base = by * g.bw;
+    const int y = 2 * by;
+    const bool has_row1 = y + 1 < g.height;
+    RunCarry c{0u, -1};
+    for (int s = 0; s < g.nseg; ++s) {
+        const int chunk = s * 32 + lane;
+        const u64 a0 = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
+        const Runs r = analyze_runs(a0 | a1, chunk, lane, c);
+        u64 keep = 0, rem = r.occE;
+        while (rem) {
+            int fb;
+            const u64 range = next_piece(r, chunk, rem, fb);
+            const int32_t root = L[cur_base + fb];          // fully compressed by rccl_compress_kernel<1>
+            if ((F[root >> 5] >> (root & 31)) & 1u) keep |= range;
         }
-    }
-    if (OUT_BITS) {
-        // lanes 0-15 and 16-31 each cover 32 consecutive pixels
-        uint32_t w0 = (keep & 3u) << (2 * (threadIdx.x & 15));
-        uint32_t w1 = ((keep >> 2) & 3u) << (2 * (threadIdx.x & 15));
+        if (chunk >= g.cpr) continue;
+        const u64 o0 = a0 & keep, o1 = a1 & keep;
+        if (OUT_BITS) {
+            uint2 *p0 = (uint2 *)(obits.p + img * obits.bs + (int64_t)y * obits.wpr) + chunk;
+            uint2 w0 = make_uint2((uint32_t)o0, (uint32_t)(o0 >> 32));
+            if (or_bits) { const uint2 e = *p0; w0.x |= e.x; w0.y |= e.y; }
+            *p0 = w0;
+            if (has_row1) {
+                uint2 *p1 = (uint2 *)((uint32_t *)p0 + obits.wpr);
+                uint2 w1 = make_uint2((uint32_t)o1, (uint32_t)(o1 >> 32));
+                if (or_bits) { const uint2 e = *p1; w1.x |= e.x; w1.y |= e.y; }
+                *p1 = w1;
+            }
+        } else {
+            const int x0 = 64 * chunk;
+            for (int rr = 0; rr < (has_row1 ? 2 : 1); ++rr) {
+                const u64 o = rr ? o1 : o0;
+                uint8_t *orow = out.p + img * out.bs + (int64_t)(y + rr) * out.rs + x0;
+                if (out_al16 && x0 + 64 <= g.width) {
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) { w0 |= __shfl_xor_sync(0xffffffffu, w0, d); w1 |= __shfl_xor_sync(0xffffffffu, w1, d); }
-        if (inside && (threadIdx.x & 15) == 0) {
-            uint32_t *p0 = obits.p + img * obits.bs + (int64_t)r * obits.wpr + (c >> 5);
-            *p0 = or_bits ? (*p0 | w0) : w0;
-            if (r + 1 < height) { uint32_t *p1 = p0 + obits.wpr; *p1 = or_bits ? (*p1 | w1) : w1; }
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t h = (uint32_t)(o >> (16 * q)) & 0xFFFFu;
+                        ((uint4 *)orow)[q] = make_uint4(bytes_of_nibble(h & 15u), bytes_of_nibble((h >> 4) & 15u),
+                                                        bytes_of_nibble((h >> 8) & 15u), bytes_of_nibble(h >> 12));
+                    }
+                } else {
+                    const int n = min(64, g.width - x0);
+                    for (int j = 0; j < n; ++j) orow[j] = ((o >> j) & 1ULL) ? 255 : 0;
+                }
+            }
         }
-    } else if (inside) {
-        uint8_t *orow = out.p + img * out.bs + r * out.rs + c;
-        orow[0] = (keep & 1u) ? 255 : 0;
-        if (c + 1 < width) orow[1] = (keep & 2u) ? 255 : 0;
-        if (r + 1 < height) { orow[out.rs] = (keep & 4u) ? 255 : 0; if (c + 1 < width) orow[out.rs + 1] = (keep & 8u) ? 255 : 0; }
     }
 }
 
-MaskAcc mask_acc(const CclMask &m)
+RowGeom geom_of(BitPlane bits, int width, int height)
 {
-    MaskAcc a;
-    if (m.u8) { a.p = (const uint8_t *)m.u8->data; a.rs = m.u8->row_stride; a.bs = m.u8->batch_stride; a.bits = nullptr; a.wpr = 0; a.wbs = 0; }
-    else { a.p = nullptr; a.rs = 0; a.bs = 0; a.bits = m.bits.p; a.wpr = m.bits.wpr; a.wbs = m.bits.bs; }
-    a.width = m.width; a.height = m.height;
-    return a;
+    RowGeom g;
+    g.bits = bits.p; g.wpr = bits.wpr; g.wbs = bits.bs;
+    g.width = width; g.height = height;
+    g.bw = (width + 1) / 2; g.bh = (height + 1) / 2;
+    g.bper = (int64_t)align_up((size_t)g.bw * g.bh, 4);
+    g.nseg = cdiv(width, 2048);
+    g.cpr = cdiv(width, 64);
+    return g;
 }
 
-CclGeom geom_of(int width, int height)
+inline dim3 row_grid(const RowGeom &g, int batch, int first_row) { return dim3(cdiv(g.bh - first_row, ROWS_PER_CTA), batch); }
+
+// init + merge: after this every run start's parent chain ends at the root of its component
+int run_union_find(synseg_ctx *ctx, const RowGeom &g, int batch, int32_t *L, cudaStream_t st)
 {
-    CclGeom g;
-    g.bw = (width + 1) / 2; g.bh = (height + 1) / 2; g.nblk = g.bw * g.bh;
-    g.bper = (int64_t)align_up((size_t)g.bw * g.bh, 4);
-    return g;
+    rccl_init_kernel<<<row_grid(g, batch, 0), 256, 0, st>>>(g, L);
+    SS_LAUNCH_CHECK(ctx, "ccl_init", st);
+    if (g.bh > 1) {
+        rccl_merge_kernel<<<row_grid(g, batch, 1), 256, 0, st>>>(g, L);
+        SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
+    }
+    return SYNSEG_OK;
 }
 
 }  // namespace
 
 size_t ccl_label_scratch_bytes(int width, int height, int batch)
 {
-    CclGeom g = geom_of(width, height);
-    return (size_t)g.bper * batch * sizeof(int32_t);
+    const int64_t bw = (width + 1) / 2, bh = (height + 1) / 2;
+    return align_up((size_t)(bw * bh), 4) * batch * sizeof(int32_t) + 256;
 }
 
-int run_ccl_core(synseg_ctx *ctx, const CclMask &m, int32_t *L, cudaStream_t st)
+size_t hysteresis_scratch_bytes(int width, int height, int batch)
 {
-    const MaskAcc a = mask_acc(m);
-    const CclGeom g = geom_of(m.width, m.height);
-    dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), m.batch);
-    ccl_init_kernel<<<grid, block, 0, st>>>(a, g, L);
-    SS_LAUNCH_CHECK(ctx, "ccl_init", st);
-    ccl_merge_kernel<<<grid, block, 0, st>>>(a, g, L);
-    SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
-    const int64_t n = g.bper * m.batch;
-    ccl_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(n, L, g.bper, g.nblk);
-    SS_LAUNCH_CHECK(ctx, "ccl_compress", st);
-    return SYNSEG_OK;
+    const int64_t bw = (width + 1) / 2, bh = (height + 1) / 2;
+    return ccl_label_scratch_bytes(width, height, batch) + (size_t)cdiv(bw * bh, 32) * 4 * batch + 512;
+}
+
+size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels)
+{
+    const int64_t bh = (height + 1) / 2;
+    const size_t plane = (size_t)bit_wpr(width) * height * batch * 4 + 256;      // packed copy of a u8 mask
+    return ccl_label_scratch_bytes(width, height, batch) + plane + (size_t)bh * cdiv(width, 64) * 8 * batch + (size_t)bh * batch * 4 +
+           (size_t)batch * max_labels * 36 + (size_t)batch * 4 + 16 * 256;
 }
 
 int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, int32_t *n_labels, int32_t *stats,
                   double *centroids, int32_t max_labels, cudaStream_t st)
 {
-    const CclGeom g = geom_of(m.width, m.height);
     const int batch = m.batch;
-    const int nchunks = cdiv(g.bper, CHUNK);
     void *p;
+    BitPlane bits = m.bits;
+    if (m.u8) {
+        const int wpr = bit_wpr(m.width);
+        SS_TRY(arena_alloc(ctx, (size_t)wpr * m.height * batch * 4, &p, st));
+        bits = BitPlane{(uint32_t *)p, wpr, (int64_t)wpr * m.height};
+        SS_TRY(launch_pack_bits(ctx, m.u8, bits, st));
+    }
+    const RowGeom g = geom_of(bits, m.width, m.height);
     SS_TRY(arena_alloc(ctx, (size_t)g.bper * batch * 4, &p, st));
     int32_t *L = (int32_t *)p;
-    SS_TRY(arena_alloc(ctx, (size_t)nchunks * batch * 4, &p, st));
-    int32_t *chunk_cnt = (int32_t *)p;
+    SS_TRY(arena_alloc(ctx, (size_t)g.bh * g.cpr * 8 * batch, &p, st));
+    u64 *rootbits = (u64 *)p;
+    SS_TRY(arena_alloc(ctx, (size_t)g.bh * batch * 4, &p, st));
+    int32_t *row_count = (int32_t *)p;
     SS_TRY(arena_alloc(ctx, (size_t)batch * 4, &p, st));
     int32_t *n_roots = (int32_t *)p;
     StatAcc a;
@@ -477,48 +646,51 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
     SS_TRY(arena_alloc(ctx, nacc * 4, &p, st)); a.maxx = (int32_t *)p;
     SS_TRY(arena_alloc(ctx, nacc * 4, &p, st)); a.maxy = (int32_t *)p;
     SS_TRY(arena_alloc(ctx, nacc * 4, &p, st)); a.area = (int32_t *)p;
-    SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumx = (unsigned long long *)p;
-    SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumy = (unsigned long long *)p;
+    SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumx = (u64 *)p;
+    SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumy = (u64 *)p;
 
-    SS_TRY(run_ccl_core(ctx, m, L, st));
-    ccl_count_kernel<<<dim3(nchunks, batch), 256, 0, st>>>(L, g.bper, g.nblk, nchunks, chunk_cnt);
-    SS_LAUNCH_CHECK(ctx, "ccl_count", st);
-    ccl_scan_kernel<<<batch, 256, 0, st>>>(nchunks, chunk_cnt, n_roots);
+    SS_TRY(run_union_find(ctx, g, batch, L, st));
+    const dim3 grid = row_grid(g, batch, 0);
+    rccl_compress_kernel<0><<<grid, 256, 0, st>>>(g, L, rootbits, row_count, BitPlane{nullptr, 0, 0}, nullptr, 0);
+    SS_LAUNCH_CHECK(ctx, "ccl_compress", st);
+    ccl_scan_kernel<<<batch, 256, 0, st>>>(g.bh, row_count, n_roots);
     SS_LAUNCH_CHECK(ctx, "ccl_scan", st);
-    ccl_assign_kernel<<<dim3(nchunks, batch), 256, 0, st>>>(L, g.bper, g.nblk, nchunks, chunk_cnt);
+    rccl_assign_kernel<<<grid, 256, 0, st>>>(g, L, rootbits, row_count);
     SS_LAUNCH_CHECK(ctx, "ccl_assign", st);
     stats_init_kernel<<<(unsigned)cdiv(nacc, 256), 256, 0, st>>>(a, (int64_t)nacc);
     SS_LAUNCH_CHECK(ctx, "stats_init", st);
-    const MaskAcc ma = mask_acc(m);
-    dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), batch);
-    if (labels) ccl_final_kernel<true><<<grid, block, 0, st>>>(ma, g, L, plane_of(labels), a);
-    else ccl_final_kernel<false><<<grid, block, 0, st>>>(ma, g, L, Plane{nullptr, 0, 0}, a);
+    if (labels) {
+        const bool al16 = plane_aligned(labels, 16);
+        rccl_final_kernel<true><<<grid, 256, ROWS_PER_CTA * sizeof(LabelStage), st>>>(g, L, plane_of(labels), al16, a);
+    } else {
+        rccl_final_kernel<false><<<grid, 256, 0, st>>>(g, L, Plane{nullptr, 0, 0}, false, a);
+    }
     SS_LAUNCH_CHECK(ctx, "ccl_final", st);
     stats_finalize_kernel<<<dim3(cdiv(max_labels, 128), batch), 128, 0, st>>>(a, n_roots, batch, n_labels, stats, centroids);
     SS_LAUNCH_CHECK(ctx, "stats_finalize", st);
     return SYNSEG_OK;
 }
 
-size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels)
+int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, int height, int batch, const synseg_img *edges_u8,
+                   BitPlane edges_bits, bool or_bits, cudaStream_t st)
 {
-    CclGeom g = geom_of(width, height);
-    return (size_t)g.bper * batch * 4 + (size_t)cdiv(g.bper, CHUNK) * batch * 4 + (size_t)batch * max_labels * 36 + 16 * 256 + batch * 4;
-}
-
-int run_hysteresis(synseg_ctx *ctx, const synseg_img *cls, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
-                   cudaStream_t st)
-{
-    CclMask m; m.u8 = cls; m.bits = BitPlane{nullptr, 0, 0}; m.width = cls->width; m.height = cls->height; m.batch = cls->batch;
-    const CclGeom g = geom_of(m.width, m.height);
+    const RowGeom g = geom_of(kept, width, height);
     void *p;
-    SS_TRY(arena_alloc(ctx, (size_t)g.bper * m.batch * 4, &p, st));
+    SS_TRY(arena_alloc(ctx, (size_t)g.bper * batch * 4, &p, st));
     int32_t *L = (int32_t *)p;
-    SS_TRY(run_ccl_core(ctx, m, L, st));
-    dim3 block(32, 8), grid(cdiv(g.bw, 32), cdiv(g.bh, 8), m.batch);
-    hyst_flag_kernel<<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L);
+    const int64_t fper = cdiv((int64_t)g.bw * g.bh, 32);
+    SS_TRY(arena_alloc(ctx, (size_t)fper * 4 * batch, &p, st));
+    uint32_t *flags = (uint32_t *)p;
+    SS_CUDA(cudaMemsetAsync(flags, 0, (size_t)fper * 4 * batch, st));
+    SS_TRY(run_union_find(ctx, g, batch, L, st));
+    const dim3 grid = row_grid(g, batch, 0);
+    rccl_compress_kernel<1><<<grid, 256, 0, st>>>(g, L, nullptr, nullptr, strong, flags, fper);
     SS_LAUNCH_CHECK(ctx, "hyst_flag", st);
-    if (edges_u8) hyst_final_kernel<false><<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L, plane_of(edges_u8), BitPlane{nullptr, 0, 0}, false);
-    else hyst_final_kernel<true><<<grid, block, 0, st>>>(plane_of(cls), m.width, m.height, g, L, Plane{nullptr, 0, 0}, edges_bits, or_bits);
+    if (edges_u8)
+        rccl_hyst_final_kernel<false><<<grid, 256, 0, st>>>(g, L, flags, fper, plane_of(edges_u8), plane_aligned(edges_u8, 16),
+                                                             BitPlane{nullptr, 0, 0}, false);
+    else
+        rccl_hyst_final_kernel<true><<<grid, 256, 0, st>>>(g, L, flags, fper, Plane{nullptr, 0, 0}, false, edges_bits, or_bits);
     SS_LAUNCH_CHECK(ctx, "hyst_final", st);
     return SYNSEG_OK;
 }
@@ -537,6 +709,7 @@ extern "C" SYNSEG_EXPORT int synseg_ccl_stats(synseg_ctx *ctx, const synseg_img 
     }
     if (!n_labels || !stats || !centroids || max_labels < 1) { synseg_set_error("synseg_ccl_stats: bad result buffers"); return SYNSEG_E_INVALID; }
     if (mask->width > 32766 || mask->height > 32766) { synseg_set_error("synseg_ccl_stats: image larger than 32766"); return SYNSEG_E_INVALID; }
+    if (mask->batch > 65535) { synseg_set_error("synseg_ccl_stats: batch > 65535"); return SYNSEG_E_INVALID; }
     SS_TRY(arena_ensure(ctx, ccl_stats_scratch_bytes(mask->width, mask->height, mask->batch, max_labels)));
     arena_begin(ctx);
     CclMask m; m.u8 = mask; m.bits = BitPlane{nullptr, 0, 0}; m.width = mask->width; m.height = mask->height; m.batch = mask->batch;

@@ -105,8 +105,8 @@ int launch_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gr
 int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *out_u8, BitPlane out_bits,
                          int block_size, int C, int invert, cudaStream_t st);
 
-// Canny stage 1: grey -> class map (0 suppressed, 1 weak, 2 strong), u8 plane with W x H x batch.
-int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *cls, int lo, int hi, cudaStream_t st);
+// Canny stage 1: grey -> two bit planes: kept (survived non-maximum suppression, mag > lo) and strong (kept, mag > hi).
+int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept, BitPlane strong, int lo, int hi, cudaStream_t st);
 // Full Canny.  Exactly one of edges_u8 / edges_bits receives the result (the other NULL / {nullptr}).
 // or_bits: when edges_bits is given, OR into it instead of overwriting.
 int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
@@ -140,16 +140,14 @@ struct CclMask {
     BitPlane bits;         // used when u8 == NULL
     int width, height, batch;
 };
-// Block union-find core: fills blk_labels (int32 per 2x2 block, [batch][bh][bw]) with the root block
-// index of every block (fully compressed); background blocks hold -1.
-int run_ccl_core(synseg_ctx *ctx, const CclMask &m, int32_t *blk_labels, cudaStream_t st);
 int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, int32_t *n_labels, int32_t *stats,
                   double *centroids, int32_t max_labels, cudaStream_t st);
-// Hysteresis: keep pixels of cls (non-zero) whose component holds a class-2 pixel.
-int run_hysteresis(synseg_ctx *ctx, const synseg_img *cls, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
-                   cudaStream_t st);
+// Hysteresis: keep the pixels of `kept` whose 8-connected component (through kept pixels) holds a `strong` pixel.
+int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, int height, int batch, const synseg_img *edges_u8,
+                   BitPlane edges_bits, bool or_bits, cudaStream_t st);
 
 size_t ccl_label_scratch_bytes(int width, int height, int batch);
+size_t hysteresis_scratch_bytes(int width, int height, int batch);
 size_t canny_scratch_bytes(int width, int height, int batch);
 size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels);
 

@@ -151,7 +151,9 @@ def test_streaming_equals_direct(ctx):
     for i, hb in enumerate(batches):
         n, stats, _ = det.detect_components(hb.cuda())
         assert torch.equal(got[i][0], n.cpu())
-        assert torch.equal(got[i][1][:, :64], stats[:, :64].cpu())
+        for j in range(n.shape[0]):          # rows past n_labels are never written by the library
+            k = min(int(n[j]), 64)
+            assert k > 0 and torch.equal(got[i][1][j, :k], stats[j, :k].cpu())
 
 
 def test_dedup_finds_repeated_figures(ctx):
