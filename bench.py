@@ -263,7 +263,7 @@ def main():
     # ---- end to end: pinned host pages -> H2D -> pipeline -> D2H -> host box filter/merge ---------------------
     e2e = None
     if not args.no_e2e:
-        streamer = PageStreamer(det, B, h, w, slots=2)
+        streamer = PageStreamer(det, B, h, w, slots=3)
         pw, ph = w * 72.0 / args.dpi, h * 72.0 / args.dpi
         n_regions = [0]
 
@@ -283,9 +283,21 @@ def main():
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dt = float(td.item())
+        # the PCIe bound of this step: the same pinned batch copied alone (no compute), CUDA events
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        streamer.dev_pages[0].copy_(host_pages, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(3):
+            streamer.dev_pages[0].copy_(host_pages, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_ms = c0.elapsed_time(c1) / 3
         e2e = {"value": world * K * B / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // K,
                "d2h_bytes_per_step": streamer.d2h_bytes // K, "ms_per_step": 1000.0 * dt / K,
-               "includes": "pinned H2D, fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
+               "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": host_pages.numel() / h2d_ms / 1e6,
+               "frac_of_pcie_bound": h2d_ms / (1000.0 * dt / K),
+               "includes": "pinned H2D (3 slots, copy stream), fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
         del streamer
 
     # ---- per-kernel timing of profiled steps (same run, same stream) -> roofline of the dominant kernel -------

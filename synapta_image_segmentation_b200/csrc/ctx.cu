@@ -1,6 +1,7 @@
 // ctx.cu -- context, scratch arena, error reporting.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "internal.cuh"
 
@@ -43,6 +44,9 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->arena = nullptr; c->arena_bytes = 0; c->arena_top = 0; c->launches = 0; c->phash_basis = nullptr;
     c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
+    const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
+    c->tune_ad_band = e1 ? atoi(e1) : 0;
+    c->tune_canny_band = e2 ? atoi(e2) : 0;
     c->sm_count = prop.multiProcessorCount;
     // integer DCT basis of the perceptual hash (same formula as oracle/synseg_oracle.c:orc_phash_basis)
     int32_t basis[8 * 32];

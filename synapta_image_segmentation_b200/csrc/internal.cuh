@@ -26,6 +26,8 @@ struct synseg_ctx {
     size_t arena_top;     // bump pointer, reset at the start of every public call
     int64_t launches;     // kernels launched through this context
     int32_t *phash_basis; // device int32[8*32]
+    int tune_ad_band;     // experiment knobs (env SYNSEG_TUNE_AD_BAND / SYNSEG_TUNE_CANNY_BAND), 0 = automatic
+    int tune_canny_band;
     // optional per-kernel timing (synseg_profile_*): one event after every launch on the profiled stream
     bool prof_on;
     cudaEvent_t prof_start;

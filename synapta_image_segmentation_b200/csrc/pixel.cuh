@@ -44,3 +44,25 @@ __device__ __forceinline__ bool hsv_mask_px(uint32_t r, uint32_t g, uint32_t b, 
     const uint32_t s = ((v - mn) * sdiv_tab[v] + 2048u) >> 12;
     return s > 30u && v > 40u && v < 240u;
 }
+
+// 16 consecutive grey pixels of a row starting at column x (any x), replicated outside [0, W)
+// (BORDER_REPLICATE).  `aligned`: row base and stride are 16-byte aligned (x must then be a multiple of 16).
+__device__ __forceinline__ uint4 load16_rep(const uint8_t *row, int x, int W, bool aligned)
+{
+    if (aligned && x >= 0 && x + 15 < W) return __ldg((const uint4 *)(row + x));
+    if (x + 15 < 0 || x >= W) {
+        const uint32_t b = (uint32_t)__ldg(row + (x < 0 ? 0 : W - 1)) * 0x01010101u;
+        return make_uint4(b, b, b, b);
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        w[q] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = min(max(x + 4 * q + j, 0), W - 1);
+            w[q] |= (uint32_t)__ldg(row + c) << (8 * j);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}

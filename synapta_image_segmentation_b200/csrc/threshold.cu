@@ -5,16 +5,25 @@
 //          mean = floor((2s + n) / 2n) exactly),
 //   THRESH_BINARY: 255 iff g - mean > -C ;  THRESH_BINARY_INV: 255 iff g - mean <= -C.
 //
-// Roofline: HBM-bound, 2 algorithmic bytes per pixel (1 read + 1 written).
-// Design: a CTA owns a strip of columns and a band of rows and marches down the band keeping the
-// vertical running column sums (new row in, old row out) in registers, 4 columns per thread.
-// Each row the horizontal window sums come from one block-wide inclusive scan of the column sums
-// (local 4 + warp shuffle scan + cross-warp redux) parked in shared memory: S = P[x+r] - P[x-r-1].
-// Every source byte is fetched from HBM once (the second, "row out", read hits L2); no integral
-// image is ever written.  Output is either a u8 {0,255} plane or a bit plane (8 lanes -> 1 word).
+// Roofline: HBM-bound, 2 algorithmic bytes per pixel with a u8 output (1 read + 1 written), 1.125 with
+// the bit-plane output the page pipeline uses.
+// Design: warp-autonomous strips, no block-level barrier.  A warp owns a strip of 512 columns (16 per
+// lane, one 128-bit load per lane and row) and marches down a band of rows keeping the vertical running
+// column sums (row y+r+1 in, row y-r out) in registers, two 16-bit sums per register (255 rows x 255 fit).
+// Each row the horizontal window sums come from a warp-wide inclusive prefix of the column sums (local
+// prefix + shuffle scan) parked in a transposed, conflict-free shared-memory tile: S = P[x+r] - P[x-r-1].
+// The threshold test needs no division: mean >= g + C  <=>  2s + n >= 2n (g + C).
+// Every source byte comes from HBM once; the "row out" and centre-row reads of a band hit L2.
+// Output is either a u8 {0,255} plane or a bit plane (two lanes -> one 32-bit word).
 #include "internal.cuh"
+#include "pixel.cuh"
 
 namespace {
+
+constexpr int CPL = 16;                 // columns per lane
+constexpr int SW = 32 * CPL;            // columns per warp strip
+constexpr int AD_WARPS = 4;             // independent warps per CTA
+constexpr unsigned FULL = 0xffffffffu;
 
 struct AdParams {
     Plane src;
@@ -22,124 +31,120 @@ struct AdParams {
     BitPlane bits;   // bit output (OUT_BITS = true)
     int width, height;
     int r;           // bs / 2
-    int lead;        // round_up(r, 32): columns of left halo the strip carries
+    int lead;        // round_up(r + 1, 32): columns of left halo the strip carries
     int out_w;       // output columns per strip (multiple of 32)
-    int strips;
-    int bands;
-    int band_h;
-    int C;
+    int strips, bands, band_h;
+    int n, n2;       // bs * bs, 2 * bs * bs
+    int C;           // clamped to [-256, 256] (g - mean lies in [-255, 255])
     int invert;
-    uint32_t n;      // bs * bs
-    uint64_t magic;  // ceil(2^48 / 2n)
+    int64_t tasks;   // batch * bands * strips
 };
 
-__device__ __forceinline__ uint32_t load4_clamped(const uint8_t *row, int cx, int width, bool aligned)
+// cs[2q] holds columns 4q (low half) and 4q+2 (high half); cs[2q+1] columns 4q+1 and 4q+3
+__device__ __forceinline__ void add16(uint32_t cs[8], const uint4 v)
 {
-    if (aligned && cx >= 0 && cx + 3 < width) return __ldg((const uint32_t *)(row + cx));
-    uint32_t v = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int c = min(max(cx + j, 0), width - 1);
-        v |= (uint32_t)__ldg(row + c) << (8 * j);
-    }
-    return v;
+    cs[0] += v.x & 0x00FF00FFu; cs[1] += (v.x >> 8) & 0x00FF00FFu;
+    cs[2] += v.y & 0x00FF00FFu; cs[3] += (v.y >> 8) & 0x00FF00FFu;
+    cs[4] += v.z & 0x00FF00FFu; cs[5] += (v.z >> 8) & 0x00FF00FFu;
+    cs[6] += v.w & 0x00FF00FFu; cs[7] += (v.w >> 8) & 0x00FF00FFu;
+}
+__device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
+{
+    cs[0] -= v.x & 0x00FF00FFu; cs[1] -= (v.x >> 8) & 0x00FF00FFu;
+    cs[2] -= v.y & 0x00FF00FFu; cs[3] -= (v.y >> 8) & 0x00FF00FFu;
+    cs[4] -= v.z & 0x00FF00FFu; cs[5] -= (v.z >> 8) & 0x00FF00FFu;
+    cs[6] -= v.w & 0x00FF00FFu; cs[7] -= (v.w >> 8) & 0x00FF00FFu;
 }
 
+__device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
 template <bool OUT_BITS>
-__global__ void __launch_bounds__(1024) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
+__global__ void __launch_bounds__(32 * AD_WARPS) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
 {
-    extern __shared__ uint32_t smem[];
-    const int T = blockDim.x;
-    const int ncols = 4 * T;
-    uint32_t *P[2] = {smem, smem + (ncols + 1)};             // inclusive prefix with P[0] = 0
-    uint32_t *wt[2] = {smem + 2 * (ncols + 1), smem + 2 * (ncols + 1) + 32};
+    __shared__ uint32_t Psm[AD_WARPS][2][16 * 33];   // [column within lane][lane], padded: conflict-free both ways
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t task = (int64_t)blockIdx.x * AD_WARPS + warp;
+    if (task >= p.tasks) return;                      // warp-uniform
+    const int strip = (int)(task % p.strips); task /= p.strips;
+    const int band = (int)(task % p.bands);
+    const int img = (int)(task / p.bands);
 
-    int bid = blockIdx.x;
-    const int band = bid % p.bands; bid /= p.bands;
-    const int strip = bid % p.strips;
-    const int img = bid / p.strips;
-
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int x_strip = strip * p.out_w;
-    const int cx = x_strip - p.lead + 4 * t;                 // first of this thread's 4 columns
-    const int y0 = band * p.band_h;
-    const int y1 = min(y0 + p.band_h, p.height);
+    const int W = p.width, H = p.height, r = p.r;
+    const int x = strip * p.out_w - p.lead + CPL * lane;     // first of this lane's 16 columns
+    const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
     const uint8_t *base = p.src.p + img * p.src.bs;
-    const int r = p.r, H = p.height, W = p.width;
-
-    if (t == 0) { P[0][0] = 0; P[1][0] = 0; }
+    const bool live = x <= W - 1 + r;                        // columns further right feed no output
+    const bool out_lane = (CPL * lane >= p.lead) && (CPL * lane < p.lead + p.out_w) && (x < W);
 
     // running column sums over rows [y - r, y + r] (replicate)
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    for (int dy = -r; dy <= r; ++dy) {
-        int yy = min(max(y0 + dy, 0), H - 1);
-        uint32_t v = load4_clamped(base + yy * p.src.rs, cx, W, src_aligned);
-        c0 += v & 255; c1 += (v >> 8) & 255; c2 += (v >> 16) & 255; c3 += v >> 24;
+    uint32_t cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+#pragma unroll 4
+        for (int dy = -r; dy <= r; ++dy) {
+            const int yy = min(max(y0 + dy, 0), H - 1);
+            add16(cs, load16_rep(base + (int64_t)yy * p.src.rs, x, W, src_aligned));
+        }
     }
-
-    const bool out_thread = (4 * t >= p.lead) && (4 * t < p.lead + p.out_w) && (cx < W);
-    const int li = 4 * t;   // local column index of c0
+    const int kx = CPL * lane + r, ky = CPL * lane - r - 1;  // prefix indices of column j: kx + j, ky + j
 
     for (int y = y0; y < y1; ++y) {
-        const int buf = y & 1;
-        // issue next iteration's loads early
-        const int yn = min(y + r + 1, H - 1), yo = max(y - r, 0);
-        uint32_t vnew = load4_clamped(base + yn * p.src.rs, cx, W, src_aligned);
-        uint32_t vold = load4_clamped(base + yo * p.src.rs, cx, W, src_aligned);
-        uint32_t vcen = 0;
-        if (out_thread) vcen = load4_clamped(base + (int64_t)y * p.src.rs, cx, W, src_aligned);
+        uint32_t *Pb = Psm[warp][y & 1];
+        uint4 vnew = make_uint4(0, 0, 0, 0), vold = vnew, vcen = vnew;
+        if (live) {
+            vnew = load16_rep(base + (int64_t)min(y + r + 1, H - 1) * p.src.rs, x, W, src_aligned);
+            vold = load16_rep(base + (int64_t)max(y - r, 0) * p.src.rs, x, W, src_aligned);
+        }
+        if (out_lane) vcen = load16_rep(base + (int64_t)y * p.src.rs, x, W, src_aligned);
 
-        uint32_t a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
-        uint32_t v = a3;
+        // inclusive prefix of the 16 column sums of this lane, then across the warp
+        uint32_t a[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = cs[2 * q], o = cs[2 * q + 1];
+            a[4 * q + 0] = (q ? a[4 * q - 1] : 0u) + (e & 0xFFFFu);
+            a[4 * q + 1] = a[4 * q + 0] + (o & 0xFFFFu);
+            a[4 * q + 2] = a[4 * q + 1] + (e >> 16);
+            a[4 * q + 3] = a[4 * q + 2] + (o >> 16);
+        }
+        uint32_t v = a[15];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t nb = __shfl_up_sync(0xffffffffu, v, d);
+            const uint32_t nb = __shfl_up_sync(FULL, v, d);
             if (lane >= d) v += nb;
         }
-        if (lane == 31) wt[buf][warp] = v;
-        __syncthreads();
-        uint32_t w = (lane < warp) ? wt[buf][lane] : 0u;
-        w = __reduce_add_sync(0xffffffffu, w);
-        const uint32_t off = w + v - a3;
-        uint32_t *Pp = P[buf] + 1 + li;
-        Pp[0] = off + a0; Pp[1] = off + a1; Pp[2] = off + a2; Pp[3] = off + a3;
-        __syncthreads();
-
-        uint32_t nib = 0;
-        if (out_thread) {
-            const uint32_t *Pq = P[buf];
+        const uint32_t off = v - a[15];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t s = Pq[li + j + r + 1] - Pq[li + j - r];
-                uint32_t num = 2 * s + p.n;
-                int mean = (int)__umul64hi((uint64_t)num << 16, p.magic);
-                int g = (vcen >> (8 * j)) & 255;
-                int diff = g - mean;
-                bool on = p.invert ? (diff <= -p.C) : (diff > -p.C);
-                if (cx + j < W && on) nib |= 1u << j;
+        for (int j = 0; j < 16; ++j) Pb[j * 33 + lane] = off + a[j];
+        __syncwarp();
+
+        uint32_t bits16 = 0;
+        if (out_lane) {
+            const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int X = kx + j, Y = ky + j;              // Y >= 0 because lead >= r + 1
+                const uint32_t S = Pb[(X & 15) * 33 + (X >> 4)] - Pb[(Y & 15) * 33 + (Y >> 4)];
+                const int g = (int)((cw[j >> 2] >> (8 * (j & 3))) & 255u);
+                const bool ge = (int)(2u * S) + p.n >= p.n2 * (g + p.C);      // mean >= g + C
+                const bool on = p.invert ? ge : !ge;
+                if (on && x + j < W) bits16 |= 1u << j;
             }
         }
         if (OUT_BITS) {
-            uint32_t wv = nib << (4 * (lane & 7));
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
-            wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
-            if (out_thread && (lane & 7) == 0) p.bits.p[img * p.bits.bs + (int64_t)y * p.bits.wpr + (cx >> 5)] = wv;
-        } else if (out_thread) {
-            uint8_t *drow = p.dst.p + img * p.dst.bs + y * p.dst.rs;
-            uint32_t bytes = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
-            if (dst_aligned && cx + 3 < W) *(uint32_t *)(drow + cx) = bytes;
-            else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (cx + j < W) drow[cx + j] = (uint8_t)(bytes >> (8 * j));
+            const uint32_t other = __shfl_xor_sync(FULL, bits16, 1);
+            if (out_lane && !(lane & 1)) p.bits.p[img * p.bits.bs + (int64_t)y * p.bits.wpr + (x >> 5)] = bits16 | (other << 16);
+        } else if (out_lane) {
+            uint8_t *drow = p.dst.p + img * p.dst.bs + (int64_t)y * p.dst.rs + x;
+            if (dst_aligned && x + 15 < W) {
+                *(uint4 *)drow = make_uint4(bytes_of_nib(bits16 & 15u), bytes_of_nib((bits16 >> 4) & 15u),
+                                            bytes_of_nib((bits16 >> 8) & 15u), bytes_of_nib(bits16 >> 12));
+            } else {
+                const int nvalid = min(16, W - x);
+                for (int j = 0; j < nvalid; ++j) drow[j] = ((bits16 >> j) & 1u) ? 255 : 0;
             }
         }
-
-        c0 += (vnew & 255) - (vold & 255);
-        c1 += ((vnew >> 8) & 255) - ((vold >> 8) & 255);
-        c2 += ((vnew >> 16) & 255) - ((vold >> 16) & 255);
-        c3 += (vnew >> 24) - (vold >> 24);
+        sub16(cs, vold);
+        add16(cs, vnew);
     }
 }
 
@@ -152,33 +157,30 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     p.src = plane_of(gray);
     p.width = gray->width; p.height = gray->height;
     p.r = block_size / 2;
-    p.lead = (int)align_up((size_t)p.r, 32);
+    p.lead = (int)align_up((size_t)p.r + 1, 32);
+    p.out_w = (SW - p.lead - p.r) & ~31;
     const bool to_bits = (out_u8 == nullptr);
     if (!to_bits) p.dst = plane_of(out_u8); else p.dst = Plane{nullptr, 0, 0};
     p.bits = out_bits;
-    // one strip if the row + halos fit 1024 threads x 4 columns, otherwise strips of 4096 - 2*lead
-    int need = (int)align_up((size_t)p.width, 32) + 2 * p.lead;
-    int T;
-    if (need <= 4096) { T = (int)align_up((size_t)cdiv(need, 4), 32); p.out_w = 4 * T - 2 * p.lead; p.strips = 1; }
-    else { T = 1024; p.out_w = 4096 - 2 * p.lead; p.strips = cdiv(p.width, p.out_w); }
-    if (T < 64) T = 64;
-    // bands: enough CTAs for ~4 per SM, band height 32..256
-    int64_t rows_total = (int64_t)gray->height * gray->batch * p.strips;
-    int band_h = (int)(rows_total / (4 * (int64_t)ctx->sm_count));
-    band_h = band_h < 32 ? 32 : (band_h > 256 ? 256 : band_h);
+    p.strips = cdiv(p.width, p.out_w);
+    // bands: about 20 resident warps per SM; a band re-reads block_size - 1 rows of its neighbours (L2)
+    const int64_t rows_total = (int64_t)gray->height * gray->batch * p.strips;
+    int band_h = (int)(rows_total / (20 * (int64_t)ctx->sm_count));
+    band_h = band_h < 64 ? 64 : (band_h > 320 ? 320 : band_h);
+    if (ctx->tune_ad_band > 0) band_h = ctx->tune_ad_band;
     if (band_h > gray->height) band_h = gray->height;
     p.band_h = band_h;
     p.bands = cdiv(gray->height, band_h);
-    p.C = C; p.invert = invert;
-    p.n = (uint32_t)block_size * block_size;
-    const uint64_t d = 2ull * p.n;
-    p.magic = ((1ull << 48) + d - 1) / d;
-    const int64_t nblocks = (int64_t)gray->batch * p.strips * p.bands;
-    const size_t smem = (size_t)(2 * (4 * T + 1) + 64) * sizeof(uint32_t);
-    const bool sal = plane_aligned(gray, 4);
-    const bool dal = to_bits ? true : plane_aligned(out_u8, 4);
-    if (to_bits) adaptive_mean_kernel<true><<<(unsigned)nblocks, T, smem, st>>>(p, sal, dal);
-    else adaptive_mean_kernel<false><<<(unsigned)nblocks, T, smem, st>>>(p, sal, dal);
+    p.n = block_size * block_size;
+    p.n2 = 2 * p.n;
+    p.C = C < -256 ? -256 : (C > 256 ? 256 : C);
+    p.invert = invert;
+    p.tasks = (int64_t)gray->batch * p.bands * p.strips;
+    const bool sal = plane_aligned(gray, 16);
+    const bool dal = to_bits ? true : plane_aligned(out_u8, 16);
+    const unsigned nblocks = (unsigned)cdiv(p.tasks, AD_WARPS);
+    if (to_bits) adaptive_mean_kernel<true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, sal, dal);
+    else adaptive_mean_kernel<false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, sal, dal);
     SS_LAUNCH_CHECK(ctx, "adaptive_mean", st);
     return SYNSEG_OK;
 }

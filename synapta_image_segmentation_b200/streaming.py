@@ -1,10 +1,11 @@
-"""Pinned, double-buffered host->device page streaming: the rasterisation handoff of this stage.
+"""Pinned, multi-buffered host->device page streaming: the rasterisation handoff of this stage.
 
 The reference hands a rasterised region over as RGB u8 pixels (pdf_image_segmentation.py:3638-3657).  Here
-whole pages arrive in pinned host memory (row-major HWC, stride 3W, no alpha); a copy stream moves batch
-i+1 to the device while the compute stream runs the fused detection pipeline on batch i, and the small
-result tensors (n_labels, stats) come back through pinned buffers.  End to end this stage is PCIe-bound
-(25.2 MB per 300-DPI page), not HBM-bound.
+whole pages arrive in pinned host memory (row-major HWC, stride 3W, no alpha); a copy stream moves batches
+i+1, i+2 to the device while the compute stream runs the fused detection pipeline on batch i, and the small
+result tensors (n_labels, stats) come back through pinned buffers.  The host consumes the results of batch
+i-slots+1 (box filter / merge in Python) only after the next copy has been queued, so the copy engine never
+waits for Python.  End to end this stage is PCIe-bound (25.2 MB per 300-DPI page), not HBM-bound.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ from .detector import RasterRegionDetector
 
 
 class PageStreamer:
-    def __init__(self, detector: RasterRegionDetector, batch: int, height: int, width: int, slots: int = 2):
+    def __init__(self, detector: RasterRegionDetector, batch: int, height: int, width: int, slots: int = 3):
         self.det = detector
         self.batch, self.h, self.w = batch, height, width
         dev = detector.ctx.device
@@ -47,8 +48,9 @@ class PageStreamer:
             s = i % self.slots
             b = hb.shape[0]
             # the slot's previous batch must be consumed (host-side wait on its `computed` event) before its
-            # page buffer is overwritten and its result buffers are reused
-            if i >= self.slots:
+            # page buffer is overwritten and its result buffers are reused; up to slots-1 batches stay queued
+            # on the device while the host post-processes the oldest one
+            while len(pending) >= self.slots:
                 self._finish(pending.pop(0), on_result)
             with torch.cuda.stream(self.copy_stream):
                 self.dev_pages[s][:b].copy_(hb, non_blocking=True)
