@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsynseg.so")
 SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "ccl.cu", "reduce.cu", "phash.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("SYNSEG_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

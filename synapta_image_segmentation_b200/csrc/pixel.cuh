@@ -46,13 +46,30 @@ __device__ __forceinline__ bool hsv_mask_px(uint32_t r, uint32_t g, uint32_t b, 
 }
 
 // 16 consecutive grey pixels of a row starting at column x (any x), replicated outside [0, W)
-// (BORDER_REPLICATE).  `aligned`: row base and stride are 16-byte aligned (x must then be a multiple of 16).
+// (BORDER_REPLICATE).  `aligned` (kernel-uniform): row base and stride are 16-byte aligned and x is a multiple
+// of 16.  The aligned path issues exactly ONE 128-bit load per call for every lane (no divergent loads): the
+// address is clamped to the row's first / last 16-byte unit and the edge pixel is replicated with register
+// arithmetic.  It may read (never write) up to 15 bytes past column W-1 inside the row stride.
 __device__ __forceinline__ uint4 load16_rep(const uint8_t *row, int x, int W, bool aligned)
 {
-    if (aligned && x >= 0 && x + 15 < W) return __ldg((const uint4 *)(row + x));
-    if (x + 15 < 0 || x >= W) {
-        const uint32_t b = (uint32_t)__ldg(row + (x < 0 ? 0 : W - 1)) * 0x01010101u;
-        return make_uint4(b, b, b, b);
+    if (aligned) {
+        const int xl = min(max(x, 0), (W - 1) & ~15);
+        uint4 v = __ldg((const uint4 *)(row + xl));
+        const int nv = W - xl;                             // valid bytes from xl on (>= 1)
+        if (x == xl && nv >= 16) return v;
+        const int bi = (x < 0) ? 0 : (min(nv, 16) - 1);    // byte that is replicated
+        const int lq = bi >> 2;
+        const uint32_t lw = lq == 0 ? v.x : (lq == 1 ? v.y : (lq == 2 ? v.z : v.w));
+        const uint32_t rep = ((lw >> (8 * (bi & 3))) & 0xFFu) * 0x01010101u;
+        if (x != xl) return make_uint4(rep, rep, rep, rep);                // wholly outside the image
+        const int k1 = nv - 4, k2 = nv - 8, k3 = nv - 12;                  // valid bytes in each word (nv < 16)
+        const uint32_t m0 = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+        const uint32_t m1 = k1 >= 4 ? 0xFFFFFFFFu : (k1 <= 0 ? 0u : ((1u << (8 * k1)) - 1u));
+        const uint32_t m2 = k2 >= 4 ? 0xFFFFFFFFu : (k2 <= 0 ? 0u : ((1u << (8 * k2)) - 1u));
+        const uint32_t m3 = k3 <= 0 ? 0u : ((1u << (8 * k3)) - 1u);
+        v.x = (v.x & m0) | (rep & ~m0); v.y = (v.y & m1) | (rep & ~m1);
+        v.z = (v.z & m2) | (rep & ~m2); v.w = (v.w & m3) | (rep & ~m3);
+        return v;
     }
     uint32_t w[4];
 #pragma unroll

@@ -12,7 +12,9 @@
 // column sums (row y+r+1 in, row y-r out) in registers, two 16-bit sums per register (255 rows x 255 fit).
 // Each row the horizontal window sums come from a warp-wide inclusive prefix of the column sums (local
 // prefix + shuffle scan) parked in a transposed, conflict-free shared-memory tile: S = P[x+r] - P[x-r-1].
-// The threshold test needs no division: mean >= g + C  <=>  2s + n >= 2n (g + C).
+// The threshold test needs no division: mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + n C - (n-1)/2,
+// and its sign bit is funnel-shifted straight into the output word.  Rows on which no output pixel of the strip has
+// g <= 255 - C (blank paper: the mean cannot exceed 255) skip the prefix and the test altogether (warp-uniform).
 // Every source byte comes from HBM once; the "row out" and centre-row reads of a band hit L2.
 // Output is either a u8 {0,255} plane or a bit plane (two lanes -> one 32-bit word).
 #include "internal.cuh"
@@ -22,7 +24,13 @@ namespace {
 
 constexpr int CPL = 16;                 // columns per lane
 constexpr int SW = 32 * CPL;            // columns per warp strip
-constexpr int AD_WARPS = 4;             // independent warps per CTA
+#ifndef SYNSEG_AD_WARPS
+#define SYNSEG_AD_WARPS 1
+#endif
+constexpr int AD_WARPS = SYNSEG_AD_WARPS;   // independent warps per CTA (1: a finished warp frees its registers at once)
+#ifndef SYNSEG_AD_MINBLOCKS
+#define SYNSEG_AD_MINBLOCKS (16 / SYNSEG_AD_WARPS)
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 struct AdParams {
@@ -34,8 +42,11 @@ struct AdParams {
     int lead;        // round_up(r + 1, 32): columns of left halo the strip carries
     int out_w;       // output columns per strip (multiple of 32)
     int strips, bands, band_h;
-    int n, n2;       // bs * bs, 2 * bs * bs
+    int n;           // bs * bs
+    int k2m1;        // n C - (n - 1) / 2 - 1
     int C;           // clamped to [-256, 256] (g - mean lies in [-255, 255])
+    int skip_ok;     // 1 <= C <= 128: the blank-row shortcut applies
+    uint32_t skip_add;
     int invert;
     int64_t tasks;   // batch * bands * strips
 };
@@ -59,7 +70,7 @@ __device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
 __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
 template <bool OUT_BITS>
-__global__ void __launch_bounds__(32 * AD_WARPS) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
+__global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
 {
     __shared__ uint32_t Psm[AD_WARPS][2][16 * 33];   // [column within lane][lane], padded: conflict-free both ways
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,15 +97,54 @@ __global__ void __launch_bounds__(32 * AD_WARPS) adaptive_mean_kernel(AdParams p
         }
     }
     const int kx = CPL * lane + r, ky = CPL * lane - r - 1;  // prefix indices of column j: kx + j, ky + j
+    uint32_t colmask = 0;                                    // output columns of this lane inside the image
+    if (out_lane) colmask = (W - x >= 16) ? 0xFFFFu : ((1u << (W - x)) - 1u);
+
+    // software pipeline: the three row loads of step y + 1 are issued before step y is computed
+    uint4 nnew = make_uint4(0, 0, 0, 0), nold = nnew, ncen = nnew;
+    auto issue_loads = [&](int yy) {
+        if (live) {
+            nnew = load16_rep(base + (int64_t)min(yy + r + 1, H - 1) * p.src.rs, x, W, src_aligned);
+            nold = load16_rep(base + (int64_t)max(yy - r, 0) * p.src.rs, x, W, src_aligned);
+        }
+        if (out_lane) ncen = load16_rep(base + (int64_t)yy * p.src.rs, x, W, src_aligned);
+    };
+    issue_loads(y0);
 
     for (int y = y0; y < y1; ++y) {
         uint32_t *Pb = Psm[warp][y & 1];
-        uint4 vnew = make_uint4(0, 0, 0, 0), vold = vnew, vcen = vnew;
-        if (live) {
-            vnew = load16_rep(base + (int64_t)min(y + r + 1, H - 1) * p.src.rs, x, W, src_aligned);
-            vold = load16_rep(base + (int64_t)max(y - r, 0) * p.src.rs, x, W, src_aligned);
+        const uint4 vnew = nnew, vold = nold, vcen = ncen;
+        if (y + 1 < y1) issue_loads(y + 1);
+
+        // Row shortcut: mean <= 255, so a pixel with g + C > 255 can never satisfy mean >= g + C.  When no output
+        // pixel of the whole strip row has g <= 255 - C (blank paper) the result is known without the window sums.
+        if (p.skip_ok) {
+            bool need = false;
+            if (out_lane) {
+                const uint32_t add = p.skip_add;               // 0x01010101 * (127 - (C - 1))
+                const uint32_t a0 = ~vcen.x, a1 = ~vcen.y, a2 = ~vcen.z, a3 = ~vcen.w;   // 255 - g > C - 1 ?
+                need = ((((a0 + add) | a0) | ((a1 + add) | a1) | ((a2 + add) | a2) | ((a3 + add) | a3)) & 0x80808080u) != 0u;
+            }
+            if (!__any_sync(FULL, need)) {
+                const uint32_t cbits = p.invert ? 0u : colmask;
+                if (OUT_BITS) {
+                    const uint32_t other = __shfl_xor_sync(FULL, cbits, 1);
+                    if (out_lane && !(lane & 1)) p.bits.p[img * p.bits.bs + (int64_t)y * p.bits.wpr + (x >> 5)] = cbits | (other << 16);
+                } else if (out_lane) {
+                    uint8_t *drow = p.dst.p + img * p.dst.bs + (int64_t)y * p.dst.rs + x;
+                    const uint32_t fill = p.invert ? 0u : 0xFFFFFFFFu;
+                    if (dst_aligned && x + 15 < W) *(uint4 *)drow = make_uint4(fill, fill, fill, fill);
+                    else {
+                        const int nvalid = min(16, W - x);
+                        for (int j = 0; j < nvalid; ++j) drow[j] = (uint8_t)fill;
+                    }
+                }
+                sub16(cs, vold);
+                add16(cs, vnew);
+                __syncwarp();
+                continue;
+            }
         }
-        if (out_lane) vcen = load16_rep(base + (int64_t)y * p.src.rs, x, W, src_aligned);
 
         // inclusive prefix of the 16 column sums of this lane, then across the warp
         uint32_t a[16];
@@ -120,15 +170,16 @@ __global__ void __launch_bounds__(32 * AD_WARPS) adaptive_mean_kernel(AdParams p
         uint32_t bits16 = 0;
         if (out_lane) {
             const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
+            // mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + k2  (n odd)  <=>  sign(n g + k2 - 1 - s) set
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 15; j >= 0; --j) {
                 const int X = kx + j, Y = ky + j;              // Y >= 0 because lead >= r + 1
-                const uint32_t S = Pb[(X & 15) * 33 + (X >> 4)] - Pb[(Y & 15) * 33 + (Y >> 4)];
                 const int g = (int)((cw[j >> 2] >> (8 * (j & 3))) & 255u);
-                const bool ge = (int)(2u * S) + p.n >= p.n2 * (g + p.C);      // mean >= g + C
-                const bool on = p.invert ? ge : !ge;
-                if (on && x + j < W) bits16 |= 1u << j;
+                const int e = g * p.n + p.k2m1 - (int)Pb[(X & 15) * 33 + (X >> 4)] + (int)Pb[(Y & 15) * 33 + (Y >> 4)];
+                bits16 = __funnelshift_l((uint32_t)e, bits16, 1);
             }
+            if (!p.invert) bits16 = ~bits16;
+            bits16 &= colmask;
         }
         if (OUT_BITS) {
             const uint32_t other = __shfl_xor_sync(FULL, bits16, 1);
@@ -163,17 +214,21 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     if (!to_bits) p.dst = plane_of(out_u8); else p.dst = Plane{nullptr, 0, 0};
     p.bits = out_bits;
     p.strips = cdiv(p.width, p.out_w);
-    // bands: about 20 resident warps per SM; a band re-reads block_size - 1 rows of its neighbours (L2)
+    // Bands: a band re-reads block_size - 1 rows of its neighbours (L2 hits, cheap: load + accumulate only).  Short
+    // bands win because the cost of a band depends on its content (blank rows skip the prefix and the test), so
+    // many small tasks balance the SMs better (measured on B200: 320 rows 1.16 ms, 64 rows 0.81 ms per 50 pages).
     const int64_t rows_total = (int64_t)gray->height * gray->batch * p.strips;
-    int band_h = (int)(rows_total / (20 * (int64_t)ctx->sm_count));
-    band_h = band_h < 64 ? 64 : (band_h > 320 ? 320 : band_h);
+    int band_h = (int)(rows_total / (64 * (int64_t)ctx->sm_count));
+    band_h = band_h < 32 ? 32 : (band_h > 64 ? 64 : band_h);
     if (ctx->tune_ad_band > 0) band_h = ctx->tune_ad_band;
     if (band_h > gray->height) band_h = gray->height;
     p.band_h = band_h;
     p.bands = cdiv(gray->height, band_h);
     p.n = block_size * block_size;
-    p.n2 = 2 * p.n;
     p.C = C < -256 ? -256 : (C > 256 ? 256 : C);
+    p.k2m1 = p.n * p.C - (p.n - 1) / 2 - 1;
+    p.skip_ok = (p.C >= 1 && p.C <= 128) ? 1 : 0;
+    p.skip_add = 0x01010101u * (uint32_t)(127 - (p.C - 1));
     p.invert = invert;
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
     const bool sal = plane_aligned(gray, 16);
