@@ -37,11 +37,11 @@ UNIT = "pages/s"
 ALG_BYTES_PER_PX = {
     "rgb2gray": 4.0,            # 3 read + 1 written
     "adaptive_mean": 1.125,     # grey read + bit plane written
-    "canny_classes": 2.0,       # grey read + class map written
-    "ccl_init": 2.0, "ccl_merge": 1.0, "ccl_compress": 2.0,   # u8 class map / block labels (1 B/px)
-    "hyst_flag": 2.0, "hyst_final": 2.25,
-    "bitmorph_h": 0.25, "bitmorph_v": 0.25,
-    "ccl_count": 1.0, "ccl_scan": 0.0, "ccl_assign": 1.0, "stats_init": 0.0, "ccl_final": 1.125, "stats_finalize": 0.0,
+    "canny_classes": 1.25,      # grey read + kept / strong bit planes written
+    "ccl_init": 0.125, "ccl_merge": 0.125, "ccl_compress": 0.125,   # bit plane read; parent array touched at run starts only
+    "hyst_flag": 0.25, "hyst_final": 0.375,                          # kept (+ strong) read; edges OR-ed into the mask plane
+    "bitmorph_h": 0.25, "bitmorph_v": 0.25,                          # bit plane read + written
+    "ccl_scan": 0.0, "ccl_assign": 0.0, "stats_init": 0.0, "ccl_final": 0.125, "stats_finalize": 0.0,
 }
 
 
@@ -137,6 +137,16 @@ def build_textbook(dpi: int, batch: int, unique: int, start_page: int, pin: bool
     return t
 
 
+def workload_config(args, world, h, w):
+    """The `config` object both arms print (the reference arm adds its bounded sample)."""
+    B, K = args.batch, args.steps
+    return {"workload": f"{K * B}-page synthetic textbook at {args.dpi} DPI ({w}x{h} RGB) per GPU, {B} pages per step, "
+                        f"assembled from {min(args.unique, B)} unique seeded pages",
+            "pages_per_step_per_gpu": B, "dpi": args.dpi, "parallelism": f"pages sharded over {world} GPU(s)",
+            "l2": f"inputs larger than L2: {B * h * w * 3 / 1e6:.0f} MB RGB per step vs 126 MB L2",
+            "chain": "gray(cv2) -> adaptive(51,10,INV)|Canny(50,150) -> dilate(k) -> close(k) -> CCL8+stats" if args.dpi == 300 else "see DetectConfig"}
+
+
 def run_reference(args):
     """--impl reference: the CPU OpenCV chain on all host cores; each step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -144,8 +154,10 @@ def run_reference(args):
         return
     import numpy as np
     from oracle import cpu_baseline
-    from synapta_image_segmentation_b200.synth import synth_pages
+    from synapta_image_segmentation_b200.synth import page_shape, synth_pages
     cores = os.cpu_count() or 1
+    h, w = page_shape(args.dpi)
+    cfg = workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), h, w)
     per_step = max(8, cores)
     pages = synth_pages(per_step, args.dpi, start=1000)
     best = None
@@ -164,8 +176,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"cv2 4.13 chain gray->adaptive|canny->dilate->close->CCL+stats on synthetic {args.dpi}-DPI letter pages",
-                       "pages_per_step": per_step, "dpi": args.dpi},
+            "config": dict(cfg, reference_sample=f"each step = {per_step} pages of the same generator through the cv2 4.13 chain "
+                                                 f"(oracle/cv2_chain.py) on {cores} host cores"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{per_step} pages per step x {len(vals)} steps; best arrangement: {best['arrangement']}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,11 +360,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"{K * B}-page synthetic textbook at {args.dpi} DPI ({w}x{h} RGB) per GPU, {B} pages per step, "
-                                       f"assembled from {min(args.unique, B)} unique seeded pages",
-                           "pages_per_step_per_gpu": B, "dpi": args.dpi, "parallelism": f"pages sharded over {world} GPU(s)",
-                           "l2": f"inputs larger than L2: {B * npx * 3 / 1e6:.0f} MB RGB per step vs 126 MB L2",
-                           "chain": "gray(cv2) -> adaptive(51,10,INV)|Canny(50,150) -> dilate(k) -> close(k) -> CCL8+stats" if args.dpi == 300 else "see DetectConfig"},
+                "config": workload_config(args, world, h, w),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         if n_survivors is not None:
             line["dedup"] = {"regions_hashed": int(k_all.numel()), "survivors": n_survivors, "collective": "nccl all_gather_into_tensor"}

@@ -39,7 +39,7 @@ class PageStreamer:
         self.d2h_bytes = 0
         detector.ctx.reserve(width, height, batch)
 
-    def run(self, host_batches: Iterable[torch.Tensor], on_result: Optional[Callable] = None, stats_rows: int = 64) -> int:
+    def run(self, host_batches: Iterable[torch.Tensor], on_result: Optional[Callable] = None) -> int:
         """host_batches: pinned u8 tensors [b<=batch, H, W, 3].  Calls on_result(batch_index, n_labels, stats)
         with host tensors (valid until the slot is reused).  Returns the number of pages processed."""
         pending: List[tuple] = []
@@ -60,10 +60,12 @@ class PageStreamer:
                 self.compute_stream.wait_event(self.copied[s])
                 n, st, ce = self.dev_out[s]
                 self.det.detect_components(self.dev_pages[s][:b], out=(n[:b], st[:b], ce[:b]))
+                # contiguous -> contiguous pinned copies only: a strided device->host copy_ goes through a staging
+                # buffer and BLOCKS the host, which would serialise the next H2D behind this batch's compute
                 self.host_n[s][:b].copy_(n[:b], non_blocking=True)
-                self.host_stats[s][:b, :stats_rows].copy_(st[:b, :stats_rows], non_blocking=True)
+                self.host_stats[s][:b].copy_(st[:b], non_blocking=True)
                 self.computed[s].record(self.compute_stream)
-            self.d2h_bytes += b * 4 + b * stats_rows * 20
+            self.d2h_bytes += b * 4 + b * self.host_stats[s].shape[1] * 20
             pending.append((i, s, b))
             pages += b
         while pending:

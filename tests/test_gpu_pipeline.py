@@ -146,7 +146,7 @@ def test_streaming_equals_direct(ctx):
     batches = [torch.from_numpy(synth_pages(4, 72, base_seed=5, start=4 * i)).pin_memory() for i in range(5)]
     got = {}
     st = PageStreamer(det, 4, h, w, slots=2)
-    n_pages = st.run(iter(batches), lambda i, n, s: got.__setitem__(i, (n.clone(), s.clone())), stats_rows=64)
+    n_pages = st.run(iter(batches), lambda i, n, s: got.__setitem__(i, (n.clone(), s.clone())))
     assert n_pages == 20 and st.h2d_bytes == 20 * h * w * 3
     for i, hb in enumerate(batches):
         n, stats, _ = det.detect_components(hb.cuda())
