@@ -13,9 +13,10 @@ BASELINE.json configs[2]: a 1,000-page synthetic textbook at 300 DPI on one B200
           algorithmic bytes / its time / measured HBM peak (MEASURED_PEAKS.json).
   cpu_baseline : the cv2 chain (oracle/cv2_chain.py) on the box's host cores, bounded sample, rank 0, N=1.
 
-N>1 (torchrun, one rank per GPU): pages shard across ranks (weak scaling, no data-path collective); each step
-also hashes the candidate component boxes on the device, and after the K steps ONE NCCL all-gather of the
-(hash, key) pairs plus the replicated Hamming dedup runs inside the timed region.
+Every step also selects the candidate component boxes on the device; after the K steps their perceptual hashes are
+computed and the replicated Hamming dedup runs, inside the timed region.  N>1 (torchrun, one rank per GPU): pages
+shard across ranks (weak scaling, no data-path collective) and ONE NCCL all-gather of the (hash, key) pairs
+precedes the dedup.
 """
 from __future__ import annotations
 
@@ -206,6 +207,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SYNSEG_NCCL_DEBUG", "WARN")   # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = Context(local)
@@ -222,8 +224,9 @@ def main():
     ml = det.cfg.max_labels
     out = (torch.empty(B, dtype=torch.int32, device=dev), torch.empty((B, ml, 5), dtype=torch.int32, device=dev),
            torch.empty((B, ml, 2), dtype=torch.float64, device=dev))
-    # device-side candidate selection + hashing (used at N>1 for the dedup exchange)
-    cap = 16 * B * max(K, 1)
+    # device-side candidate selection + hashing for the cross-page duplicate removal (every N; the gather is a
+    # real NCCL collective at N>1 and local at N=1, so per-GPU work is identical for every N)
+    cap = 16 * B * max(K, W_, 1)
     rois = torch.empty((cap, 5), dtype=torch.int32, device=dev)
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
     hashes = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -232,19 +235,24 @@ def main():
     min_area, max_area = int(5000 * s * s), int(0.8 * npx)
     min_ext = int(50 * s)
 
-    def step(i, with_hash):
+    def step(i):
         det.detect_components(pages, out=out)
-        if with_hash:
-            ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
+        ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
+
+    def dedup_exchange():
+        ctx.phash_indirect(pages, 1, rois, count, hashes)      # all candidate boxes of the K steps share `pages`
+        n_valid = int(count.item())
+        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4)
+        return k_all, int(keep.sum().item())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with_hash = world > 1
     for i in range(W_):
-        step(i, with_hash)
+        step(i)
+    dedup_exchange()            # warm-up of the exchange too (the first collective creates the NCCL communicator)
     barrier()
     count.zero_()
     sampler = ClockSampler(local)
@@ -254,13 +262,8 @@ def main():
     barrier()
     e0.record()
     for i in range(K):
-        step(i, with_hash)
-    n_survivors = None
-    if with_hash:
-        ctx.phash_indirect(pages, 1, rois, count, hashes)      # all candidate boxes of the K steps share `pages`
-        n_valid = int(count.item())
-        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4)
-        n_survivors = int(keep.sum().item())
+        step(i)
+    k_all, n_survivors = dedup_exchange()
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -362,8 +365,8 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": workload_config(args, world, h, w),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        if n_survivors is not None:
-            line["dedup"] = {"regions_hashed": int(k_all.numel()), "survivors": n_survivors, "collective": "nccl all_gather_into_tensor"}
+        line["dedup"] = {"regions_hashed": int(k_all.numel()), "survivors": n_survivors,
+                         "collective": "nccl all_gather_into_tensor" if world > 1 else "none (single GPU)"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

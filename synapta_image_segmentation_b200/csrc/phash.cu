@@ -6,7 +6,8 @@
 // the C oracle (oracle/synseg_oracle.c:orc_phash) and every rank agree bit for bit:
 //   grey -> 32x32 cell means q = (256*sum + cnt/2)/cnt -> F = C q C^T with C[u][x] =
 //   lround(16384 cos(pi (2x+1) u / 64)), u < 8 -> bit k = 2 F[k] > (sorted[31] + sorted[32]).
-// One CTA per region; every pixel is read once, coalesced (thread per column, 32 row groups).
+// Two kernels: cell means with one CTA per (row group, region) -- every pixel is read once, thread per column --
+// then one CTA per region for the 32-point integer DCTs, the median and the bits.
 #include "internal.cuh"
 #include "pixel.cuh"
 
@@ -14,57 +15,78 @@ namespace {
 
 constexpr int PH_MAXW = 8192;
 
-__global__ void __launch_bounds__(256) phash_kernel(Plane src, int width, int height, int src_kind, const synseg_roi *rois,
-                                                    const int32_t *basis, unsigned long long *out, const int32_t *count)
+// Stage 1: cell means.  grid = (32 row groups, regions): CTA (i, r) reduces row group i of region r to its
+// 32 cell values q[i][0..31] (thread per column, rows of the group unrolled by 4 for memory-level parallelism).
+__global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, int height, int src_kind, const synseg_roi *rois,
+                                                          int32_t *qbuf, const int32_t *count)
+{
+    if (count && (int)blockIdx.y >= *count) return;
+    __shared__ uint32_t colsum[PH_MAXW];
+    synseg_roi r;
+    if (rois) r = rois[blockIdx.y];
+    else { r.image = blockIdx.y; r.x = 0; r.y = 0; r.width = width; r.height = height; }
+    const int tid = threadIdx.x, i = blockIdx.x;
+    const uint8_t *base = src.p + r.image * src.bs;
+    const int w = r.width, h = r.height;
+    const int y0 = (int)((long long)i * h / 32);
+    int y1 = (int)((long long)(i + 1) * h / 32);
+    if (y1 <= y0) y1 = y0 + 1;
+    const int mode = src_kind == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV;
+    for (int x = tid; x < w; x += 256) {
+        uint32_t s = 0;
+        if (src_kind == 0) {
+            const uint8_t *p = base + (int64_t)(r.y + y0) * src.rs + r.x + x;
+            int y = y0;
+            for (; y + 4 <= y1; y += 4, p += 4 * src.rs)
+                s += (uint32_t)__ldg(p) + __ldg(p + src.rs) + __ldg(p + 2 * src.rs) + __ldg(p + 3 * src.rs);
+            for (; y < y1; ++y, p += src.rs) s += __ldg(p);
+        } else {
+            const uint8_t *p = base + (int64_t)(r.y + y0) * src.rs + 3 * (int64_t)(r.x + x);
+            int y = y0;
+            for (; y + 4 <= y1; y += 4, p += 4 * src.rs) {
+                uint32_t px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint8_t *q = p + k * src.rs;
+                    px[k] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s += gray_dyn(px[k], mode);
+            }
+            for (; y < y1; ++y, p += src.rs)
+                s += gray_dyn((uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16), mode);
+        }
+        colsum[x] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int j = tid;
+        const int x0 = (int)((long long)j * w / 32);
+        int x1 = (int)((long long)(j + 1) * w / 32);
+        if (x1 <= x0) x1 = x0 + 1;
+        unsigned long long s = 0;
+        for (int x = x0; x < x1; ++x) s += colsum[x];
+        const unsigned long long c = (unsigned long long)(y1 - y0) * (unsigned long long)(x1 - x0);
+        qbuf[((int64_t)blockIdx.y * 32 + i) * 32 + j] = (int32_t)((256ull * s + c / 2) / c);
+    }
+}
+
+// Stage 2: one CTA per region: integer DCT of the 32x32 cell values, low 8x8 block, median bits.
+__global__ void __launch_bounds__(256) phash_dct_kernel(const int32_t *qbuf, const int32_t *basis, unsigned long long *out,
+                                                        const int32_t *count)
 {
     if (count && (int)blockIdx.x >= *count) return;
-    __shared__ uint32_t colsum[PH_MAXW];
     __shared__ int32_t q[32][33];
     __shared__ long long T[8][33];
     __shared__ long long F[64];
     __shared__ int32_t cb[8 * 32];
     __shared__ long long med2;
     __shared__ unsigned int hbits[2];
-
-    synseg_roi r;
-    if (rois) r = rois[blockIdx.x];
-    else { r.image = blockIdx.x; r.x = 0; r.y = 0; r.width = width; r.height = height; }
     const int tid = threadIdx.x;
     cb[tid] = basis[tid];
     if (tid == 0) med2 = 0;
-    const uint8_t *base = src.p + r.image * src.bs;
-    const int w = r.width, h = r.height;
-
-    for (int i = 0; i < 32; ++i) {
-        int y0 = (int)((long long)i * h / 32), y1 = (int)((long long)(i + 1) * h / 32);
-        if (y1 <= y0) y1 = y0 + 1;
-        for (int x = tid; x < w; x += 256) {
-            uint32_t s = 0;
-            for (int y = y0; y < y1; ++y) {
-                const uint8_t *row = base + (int64_t)(r.y + y) * src.rs;
-                uint32_t v;
-                if (src_kind == 0) v = __ldg(row + r.x + x);
-                else {
-                    const uint8_t *p = row + 3 * (int64_t)(r.x + x);
-                    const uint32_t rgbx = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-                    v = gray_dyn(rgbx, src_kind == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV);
-                }
-                s += v;
-            }
-            colsum[x] = s;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const int j = tid;
-            int x0 = (int)((long long)j * w / 32), x1 = (int)((long long)(j + 1) * w / 32);
-            if (x1 <= x0) x1 = x0 + 1;
-            unsigned long long s = 0;
-            for (int x = x0; x < x1; ++x) s += colsum[x];
-            const unsigned long long c = (unsigned long long)(y1 - y0) * (unsigned long long)(x1 - x0);
-            q[i][j] = (int32_t)((256ull * s + c / 2) / c);
-        }
-        __syncthreads();
-    }
+    for (int k = tid; k < 1024; k += 256) q[k >> 5][k & 31] = qbuf[(int64_t)blockIdx.x * 1024 + k];
+    __syncthreads();
     // T[v][y] = sum_x C[v][x] q[y][x]
     {
         const int v = tid >> 5, y = tid & 31;
@@ -137,6 +159,21 @@ __global__ void __launch_bounds__(256) select_rois_kernel(const int32_t *n_label
 
 }  // namespace
 
+static int run_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int n, const int32_t *count,
+                     uint64_t *out, cudaStream_t st)
+{
+    SS_TRY(arena_ensure(ctx, (size_t)n * 1024 * sizeof(int32_t) + 256));
+    arena_begin(ctx);
+    void *p;
+    SS_TRY(arena_alloc(ctx, (size_t)n * 1024 * sizeof(int32_t), &p, st));
+    int32_t *qbuf = (int32_t *)p;
+    phash_cells_kernel<<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, src_kind, rois, qbuf, count);
+    SS_LAUNCH_CHECK(ctx, "phash_cells", st);
+    phash_dct_kernel<<<n, 256, 0, st>>>(qbuf, ctx->phash_basis, (unsigned long long *)out, count);
+    SS_LAUNCH_CHECK(ctx, "phash_dct", st);
+    return SYNSEG_OK;
+}
+
 extern "C" SYNSEG_EXPORT int synseg_select_rois(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t batch,
                                                 int32_t max_labels, int64_t page_base, int32_t min_area, int32_t max_area, int32_t min_w,
                                                 int32_t min_h, synseg_roi *rois, uint64_t *keys, int32_t *count, int32_t capacity,
@@ -161,10 +198,8 @@ extern "C" SYNSEG_EXPORT int synseg_phash_indirect(synseg_ctx *ctx, const synseg
     SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
     if (!rois || !count || !out || capacity < 1) { synseg_set_error("synseg_phash_indirect: bad arguments"); return SYNSEG_E_INVALID; }
     if (src->width > PH_MAXW) { synseg_set_error("synseg_phash_indirect: width > %d", PH_MAXW); return SYNSEG_E_INVALID; }
-    phash_kernel<<<capacity, 256, 0, (cudaStream_t)stream>>>(plane_of(src), src->width, src->height, src_kind, rois, ctx->phash_basis,
-                                                              (unsigned long long *)out, count);
-    SS_LAUNCH_CHECK(ctx, "phash", (cudaStream_t)stream);
-    return SYNSEG_OK;
+    if (capacity > 65535) { synseg_set_error("synseg_phash_indirect: capacity > 65535"); return SYNSEG_E_INVALID; }
+    return run_phash(ctx, src, src_kind, rois, capacity, count, out, (cudaStream_t)stream);
 }
 
 extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois, uint64_t *out,
@@ -177,9 +212,12 @@ extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src
     if (!rois) n_rois = src->batch;
     if (n_rois <= 0) return SYNSEG_OK;
     if (src->width > PH_MAXW) { synseg_set_error("synseg_phash: width > %d", PH_MAXW); return SYNSEG_E_INVALID; }
-    phash_kernel<<<n_rois, 256, 0, (cudaStream_t)stream>>>(plane_of(src), src->width, src->height, src_kind, rois, ctx->phash_basis,
-                                                           (unsigned long long *)out, nullptr);
-    SS_LAUNCH_CHECK(ctx, "phash", (cudaStream_t)stream);
+    for (int32_t o = 0; o < n_rois; o += 32768) {       // grid.y limit
+        const int32_t n = n_rois - o < 32768 ? n_rois - o : 32768;
+        synseg_img view = *src;
+        if (!rois) { view.data = (uint8_t *)src->data + (int64_t)o * src->batch_stride; view.batch = n; }
+        SS_TRY(run_phash(ctx, &view, src_kind, rois ? rois + o : nullptr, n, nullptr, out + o, (cudaStream_t)stream));
+    }
     return SYNSEG_OK;
 }
 
