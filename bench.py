@@ -335,8 +335,15 @@ def main():
     launch_ms = dk["ms_per_step"] / max(1, dk["launches_per_step"])
     alg_bytes = ALG_BYTES_PER_PX.get(dom, 1.0) * npx * B
     achieved = alg_bytes / (launch_ms / 1000.0) / 1e9
+    traffic = None                      # DRAM bytes per launch of that kernel from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("pages_per_launch") == B and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "share_of_step": dk["share"],
                 "page_level": {"algorithmic_bytes_per_page": 19.0 * npx, "achieved": 19.0 * npx * B / (step_ms / 1000.0) / 1e9,
                                "frac": 19.0 * npx * B / (step_ms / 1000.0) / 1e9 / peak},

@@ -41,6 +41,7 @@ struct CnParams {
     int width, height, lo, hi;
     int strips, bands, band_h;
     int64_t tasks;
+    int no_nms;      // experiment knob
 };
 
 // Horizontal partials of one grey row for this lane's 16 columns, two columns per register:
@@ -128,37 +129,39 @@ __device__ __forceinline__ uint32_t produce_row(MagRing &R, CnState &st, int slo
     return (z | (z >> 8)) & 0xFFFFu;
 }
 
-// non-maximum suppression of ring row y for this lane's candidates -> kept / strong bits in column order
-__device__ __forceinline__ void nms_row(const MagRing &R, const CnState &st, int y, int lane, uint32_t cand, int hi,
-                                        uint32_t &kept16, uint32_t &strong16)
+// Per-warp staging of the balanced NMS: the candidates of a strip row are listed and dealt out evenly to the lanes.
+struct NmsStage { uint16_t list[512]; uint32_t kept[32], strong[32]; };
+
+// non-maximum suppression of candidate b (gather order) of lane `owner` in ring row y; results are OR-ed into the stage
+__device__ __forceinline__ void nms_one(const MagRing &R, const CnState &st, NmsStage &S, int y, int owner, int b, int hi)
 {
     const int sc = y % 3, su = (y + 2) % 3, sd = (y + 1) % 3;
-    while (cand) {
-        const int b = __ffs((int)cand) - 1;
-        cand &= cand - 1;
-        const int i = b & 3, t = b >> 2;
-        const int pr = 2 * i + (t >> 1), sh = 16 * (t & 1);
-        const int col = 4 * i + (t >> 1) + 2 * (t & 1);
-        const int m = (int)((R.mag[sc][pr][lane] >> sh) & 0xFFFFu);
-        const int dx = (int)(short)(R.dx[sc][pr][lane] >> sh), dy = (int)(short)(R.dy[sc][pr][lane] >> sh);
-        const int ax = abs(dx), ay = abs(dy) << 15, tg22 = ax * 13573;
-        bool keep;
-        if (ay < tg22) keep = m > ring_mag(R, st.zmask, sc, lane, col - 1) && m >= ring_mag(R, st.zmask, sc, lane, col + 1);
+    const int i = b & 3, t = b >> 2;
+    const int pr = 2 * i + (t >> 1), sh = 16 * (t & 1);
+    const int col = 4 * i + (t >> 1) + 2 * (t & 1);
+    const int m = (int)((R.mag[sc][pr][owner] >> sh) & 0xFFFFu);
+    const int dx = (int)(short)(R.dx[sc][pr][owner] >> sh), dy = (int)(short)(R.dy[sc][pr][owner] >> sh);
+    const int ax = abs(dx), ay = abs(dy) << 15, tg22 = ax * 13573;
+    bool keep;
+    if (ay < tg22) keep = m > ring_mag(R, st.zmask, sc, owner, col - 1) && m >= ring_mag(R, st.zmask, sc, owner, col + 1);
+    else {
+        const int tg67 = tg22 + (ax << 16);
+        if (ay > tg67) keep = m > ring_mag(R, st.zmask, su, owner, col) && m >= ring_mag(R, st.zmask, sd, owner, col);
         else {
-            const int tg67 = tg22 + (ax << 16);
-            if (ay > tg67) keep = m > ring_mag(R, st.zmask, su, lane, col) && m >= ring_mag(R, st.zmask, sd, lane, col);
-            else {
-                const int s = ((dx ^ dy) < 0) ? -1 : 1;
-                keep = m > ring_mag(R, st.zmask, su, lane, col - s) && m > ring_mag(R, st.zmask, sd, lane, col + s);
-            }
+            const int s = ((dx ^ dy) < 0) ? -1 : 1;
+            keep = m > ring_mag(R, st.zmask, su, owner, col - s) && m > ring_mag(R, st.zmask, sd, owner, col + s);
         }
-        if (keep) { kept16 |= 1u << col; if (m > hi) strong16 |= 1u << col; }
+    }
+    if (keep) {
+        atomicOr(&S.kept[owner], 1u << col);
+        if (m > hi) atomicOr(&S.strong[owner], 1u << col);
     }
 }
 
 __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_classes_kernel(CnParams p, bool aligned)
 {
     __shared__ MagRing rings[CN_WARPS];
+    __shared__ NmsStage stages[CN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t task = (int64_t)blockIdx.x * CN_WARPS + warp;
     if (task >= p.tasks) return;                      // warp-uniform
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     const int band = (int)(task % p.bands);
     const int img = (int)(task / p.bands);
     MagRing &R = rings[warp];
+    NmsStage &S = stages[warp];
 
     const int W = p.width, H = p.height, hi = p.hi;
     const int x = strip * CN_OUT_W - 16 + 16 * lane;  // first of this lane's 16 columns
@@ -209,8 +213,21 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         const uint32_t cand_next = produce_row(R, st, (y + 1) % 3, lane, A, B, C, y + 1 < H);                  \
         __syncwarp();                                                                                          \
         uint32_t kept16 = 0, strong16 = 0;                                                                     \
-        if (__any_sync(FULL, out_lane && cand_cur != 0u)) {                                                    \
-            if (out_lane) nms_row(R, st, y, lane, cand_cur, hi, kept16, strong16);                             \
+        const uint32_t mycand = out_lane ? cand_cur : 0u;                                                      \
+        if (!p.no_nms && __any_sync(FULL, mycand != 0u)) {                                                     \
+            /* balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes */      \
+            const int cnt = __popc(mycand);                                                                    \
+            int incl = cnt;                                                                                    \
+            _Pragma("unroll")                                                                                  \
+            for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; } \
+            const int total = __shfl_sync(FULL, incl, 31);                                                     \
+            int pos = incl - cnt;                                                                              \
+            for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1)); \
+            S.kept[lane] = 0u; S.strong[lane] = 0u;                                                            \
+            __syncwarp();                                                                                      \
+            for (int q = lane; q < total; q += 32) { const int id = S.list[q]; nms_one(R, st, S, y, id >> 4, id & 15, hi); } \
+            __syncwarp();                                                                                      \
+            kept16 = S.kept[lane]; strong16 = S.strong[lane];                                                  \
         }                                                                                                      \
         const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);   \
         if (writer) {                                                                                          \
@@ -250,6 +267,7 @@ int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept,
     p.band_h = band_h;
     p.bands = cdiv(gray->height, band_h);
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
+    p.no_nms = ctx->tune_flags & 1;
     canny_classes_kernel<<<(unsigned)cdiv(p.tasks, CN_WARPS), 32 * CN_WARPS, 0, st>>>(p, plane_aligned(gray, 16));
     SS_LAUNCH_CHECK(ctx, "canny_classes", st);
     return SYNSEG_OK;

@@ -49,22 +49,23 @@ struct AdParams {
     uint32_t skip_add;
     int invert;
     int64_t tasks;   // batch * bands * strips
+    int no_test;     // experiment knob
 };
 
 // cs[2q] holds columns 4q (low half) and 4q+2 (high half); cs[2q+1] columns 4q+1 and 4q+3
 __device__ __forceinline__ void add16(uint32_t cs[8], const uint4 v)
 {
-    cs[0] += v.x & 0x00FF00FFu; cs[1] += (v.x >> 8) & 0x00FF00FFu;
-    cs[2] += v.y & 0x00FF00FFu; cs[3] += (v.y >> 8) & 0x00FF00FFu;
-    cs[4] += v.z & 0x00FF00FFu; cs[5] += (v.z >> 8) & 0x00FF00FFu;
-    cs[6] += v.w & 0x00FF00FFu; cs[7] += (v.w >> 8) & 0x00FF00FFu;
+    cs[0] += __byte_perm(v.x, 0, 0x4240); cs[1] += __byte_perm(v.x, 0, 0x4341);
+    cs[2] += __byte_perm(v.y, 0, 0x4240); cs[3] += __byte_perm(v.y, 0, 0x4341);
+    cs[4] += __byte_perm(v.z, 0, 0x4240); cs[5] += __byte_perm(v.z, 0, 0x4341);
+    cs[6] += __byte_perm(v.w, 0, 0x4240); cs[7] += __byte_perm(v.w, 0, 0x4341);
 }
 __device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
 {
-    cs[0] -= v.x & 0x00FF00FFu; cs[1] -= (v.x >> 8) & 0x00FF00FFu;
-    cs[2] -= v.y & 0x00FF00FFu; cs[3] -= (v.y >> 8) & 0x00FF00FFu;
-    cs[4] -= v.z & 0x00FF00FFu; cs[5] -= (v.z >> 8) & 0x00FF00FFu;
-    cs[6] -= v.w & 0x00FF00FFu; cs[7] -= (v.w >> 8) & 0x00FF00FFu;
+    cs[0] -= __byte_perm(v.x, 0, 0x4240); cs[1] -= __byte_perm(v.x, 0, 0x4341);
+    cs[2] -= __byte_perm(v.y, 0, 0x4240); cs[3] -= __byte_perm(v.y, 0, 0x4341);
+    cs[4] -= __byte_perm(v.z, 0, 0x4240); cs[5] -= __byte_perm(v.z, 0, 0x4341);
+    cs[6] -= __byte_perm(v.w, 0, 0x4240); cs[7] -= __byte_perm(v.w, 0, 0x4341);
 }
 
 __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
@@ -84,30 +85,28 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     const int x = strip * p.out_w - p.lead + CPL * lane;     // first of this lane's 16 columns
     const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
     const uint8_t *base = p.src.p + img * p.src.bs;
-    const bool live = x <= W - 1 + r;                        // columns further right feed no output
     const bool out_lane = (CPL * lane >= p.lead) && (CPL * lane < p.lead + p.out_w) && (x < W);
+    // warp-uniform: every lane's 16 columns lie inside the image (4 of the 6 strips of a 300-DPI page) -> plain vector loads
+    const bool fast = src_aligned && __all_sync(FULL, x >= 0 && x + 15 < W);
+    auto ldrow = [&](int yy) -> uint4 {                      // yy inside the image
+        const uint8_t *rp = base + (int64_t)yy * p.src.rs;
+        return fast ? __ldg((const uint4 *)(rp + x)) : load16_rep(rp, x, W, src_aligned);
+    };
 
     // running column sums over rows [y - r, y + r] (replicate)
     uint32_t cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (live) {
-#pragma unroll 4
-        for (int dy = -r; dy <= r; ++dy) {
-            const int yy = min(max(y0 + dy, 0), H - 1);
-            add16(cs, load16_rep(base + (int64_t)yy * p.src.rs, x, W, src_aligned));
-        }
-    }
+#pragma unroll 8
+    for (int dy = -r; dy <= r; ++dy) add16(cs, ldrow(min(max(y0 + dy, 0), H - 1)));
     const int kx = CPL * lane + r, ky = CPL * lane - r - 1;  // prefix indices of column j: kx + j, ky + j
     uint32_t colmask = 0;                                    // output columns of this lane inside the image
     if (out_lane) colmask = (W - x >= 16) ? 0xFFFFu : ((1u << (W - x)) - 1u);
 
     // software pipeline: the three row loads of step y + 1 are issued before step y is computed
-    uint4 nnew = make_uint4(0, 0, 0, 0), nold = nnew, ncen = nnew;
+    uint4 nnew, nold, ncen;
     auto issue_loads = [&](int yy) {
-        if (live) {
-            nnew = load16_rep(base + (int64_t)min(yy + r + 1, H - 1) * p.src.rs, x, W, src_aligned);
-            nold = load16_rep(base + (int64_t)max(yy - r, 0) * p.src.rs, x, W, src_aligned);
-        }
-        if (out_lane) ncen = load16_rep(base + (int64_t)yy * p.src.rs, x, W, src_aligned);
+        nnew = ldrow(min(yy + r + 1, H - 1));
+        nold = ldrow(max(yy - r, 0));
+        ncen = ldrow(yy);
     };
     issue_loads(y0);
 
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
                 const uint32_t a0 = ~vcen.x, a1 = ~vcen.y, a2 = ~vcen.z, a3 = ~vcen.w;   // 255 - g > C - 1 ?
                 need = ((((a0 + add) | a0) | ((a1 + add) | a1) | ((a2 + add) | a2) | ((a3 + add) | a3)) & 0x80808080u) != 0u;
             }
-            if (!__any_sync(FULL, need)) {
+            if (p.no_test || !__any_sync(FULL, need)) {
                 const uint32_t cbits = p.invert ? 0u : colmask;
                 if (OUT_BITS) {
                     const uint32_t other = __shfl_xor_sync(FULL, cbits, 1);
@@ -231,6 +230,7 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     p.skip_add = 0x01010101u * (uint32_t)(127 - (p.C - 1));
     p.invert = invert;
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
+    p.no_test = (ctx->tune_flags >> 1) & 1;
     const bool sal = plane_aligned(gray, 16);
     const bool dal = to_bits ? true : plane_aligned(out_u8, 16);
     const unsigned nblocks = (unsigned)cdiv(p.tasks, AD_WARPS);
