@@ -187,6 +187,25 @@ int synseg_grid_counts(synseg_ctx *ctx, const synseg_img *rgb_or_gray, int chann
                        const synseg_roi *rois_host, int32_t n_rois, int kw, int kh, uint64_t *out,
                        const synseg_img *edges_out, void *stream);
 
+/* One crop of a ragged batch: `channels` (1 grey / 3 RGB) x width x height pixels at byte `offset` of a packed
+ * device buffer, rows `row_stride` bytes apart. */
+typedef struct synseg_crop {
+    uint64_t offset;
+    int32_t width, height;
+    int64_t row_stride;
+    int32_t channels;
+    int32_t _pad;
+} synseg_crop;
+
+/* Batched form of the deterministic per-crop hint quantities (the O:887-1010 drivers over many crops; BASELINE.json
+ * configs[3]).  For crop i, out[8*i ..] = { h_count, v_count, edge_px      (as synseg_grid_counts with PIL grey: S:1546-1564,
+ *                                           sum, sum_sq, non_zero          (PIL grey moments -> np.var: S:1805, 2989, 3073, O:1007),
+ *                                           mask_px                        (HSV mask count, S:1574-1577; 0 for grey crops),
+ *                                           0 }.
+ * crops_host is a HOST array; everything is queued on `stream` without synchronising. */
+int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
+                       uint64_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

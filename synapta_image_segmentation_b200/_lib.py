@@ -19,6 +19,12 @@ class Roi(C.Structure):
     _fields_ = [("image", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class Crop(C.Structure):
+    """synseg_crop"""
+    _fields_ = [("offset", C.c_uint64), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int64),
+                ("channels", C.c_int32), ("_pad", C.c_int32)]
+
+
 class DetectParams(C.Structure):
     """synseg_detect_params"""
     _fields_ = [("block_size", C.c_int32), ("C", C.c_int32), ("canny_lo", C.c_int32), ("canny_hi", C.c_int32),
@@ -51,6 +57,7 @@ SIGNATURES = {
     "synseg_phash": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "synseg_phash_dedup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "synseg_detect_pages": (C.c_int, [C.c_void_p, _P(Img), _P(DetectParams), _P(Img), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_hints_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),
 }
 

@@ -77,6 +77,55 @@ extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_i
     return run_ccl_stats(ctx, m, nullptr, n_labels, stats, centroids, prm->max_labels, st);
 }
 
+// grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2) -> counts of ONE image (view->batch == 1).
+// out3 = {h_count, v_count, edge_px} must be zero on entry.  The scratch arena must already be large enough.
+static int grid_counts_one(synseg_ctx *ctx, const synseg_img *view, int channels, int gray_mode, int kw, int kh, uint64_t *out3,
+                           const synseg_img *edges_out, cudaStream_t st)
+{
+    arena_begin(ctx);
+    const int W = view->width, H = view->height;
+    synseg_img gray = *view;
+    void *p;
+    if (channels == 3) {
+        gray.row_stride = (int64_t)align_up((size_t)W, 16);
+        gray.batch_stride = gray.row_stride * H;
+        SS_TRY(arena_alloc(ctx, (size_t)gray.batch_stride, &p, st));
+        gray.data = p;
+        SS_TRY(launch_rgb2gray(ctx, view, &gray, gray_mode, st));
+    }
+    const int wpr = bit_wpr(W);
+    const size_t pb = (size_t)wpr * H * 4;
+    SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane edges{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane a{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane b{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    SS_TRY(run_canny(ctx, &gray, nullptr, edges, false, 50, 150, st));
+    SS_TRY(launch_count_bits(ctx, edges, W, H, 1, out3 + 2, 0, st));
+    if (edges_out) SS_TRY(launch_unpack_bits(ctx, edges, edges_out, st));
+    const int ekw = kw > 0 ? kw : (W / 20 > 20 ? W / 20 : 20);
+    const int ekh = kh > 0 ? kh : (H / 20 > 20 ? H / 20 : 20);
+    // horizontal lines: OPEN with (ekw x 1), iterations 2
+    SS_CUDA(cudaMemcpyAsync(a.p, edges.p, pb, cudaMemcpyDeviceToDevice, st));
+    {
+        BitPlane c = a, o = b;
+        SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, ekw, 1, ekw / 2, 0, 2, st));
+        SS_TRY(launch_count_bits(ctx, c, W, H, 1, out3 + 0, 0, st));
+    }
+    // vertical lines: OPEN with (1 x ekh), iterations 2  (column passes ping-pong edges -> a -> b)
+    {
+        BitPlane c = edges, o = a;
+        SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, 1, ekh, 0, ekh / 2, 2, st));
+        SS_TRY(launch_count_bits(ctx, c, W, H, 1, out3 + 1, 0, st));
+    }
+    return SYNSEG_OK;
+}
+
+static size_t grid_counts_scratch(int mw, int mh)
+{
+    const size_t gray_bytes = (size_t)align_up((size_t)mw, 16) * mh + 256;
+    const size_t plane_bytes = (size_t)bit_wpr(mw) * mh * 4 + 256;
+    return gray_bytes + 3 * plane_bytes + canny_scratch_bytes(mw, mh, 1) + 8192;
+}
+
 extern "C" SYNSEG_EXPORT int synseg_grid_counts(synseg_ctx *ctx, const synseg_img *src, int channels, int gray_mode, const synseg_roi *rois_host,
                                   int32_t n_rois, int kw, int kh, uint64_t *out, const synseg_img *edges_out, void *stream)
 {
@@ -108,54 +157,53 @@ extern "C" SYNSEG_EXPORT int synseg_grid_counts(synseg_ctx *ctx, const synseg_im
         if (r.width > mw) mw = r.width;
         if (r.height > mh) mh = r.height;
     }
-    const size_t gray_bytes = (size_t)align_up((size_t)mw, 16) * mh + 256;
-    const size_t plane_bytes = (size_t)bit_wpr(mw) * mh * 4 + 256;
-    SS_TRY(arena_ensure(ctx, gray_bytes + 3 * plane_bytes + canny_scratch_bytes(mw, mh, 1) + 8192));
+    SS_TRY(arena_ensure(ctx, grid_counts_scratch(mw, mh)));
     SS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t) * 3 * (size_t)n_rois, st));
     for (int i = 0; i < n_rois; ++i) {
         const synseg_roi &r = rois_host[i];
-        arena_begin(ctx);
-        const int W = r.width, H = r.height;
         synseg_img view = *src;
         view.data = (uint8_t *)src->data + r.image * src->batch_stride + (int64_t)r.y * src->row_stride + (int64_t)r.x * channels;
-        view.width = W; view.height = H; view.batch = 1;
-        synseg_img gray = view;
-        void *p;
-        if (channels == 3) {
-            gray.row_stride = (int64_t)align_up((size_t)W, 16);
-            gray.batch_stride = gray.row_stride * H;
-            SS_TRY(arena_alloc(ctx, (size_t)gray.batch_stride, &p, st));
-            gray.data = p;
-            SS_TRY(launch_rgb2gray(ctx, &view, &gray, gray_mode, st));
-        }
-        const int wpr = bit_wpr(W);
-        const size_t pb = (size_t)wpr * H * 4;
-        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane edges{(uint32_t *)p, wpr, (int64_t)wpr * H};
-        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane a{(uint32_t *)p, wpr, (int64_t)wpr * H};
-        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane b{(uint32_t *)p, wpr, (int64_t)wpr * H};
-        SS_TRY(run_canny(ctx, &gray, nullptr, edges, false, 50, 150, st));
-        SS_TRY(launch_count_bits(ctx, edges, W, H, 1, out + 3 * (size_t)i + 2, 0, st));
+        view.width = r.width; view.height = r.height; view.batch = 1;
+        synseg_img eo;
         if (edges_out) {
-            synseg_img eo = *edges_out;
+            eo = *edges_out;
             eo.data = (uint8_t *)edges_out->data + (int64_t)i * edges_out->batch_stride;
-            eo.width = W; eo.height = H; eo.batch = 1;
-            SS_TRY(launch_unpack_bits(ctx, edges, &eo, st));
+            eo.width = r.width; eo.height = r.height; eo.batch = 1;
         }
-        const int ekw = kw > 0 ? kw : (W / 20 > 20 ? W / 20 : 20);
-        const int ekh = kh > 0 ? kh : (H / 20 > 20 ? H / 20 : 20);
-        // horizontal lines: OPEN with (ekw x 1), iterations 2
-        SS_CUDA(cudaMemcpyAsync(a.p, edges.p, pb, cudaMemcpyDeviceToDevice, st));
-        {
-            BitPlane c = a, o = b;
-            SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, ekw, 1, ekw / 2, 0, 2, st));
-            SS_TRY(launch_count_bits(ctx, c, W, H, 1, out + 3 * (size_t)i + 0, 0, st));
+        SS_TRY(grid_counts_one(ctx, &view, channels, gray_mode, kw, kh, out + 3 * (size_t)i, edges_out ? &eo : nullptr, st));
+    }
+    return SYNSEG_OK;
+}
+
+// Batched per-crop hint quantities for n crops of different sizes packed in one device buffer (config 4:
+// 10k cropped figure regions).  No host synchronisation: everything is queued on `stream`.
+extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
+                                  uint64_t *out, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_hints_crops: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (n <= 0) return SYNSEG_OK;
+    if (!base || !crops_host || !out) { synseg_set_error("synseg_hints_crops: NULL argument"); return SYNSEG_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n; ++i) {
+        const synseg_crop &c = crops_host[i];
+        if (c.width <= 0 || c.height <= 0 || (c.channels != 1 && c.channels != 3) || c.row_stride < (int64_t)c.width * c.channels) {
+            synseg_set_error("synseg_hints_crops: bad crop %d", i); return SYNSEG_E_INVALID;
         }
-        // vertical lines: OPEN with (1 x ekh), iterations 2  (column passes ping-pong edges -> a -> b)
-        {
-            BitPlane c = edges, o = a;
-            SS_TRY(run_bitmorph(ctx, c, o, W, H, 1, SYNSEG_MORPH_OPEN, 1, ekh, 0, ekh / 2, 2, st));
-            SS_TRY(launch_count_bits(ctx, c, W, H, 1, out + 3 * (size_t)i + 1, 0, st));
-        }
+        if (c.width > mw) mw = c.width;
+        if (c.height > mh) mh = c.height;
+    }
+    SS_TRY(arena_ensure(ctx, grid_counts_scratch(mw, mh)));
+    SS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t) * 8 * (size_t)n, st));
+    for (int i = 0; i < n; ++i) {
+        const synseg_crop &c = crops_host[i];
+        synseg_img view;
+        view.data = (uint8_t *)base + c.offset; view.width = c.width; view.height = c.height; view.row_stride = c.row_stride;
+        view.batch = 1; view._pad = 0; view.batch_stride = c.row_stride * c.height;
+        uint64_t *o = out + 8 * (size_t)i;
+        SS_TRY(grid_counts_one(ctx, &view, c.channels, SYNSEG_GRAY_PIL, kw, kh, o, nullptr, st));
+        SS_TRY(launch_moments(ctx, &view, c.channels == 3 ? 1 : 0, nullptr, 1, o + 3, st));
+        if (c.channels == 3) SS_TRY(synseg_hsv_mask_hist(ctx, &view, nullptr, 1, o + 6, nullptr, nullptr, nullptr, 0, stream));
     }
     return SYNSEG_OK;
 }

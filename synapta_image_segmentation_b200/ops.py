@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DetectParams, Img, Roi, check
+from ._lib import Crop, DetectParams, Img, Roi, check
 
 ERODE, DILATE, OPEN, CLOSE = 0, 1, 2, 3
 GRAY_CV, GRAY_PIL = 0, 1
@@ -281,6 +281,25 @@ class Context:
         check(self.lib.synseg_detect_pages(self._h, C.byref(img_of(rgb, 3)), C.byref(prm), gimg, n.data_ptr(), stats.data_ptr(),
                                            cent.data_ptr(), _stream()), "synseg_detect_pages")
         return n, stats, cent
+
+    def hints_crops(self, packed: torch.Tensor, crops, kw: int = 25, kh: int = 25) -> torch.Tensor:
+        """Ragged batch of crops packed in one CUDA u8 buffer.  crops = [(offset, width, height, row_stride, channels), ...].
+        Returns int64 [n, 8] = h_count, v_count, edge_px, sum, sum_sq, non_zero, mask_px, 0 (see synseg_hints_crops)."""
+        n = len(crops)
+        out = torch.empty((n, 8), dtype=torch.int64, device=packed.device)
+        if n == 0:
+            return out
+        if not packed.is_cuda or packed.dtype != torch.uint8 or not packed.is_contiguous():
+            raise ValueError("packed must be a contiguous CUDA uint8 tensor")
+        arr = (Crop * n)()
+        total = packed.numel()
+        for i, (off, w, h, rs, ch) in enumerate(crops):
+            if off < 0 or w <= 0 or h <= 0 or rs < w * ch or off + rs * (h - 1) + w * ch > total:
+                raise ValueError(f"crop {i} lies outside the packed buffer")
+            arr[i] = Crop(int(off), int(w), int(h), int(rs), int(ch), 0)
+        check(self.lib.synseg_hints_crops(self._h, C.c_void_p(packed.data_ptr()), arr, n, kw, kh, C.c_void_p(out.data_ptr()), _stream()),
+              "synseg_hints_crops")
+        return out
 
     def grid_counts(self, src: torch.Tensor, rois=None, gray_mode: int = GRAY_PIL, kw: int = 25, kh: int = 25,
                     want_edges: bool = False, channels: Optional[int] = None):

@@ -178,3 +178,35 @@ def test_dedup_finds_repeated_figures(ctx):
     direct = ctx.phash(t, 1, [tuple(r) for r in rois[:c].cpu().tolist()])
     assert torch.equal(direct, out[:c])
     assert all((int(k) >> 16) == 7 for k in keys2[:c].cpu().tolist())
+
+
+def test_config4_ragged_crop_batch(ctx):
+    """BASELINE.json configs[3] (scaled): a ragged batch of cropped figure regions -- RGB and grey, sizes from 70x67
+    up to 1191x1500 like the reference's investments_segmented crops -- through ONE synseg_hints_crops call;
+    every quantity bit-exact vs the cv2 / PIL / numpy chain (variance within 1e-9 relative: f64 vs exact integers)."""
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    from synapta_image_segmentation_b200.synth import render_figure
+    rng = np.random.default_rng(4)
+    crops = []
+    sizes = [(67, 70), (122, 161), (191, 310), (464, 799), (314, 164), (1500, 1191), (457, 699), (33, 517)]
+    for i in range(40):
+        h, w = sizes[i % len(sizes)] if i < 16 else (int(rng.integers(60, 700)), int(rng.integers(60, 900)))
+        kind = i % 4
+        if kind == 0:
+            a = render_figure([7, i], 150, h, w)
+        elif kind == 1:
+            a = imgs.rgb_noise(h, w, 100 + i)
+        elif kind == 2:
+            a = imgs.shapes(max(h, 8), max(w, 8), 200 + i)[:h, :w].copy()           # grey (mode L)
+        else:
+            a = np.repeat(imgs.blurred_noise(h, w, 300 + i)[:, :, None], 3, axis=2)
+            a[::7, :, 0] = 200                                                      # some saturated rows for the HSV mask
+        crops.append(np.ascontiguousarray(a))
+    got = FeatureHints.hints_batch([Image.fromarray(c) for c in crops])
+    assert len(got) == len(crops)
+    for c, g in zip(crops, got):
+        want = cv2_chain.crop_features(c)
+        assert (g["h_count"], g["v_count"], g["edge_px"], g["mask_px"]) == (want["h_count"], want["v_count"], want["edge_px"], want["mask_px"]), c.shape
+        assert abs(g["variance"] - want["variance"]) <= 1e-9 * max(1.0, want["variance"])
+        assert g["grid_detected"] == (want["h_count"] > 300 and want["v_count"] > 300)
+    assert FeatureHints.hints_batch([]) == []
