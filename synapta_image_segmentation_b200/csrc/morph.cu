@@ -199,6 +199,132 @@ __global__ void __launch_bounds__(32) bitmorph_v_kernel(BitPlane src, BitPlane d
 }
 
 // ---------------------------------------------------------------------------------------------
+// bit-plane row pass, register version: one thread -> 4 consecutive output words (128 pixels)
+// ---------------------------------------------------------------------------------------------
+// The thread loads the NW words that cover its windows, ORs the array with itself shifted by 1, 2, 4, ...
+// (in-place doubling: after the step with shift s every bit holds the OR of the 2s bits starting there), finishes
+// with the shift k - span and extracts its four words.  No shared memory, no synchronisation: every output word
+// costs ~45 instructions for k = 81 and the kernel runs at full occupancy.  NW = 8 serves k <= 98, NW = 12 k <= 226.
+template <int NW>
+__global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nq,
+                                                          int64_t total, int erode, int k, int anchor)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int q4 = (int)(i % nq);
+    const int64_t row = i / nq;
+    const int img = (int)(row / height);
+    const int y = (int)(row - (int64_t)img * height);
+    const int w0 = 4 * q4;
+    const int aw = (anchor + 31) >> 5, sft = 32 * aw - anchor;        // window of output bit b of word w0+q starts at bit 32q + b + sft of D
+    const uint32_t last_mask = (width & 31) ? ((1u << (width & 31)) - 1u) : 0xffffffffu;
+    const uint32_t *sp = src.p + img * src.bs + (int64_t)y * src.wpr;
+    uint32_t D[NW + 1];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const int w = w0 - aw + j;
+        uint32_t v = 0;
+        if (w >= 0 && w < nw) {
+            v = __ldg(sp + w);
+            if (erode) v = ~v;
+            if (w == nw - 1) v &= last_mask;
+        }
+        D[j] = v;
+    }
+    D[NW] = 0;
+    int span = 1;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {                 // bit shifts 1, 2, 4, 8, 16
+        if (2 * span <= k) {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) D[j] |= __funnelshift_r(D[j], D[j + 1], span);
+            span *= 2;
+        }
+    }
+    if (2 * span <= k) {                                   // 32
+#pragma unroll
+        for (int j = 0; j < NW; ++j) D[j] |= D[j + 1];
+        span *= 2;
+    }
+    if (2 * span <= k) {                                   // 64
+#pragma unroll
+        for (int j = 0; j < NW; ++j) D[j] |= (j + 2 <= NW) ? D[j + 2 < NW ? j + 2 : NW] : 0u;
+        span *= 2;
+    }
+    if (NW > 8 && 2 * span <= k) {                         // 128
+#pragma unroll
+        for (int j = 0; j < NW; ++j) D[j] |= D[j + 4 < NW ? j + 4 : NW];
+        span *= 2;
+    }
+    // E = D | (D >> (k - span)), words 0..4
+    const int t = k - span, tw = t >> 5, tb = t & 31;
+    uint32_t E[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (tw == m) { lo = D[j + m < NW ? j + m : NW]; hi = D[j + m + 1 < NW ? j + m + 1 : NW]; }
+        E[j] = D[j] | __funnelshift_r(lo, hi, tb);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v = __funnelshift_r(E[q], E[q + 1], sft);
+        if (erode) v = ~v;
+        const int w = w0 + q;
+        if (w == nw - 1) v &= last_mask;
+        if (w >= nw) v = 0;
+        o[q] = v;
+    }
+    *(uint4 *)(dst.p + img * dst.bs + (int64_t)y * dst.wpr + w0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit-plane column pass, van Herk / Gil-Werman: one thread -> one word column x k output rows
+// ---------------------------------------------------------------------------------------------
+// Output row ys + i (0 <= i < k) needs input rows [u0 + i, u0 + i + k - 1], u0 = ys - anchor: the suffix OR of block
+// [u0, u0 + k) from i on, and the prefix OR of block [u0 + k, u0 + 2k) up to i - 1.  The thread loads the first block
+// into its private shared-memory column (conflict-free: [row][thread]), turns it into suffix ORs in place, then
+// streams the second block keeping the running prefix OR in a register: ~12 instructions per output word for any k.
+__global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nseg,
+                                                            int64_t total, int erode, int k, int anchor)
+{
+    extern __shared__ uint32_t sm[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int64_t id = (int64_t)blockIdx.x * T + tid;
+    if (id >= total) return;
+    const int w = (int)(id % nw);
+    const int seg = (int)((id / nw) % nseg);
+    const int img = (int)(id / ((int64_t)nw * nseg));
+    const uint32_t last_mask = (width & 31) ? ((1u << (width & 31)) - 1u) : 0xffffffffu;
+    const uint32_t vmask = (w == nw - 1) ? last_mask : 0xffffffffu;
+    const uint32_t *sp = src.p + img * src.bs + w;
+    uint32_t *dp = dst.p + img * dst.bs + w;
+    const int ys = seg * k, u0 = ys - anchor;
+    auto ld = [&](int u) -> uint32_t {
+        if (u < 0 || u >= height) return 0u;
+        uint32_t v = __ldg(sp + (int64_t)u * src.wpr);
+        return erode ? (~v & vmask) : v;
+    };
+#pragma unroll 8
+    for (int j = 0; j < k; ++j) sm[j * T + tid] = ld(u0 + j);
+    {
+        uint32_t acc = sm[(k - 1) * T + tid];
+        for (int j = k - 2; j >= 0; --j) { acc |= sm[j * T + tid]; sm[j * T + tid] = acc; }
+    }
+    uint32_t g = 0;
+    const int n_out = min(k, height - ys);
+#pragma unroll 4
+    for (int i = 0; i < n_out; ++i) {
+        if (i > 0) g |= ld(u0 + k + i - 1);
+        uint32_t v = sm[i * T + tid] | g;
+        if (erode) v = ~v;
+        dp[(int64_t)(ys + i) * dst.wpr] = v & vmask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic 8-bit passes
 // ---------------------------------------------------------------------------------------------
 template <bool DIL> __device__ __forceinline__ uint32_t vop4(uint32_t a, uint32_t b) { return DIL ? __vmaxu4(a, b) : __vminu4(a, b); }
@@ -349,6 +475,15 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
                       cudaStream_t st)
 {
     const int nw = cdiv(width, 32);
+    if (k <= 226 && src.p != dst.p) {                      // register kernel (not in place: threads read their neighbours' words)
+        const int nq = src.wpr / 4;
+        const int64_t total = (int64_t)nq * height * batch;
+        const unsigned grid = (unsigned)cdiv(total, 256);
+        if (k <= 98) bitmorph_h4_kernel<8><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        else bitmorph_h4_kernel<12><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        SS_LAUNCH_CHECK(ctx, "bitmorph_h", st);
+        return SYNSEG_OK;
+    }
     const int padw = cdiv(k, 32) + 1;
     const size_t smem = (size_t)8 * 2 * (nw + 2 * padw + 1) * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_h: row too wide for shared memory"); return SYNSEG_E_INVALID; }
@@ -367,6 +502,17 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
                       cudaStream_t st)
 {
     const int nw = cdiv(width, 32);
+    if (k <= 384) {                                        // van Herk kernel, k words of shared memory per thread
+        const int T = k <= 190 ? 256 : 128;
+        const int nseg = cdiv(height, k);
+        const int64_t total = (int64_t)nw * nseg * batch;
+        static bool vh_attr = false;
+        if (!vh_attr) { SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); vh_attr = true; }
+        bitmorph_v_vh_kernel<<<(unsigned)cdiv(total, T), T, (size_t)k * T * sizeof(uint32_t), st>>>(src, dst, width, height, nw, nseg, total,
+                                                                                                   op == SYNSEG_MORPH_ERODE, k, anchor);
+        SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
+        return SYNSEG_OK;
+    }
     const size_t smem = (size_t)(BV_TH + k - 1) * 32 * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_v: kernel height %d too large", k); return SYNSEG_E_INVALID; }
     static bool attr_set = false;
@@ -381,7 +527,10 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
 static int bit_rect_pass(synseg_ctx *ctx, BitPlane &cur, BitPlane &other, int width, int height, int batch, int op, int kw, int kh,
                          int ax, int ay, cudaStream_t st)
 {
-    if (kw > 1) SS_TRY(launch_bitmorph_h(ctx, cur, cur, width, height, batch, op, kw, ax, st));
+    if (kw > 1) {
+        SS_TRY(launch_bitmorph_h(ctx, cur, other, width, height, batch, op, kw, ax, st));
+        BitPlane t = cur; cur = other; other = t;
+    }
     if (kh > 1) {
         SS_TRY(launch_bitmorph_v(ctx, cur, other, width, height, batch, op, kh, ay, st));
         BitPlane t = cur; cur = other; other = t;
