@@ -210,3 +210,50 @@ def test_config4_ragged_crop_batch(ctx):
         assert abs(g["variance"] - want["variance"]) <= 1e-9 * max(1.0, want["variance"])
         assert g["grid_detected"] == (want["h_count"] > 300 and want["v_count"] > 300)
     assert FeatureHints.hints_batch([]) == []
+
+
+def test_pipeline_edge_cases(ctx):
+    """Blank page (background only), all-ink page (one component; cv2 reports an empty background row), 1x1 and
+    1-row / 1-column pages, label overflow (n_labels = -(required)), and a ragged last batch through the streamer."""
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    from synapta_image_segmentation_b200.streaming import PageStreamer
+
+    def cv_chain(page, bs, c, k):
+        g = cv2.cvtColor(page, cv2.COLOR_RGB2GRAY)
+        ink = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, bs, c) | cv2.Canny(g, 50, 150)
+        se = cv2.getStructuringElement(cv2.MORPH_RECT, (k, k))
+        return cv2.connectedComponentsWithStats(cv2.morphologyEx(cv2.dilate(ink, se), cv2.MORPH_CLOSE, se), 8, cv2.CV_32S)
+
+    cases = [np.full((120, 90, 3), 255, np.uint8), np.zeros((64, 64, 3), np.uint8), np.full((1, 1, 3), 7, np.uint8),
+             imgs.rgb_noise(1, 300, 5), imgs.rgb_noise(300, 1, 6), imgs.rgb_noise(2, 2, 7)]
+    half = np.full((200, 333, 3), 255, np.uint8); half[:, :100] = 0           # ink touching three borders
+    cases.append(half)
+    for page in cases:
+        for (bs, c, k) in ((15, 5, 5), (3, -2, 3)):                           # C < 0: blank paper fires everywhere
+            n, stats, cent = ctx.detect_pages(torch.from_numpy(page).cuda()[None], bs, c, k, max_labels=64)
+            n_w, _, st_w, ce_w = cv_chain(page, bs, c, k)
+            assert int(n[0]) == n_w, (page.shape, bs, c, k)
+            assert np.array_equal(stats[0, :n_w].cpu().numpy(), st_w), (page.shape, bs, c, k)
+            assert np.array_equal(cent[0, :n_w].cpu().numpy(), ce_w, equal_nan=True)
+    # label overflow: more components than max_labels -> n_labels = -(required), first rows still exact
+    dots = np.full((200, 200, 3), 255, np.uint8)
+    dots[10::20, 10::20] = 0
+    n_w, _, st_w, _ = cv_chain(dots, 15, 5, 3)
+    assert n_w > 8
+    n, stats, _ = ctx.detect_pages(torch.from_numpy(dots).cuda()[None], 15, 5, 3, max_labels=8)
+    assert int(n[0]) == -n_w
+    assert np.array_equal(stats[0, :8].cpu().numpy(), st_w[:8])
+    det = RasterRegionDetector(DetectConfig(dpi=72, max_labels=8), ctx=ctx)
+    with pytest.raises(RuntimeError):
+        det.candidate_regions(stats[0].cpu().numpy(), int(n[0]), 200.0, 200.0)
+    # ragged last batch through the streamer (3 + 3 + 1 pages, slots = 2)
+    det = RasterRegionDetector(DetectConfig(dpi=72, max_labels=256), ctx=ctx)
+    h, w = page_shape(72)
+    pages = synth_pages(7, 72, base_seed=9)
+    batches = [torch.from_numpy(pages[i:i + 3]).pin_memory() for i in (0, 3, 6)]
+    seen = {}
+    st = PageStreamer(det, 3, h, w, slots=2)
+    assert st.run(iter(batches), lambda i, n, s: seen.__setitem__(i, n.clone())) == 7
+    assert [len(seen[i]) for i in range(3)] == [3, 3, 1]
+    ref_n, _, _ = det.detect_components(torch.from_numpy(pages).cuda())
+    assert torch.equal(torch.cat([seen[i] for i in range(3)]), ref_n.cpu())
