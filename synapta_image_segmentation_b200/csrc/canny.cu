@@ -41,7 +41,6 @@ struct CnParams {
     int width, height, lo, hi;
     int strips, bands, band_h;
     int64_t tasks;
-    int no_nms;      // experiment knob
 };
 
 // Horizontal partials of one grey row for this lane's 16 columns, two columns per register:
@@ -214,7 +213,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         __syncwarp();                                                                                          \
         uint32_t kept16 = 0, strong16 = 0;                                                                     \
         const uint32_t mycand = out_lane ? cand_cur : 0u;                                                      \
-        if (!p.no_nms && __any_sync(FULL, mycand != 0u)) {                                                     \
+        if (__any_sync(FULL, mycand != 0u)) {                                                                   \
             /* balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes */      \
             const int cnt = __popc(mycand);                                                                    \
             int incl = cnt;                                                                                    \
@@ -267,7 +266,6 @@ int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept,
     p.band_h = band_h;
     p.bands = cdiv(gray->height, band_h);
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
-    p.no_nms = ctx->tune_flags & 1;
     canny_classes_kernel<<<(unsigned)cdiv(p.tasks, CN_WARPS), 32 * CN_WARPS, 0, st>>>(p, plane_aligned(gray, 16));
     SS_LAUNCH_CHECK(ctx, "canny_classes", st);
     return SYNSEG_OK;

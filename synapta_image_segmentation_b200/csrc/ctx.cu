@@ -47,8 +47,6 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
     c->tune_ad_band = e1 ? atoi(e1) : 0;
     c->tune_canny_band = e2 ? atoi(e2) : 0;
-    const char *e3 = getenv("SYNSEG_TUNE_FLAGS");
-    c->tune_flags = e3 ? atoi(e3) : 0;
     c->sm_count = prop.multiProcessorCount;
     // integer DCT basis of the perceptual hash (same formula as oracle/synseg_oracle.c:orc_phash_basis)
     int32_t basis[8 * 32];

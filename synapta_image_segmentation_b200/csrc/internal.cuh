@@ -28,7 +28,6 @@ struct synseg_ctx {
     int32_t *phash_basis; // device int32[8*32]
     int tune_ad_band;     // experiment knobs (env SYNSEG_TUNE_AD_BAND / SYNSEG_TUNE_CANNY_BAND), 0 = automatic
     int tune_canny_band;
-    int tune_flags;       // experiments only (env SYNSEG_TUNE_FLAGS): bit0 canny without NMS, bit1 adaptive without the per-pixel test
     // optional per-kernel timing (synseg_profile_*): one event after every launch on the profiled stream
     bool prof_on;
     cudaEvent_t prof_start;

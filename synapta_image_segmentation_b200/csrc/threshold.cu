@@ -49,7 +49,6 @@ struct AdParams {
     uint32_t skip_add;
     int invert;
     int64_t tasks;   // batch * bands * strips
-    int no_test;     // experiment knob
 };
 
 // cs[2q] holds columns 4q (low half) and 4q+2 (high half); cs[2q+1] columns 4q+1 and 4q+3
@@ -124,7 +123,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
                 const uint32_t a0 = ~vcen.x, a1 = ~vcen.y, a2 = ~vcen.z, a3 = ~vcen.w;   // 255 - g > C - 1 ?
                 need = ((((a0 + add) | a0) | ((a1 + add) | a1) | ((a2 + add) | a2) | ((a3 + add) | a3)) & 0x80808080u) != 0u;
             }
-            if (p.no_test || !__any_sync(FULL, need)) {
+            if (!__any_sync(FULL, need)) {
                 const uint32_t cbits = p.invert ? 0u : colmask;
                 if (OUT_BITS) {
                     const uint32_t other = __shfl_xor_sync(FULL, cbits, 1);
@@ -230,7 +229,6 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     p.skip_add = 0x01010101u * (uint32_t)(127 - (p.C - 1));
     p.invert = invert;
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
-    p.no_test = (ctx->tune_flags >> 1) & 1;
     const bool sal = plane_aligned(gray, 16);
     const bool dal = to_bits ? true : plane_aligned(out_u8, 16);
     const unsigned nblocks = (unsigned)cdiv(p.tasks, AD_WARPS);

@@ -257,3 +257,82 @@ def test_pipeline_edge_cases(ctx):
     assert [len(seen[i]) for i in range(3)] == [3, 3, 1]
     ref_n, _, _ = det.detect_components(torch.from_numpy(pages).cuda())
     assert torch.equal(torch.cat([seen[i] for i in range(3)]), ref_n.cpu())
+
+
+def test_config3_full_size_properties(ctx):
+    """BASELINE.json configs[2] at full size: a 1,000-page 300-DPI textbook (20 batches of 50 pages assembled from 12
+    unique seeded pages) streamed from pinned host memory.  Size-independent properties on every page -- the
+    component areas partition the page, boxes lie inside it, copies of the same page give identical tables -- and
+    the exact cv2 tables on a sample of the pages."""
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    from synapta_image_segmentation_b200.streaming import PageStreamer
+    det = RasterRegionDetector(DetectConfig(dpi=300, max_labels=1024), ctx=ctx)
+    h, w = page_shape(300)
+    uniq = synth_pages(12, 300, base_seed=31)
+    host = torch.empty((50, h, w, 3), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for i in range(50):
+        hv[i] = uniq[i % 12]
+    tables = {}
+    n_seen = [0]
+
+    def on_result(bi, n_h, stats_h):
+        n_np, st_np = n_h.numpy(), stats_h.numpy()
+        for j in range(n_np.shape[0]):
+            n = int(n_np[j])
+            assert 1 <= n <= 1024
+            st = st_np[j, :n]
+            assert int(st[:, 4].sum()) == h * w                                  # areas partition the page
+            assert (st[:, 0] >= 0).all() and (st[:, 1] >= 0).all()
+            assert (st[:, 0] + st[:, 2] <= w).all() and (st[:, 1] + st[:, 3] <= h).all()
+            assert (st[1:, 4] <= st[1:, 2] * st[1:, 3]).all() and (st[1:, 4] > 0).all()
+            key = j % 12
+            if key in tables:
+                assert np.array_equal(tables[key], st), (bi, j)                  # same page -> same table, every batch
+            else:
+                tables[key] = st.copy()
+            n_seen[0] += 1
+
+    st = PageStreamer(det, 50, h, w, slots=3)
+    assert st.run((host for _ in range(20)), on_result) == 1000 and n_seen[0] == 1000
+    for key in (0, 5, 11):                                                       # exact tables on a sample
+        r = cv2_chain.page_chain(uniq[key], 300)
+        assert np.array_equal(tables[key], r["stats"])
+
+
+def test_config5_sharding_invariance(ctx):
+    """BASELINE.json configs[4] (scaled): the survivor set of the cross-page duplicate removal is the same for
+    1, 2, 4 and 8 ranks.  Ranks are emulated one after another on this GPU (contiguous page shards, device-side
+    candidate selection + hashing per shard); the concatenation of the shards' (hash, key) pairs stands for the
+    all-gather (the real collective is covered by the gloo test on CPU and by bench.py at N>1)."""
+    from synapta_image_segmentation_b200.dedup import gather_hashes, shard_pages
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    dpi, n_pages = 100, 96
+    det = RasterRegionDetector(DetectConfig(dpi=dpi, max_labels=512), ctx=ctx)
+    pages = torch.from_numpy(synth_pages(n_pages, dpi, base_seed=55, n_figures=2)).cuda()
+    h, w = page_shape(dpi)
+    s = dpi / 72.0
+    results = {}
+    for world in (1, 2, 4, 8):
+        hs, ks = [], []
+        for rank in range(world):
+            shard = shard_pages(n_pages, rank, world)
+            sub = pages[shard.start:shard.stop]
+            n, stats, _ = det.detect_components(sub)
+            cap = 16 * len(shard)
+            rois = torch.empty((cap, 5), dtype=torch.int32, device="cuda"); keys = torch.empty(cap, dtype=torch.int64, device="cuda")
+            cnt = torch.zeros(1, dtype=torch.int32, device="cuda"); out = torch.empty(cap, dtype=torch.int64, device="cuda")
+            ctx.select_rois(n, stats, shard.start, int(5000 * s * s), int(0.8 * h * w), int(50 * s), int(50 * s), rois, keys, cnt)
+            ctx.phash_indirect(sub, 1, rois, cnt, out)
+            c = int(cnt.item())
+            hh, kk = gather_hashes(out[:c], keys[:c], capacity=cap)
+            hs.append(hh); ks.append(kk)
+        allh, allk = torch.cat(hs), torch.cat(ks)
+        order = torch.argsort(allk)
+        allh, allk = allh[order].contiguous(), allk[order].contiguous()
+        keep = ctx.phash_dedup(allh, allk, 4)
+        results[world] = (allk.cpu().tolist(), allh.cpu().tolist(), keep.cpu().tolist())
+    assert len(results[1][0]) >= n_pages          # about two figures per page
+    assert 0 < sum(results[1][2]) < len(results[1][2])   # the stock figures repeat across pages: some are removed
+    for world in (2, 4, 8):
+        assert results[world] == results[1]
