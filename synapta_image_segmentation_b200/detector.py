@@ -169,18 +169,24 @@ class RasterRegionDetector:
         for r in regions:
             x, y, w, h = r["crop_px"]
             crop = Image.fromarray(np.ascontiguousarray(page_rgb[y:y + h, x:x + w]))
-            buf = io.BytesIO()
-            crop.save(buf, format="PNG")
-            png = buf.getvalue()
-            seg_id = f"{book_id}_p{page_num:03d}_{hashlib.md5(png).hexdigest()[:8]}"
-            path = None
-            if output_dir is not None:
-                import os
-                os.makedirs(output_dir, exist_ok=True)
-                path = os.path.join(output_dir, seg_id + ".png")
-                with open(path, "wb") as f:
-                    f.write(png)
-            segs.append(VisualSegment(segment_id=seg_id, segment_type=VisualType.UNKNOWN, book_id=book_id, page_no=page_num + 1,
-                                      bbox=r["bbox"], image_path=path, image_bytes=png, extraction_method=r["detection_method"],
-                                      caption_text=r["caption"], confidence=r["confidence"], notes=f"Validation: {r['validation']}"))
+            segs.append(self.segment_from_region(r, crop, page_num, book_id, output_dir))
         return segs
+
+    @staticmethod
+    def segment_from_region(r: Dict, crop, page_num: int, book_id: str, output_dir: Optional[str] = None) -> VisualSegment:
+        """Region dict + its PIL crop -> VisualSegment with the fields the reference sets at detection time
+        (:2787-2799, :2915-2927); the crop is PNG-encoded for the id and, with output_dir, saved under it."""
+        buf = io.BytesIO()
+        crop.save(buf, format="PNG")
+        png = buf.getvalue()
+        seg_id = f"{book_id}_p{page_num:03d}_{hashlib.md5(png).hexdigest()[:8]}"
+        path = None
+        if output_dir is not None:
+            import os
+            os.makedirs(output_dir, exist_ok=True)
+            path = os.path.join(output_dir, seg_id + ".png")
+            with open(path, "wb") as f:
+                f.write(png)
+        return VisualSegment(segment_id=seg_id, segment_type=VisualType.UNKNOWN, book_id=book_id, page_no=page_num + 1,
+                             bbox=r["bbox"], image_path=path, image_bytes=png, extraction_method=r["detection_method"],
+                             caption_text=r["caption"], confidence=r["confidence"], notes=f"Validation: {r['validation']}")

@@ -336,3 +336,30 @@ def test_config5_sharding_invariance(ctx):
     assert 0 < sum(results[1][2]) < len(results[1][2])   # the stock figures repeat across pages: some are removed
     for world in (2, 4, 8):
         assert results[world] == results[1]
+
+
+def test_raster_segmentation_pipeline_writes_reference_artefacts(ctx, tmp_path):
+    """pages -> segments -> `{book}_visual_segments.json` + `{book}_visual_summary.csv` + PNG crops, laid out like the
+    reference's run artefact (offline branch: type 'figure' via the fallback analysis, figure hints from the GPU)."""
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    from synapta_image_segmentation_b200.pipeline import FALLBACK_SUMMARY, RasterSegmentationPipeline
+    from synapta_image_segmentation_b200.writers import load_segments_json
+    det = RasterRegionDetector(DetectConfig(dpi=150), ctx=ctx)
+    pages = [synth_page(i, 150, n_figures=2)[0] for i in range(5)]
+    pl = RasterSegmentationPipeline("textbook_001", tmp_path, dpi=150, pdf_path="book.pdf", detector=det, batch=2)
+    segs = pl.process(iter(pages))
+    expected = det.detect_regions_batch(torch.from_numpy(np.stack(pages)).cuda(), page_nums=list(range(5)))
+    assert len(segs) == sum(len(r) for r in expected) >= 5
+    doc = load_segments_json(tmp_path / "textbook_001_visual_segments.json")
+    assert doc["book_id"] == "textbook_001" and doc["pdf_path"] == "book.pdf" and doc["total_segments"] == len(segs)
+    gold = json.load(open(os.path.join(GOLD, "reference_writers.json")))
+    for rec, seg in zip(doc["segments"], segs):
+        assert rec["segment_id"] == seg.segment_id and rec["segment_type"] == "figure"
+        assert rec["classification_method"] == "fallback_heuristic" and rec["summary"] == FALLBACK_SUMMARY
+        assert rec["notes"].startswith("Validation: ") and rec["confidence"] >= 0.5
+        assert set(rec["figure_details"]) == {"is_composite", "sub_figure_count", "contains_chart", "contains_diagram", "contains_image"}
+        assert os.path.exists(rec["image_path"]) and os.path.basename(rec["image_path"]) == seg.segment_id + ".png"
+        assert set(gold["a1_segment_keys"]) - {"image_details"} <= set(rec)
+        assert rec["page_no"] == int(seg.segment_id.split("_p")[1][:3]) + 1
+    csv_lines = (tmp_path / "textbook_001_visual_summary.csv").read_text().splitlines()
+    assert csv_lines[0] == gold["a1_csv_header"] and len(csv_lines) == len(segs) + 1

@@ -178,3 +178,33 @@ def test_gloo_world2_gather_and_replicated_dedup(tmp_path):
                         "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_writers_match_reference_bytes(tmp_path):
+    """SegmentWriter == the reference's _initialize_json_file / _save_results / _save_summary_csv (S:3852-3952), byte
+    for byte, on the constructed segments of tests/golden/make_schema_golden.py; key layout == the shipped run artefact."""
+    import importlib.util
+    from synapta_image_segmentation_b200 import datamodel as dm
+    from synapta_image_segmentation_b200.writers import SegmentWriter, load_segments_json
+    gold = json.load(open(os.path.join(GOLD, "reference_writers.json")))
+    spec = importlib.util.spec_from_file_location("make_schema_golden_segments", os.path.join(GOLD, "make_schema_golden.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    exec(src[src.index("def segments(mod):"):src.index("def main():")], ns)      # only the segment constructor, no reference import
+    segs = ns["segments"](dm)
+    w = SegmentWriter("textbook_001", "book.pdf", tmp_path, flush_every=2)
+    w.initialize()
+    assert w.output_json.read_text(encoding="utf-8") == gold["initialized_json"]
+    assert w.extend(segs) == len(segs)
+    assert w.append(segs[0]) is False                       # duplicate id is written once (S:3886-3887)
+    w.save_results()
+    assert w.output_json.read_text(encoding="utf-8") == gold["json"]
+    assert w.output_csv.read_bytes().decode("utf-8") == gold["csv"]
+    doc = load_segments_json(w.output_json)
+    assert list(doc.keys()) == gold["a1_top_keys"] and doc["total_segments"] == len(segs)
+    assert list(doc["segments"][0]["bbox"].keys()) == gold["a1_bbox_keys"]
+    image_seg = [s for s in doc["segments"] if s["segment_type"] == "image"][0]
+    assert list(image_seg.keys()) == gold["a1_segment_keys"]                     # same keys, same order as the shipped run
+    assert list(image_seg["image_details"].keys()) == gold["a1_image_details_keys"]
+    assert list(image_seg["image_data"].keys()) == gold["a1_image_data_keys"]
+    assert w.summary_csv_text().splitlines()[0] == gold["a1_csv_header"]
