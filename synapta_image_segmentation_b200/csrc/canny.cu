@@ -34,6 +34,7 @@ constexpr int CN_WARPS = SYNSEG_CN_WARPS;   // independent warps per CTA (1: a f
 #define SYNSEG_CN_MINBLOCKS (16 / SYNSEG_CN_WARPS)
 #endif
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int CN_DEPTH = 4;             // grey rows in flight per warp (cp.async ring)
 
 struct CnParams {
     Plane src;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 {
     __shared__ MagRing rings[CN_WARPS];
     __shared__ NmsStage stages[CN_WARPS];
+    __shared__ uint4 Rows[CN_WARPS][CN_DEPTH][32];   // cp.async ring of grey rows: [step][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t task = (int64_t)blockIdx.x * CN_WARPS + warp;
     if (task >= p.tasks) return;                      // warp-uniform
@@ -186,7 +188,19 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 #pragma unroll
     for (int c = 0; c < 16; ++c) st.cv16 |= (x + c >= 0 && x + c < W) ? (1u << c) : 0u;
 
-    auto load_raw = [&](int yy) { return load16_rep(base + (int64_t)min(max(yy, 0), H - 1) * rs, x, W, aligned); };
+    // Aligned rows: one 16-byte unit per lane and row at a clamped address; the replicated border is produced in
+    // registers when the row is consumed (fix16_rep), so loads never wait on data and run CN_DEPTH rows ahead through
+    // a cp.async ring in shared memory (no registers in flight; each lane reads back only its own copy).
+    const int xl = clamp16_x(x, W);
+    uint4 *ring = &Rows[warp][0][lane];
+    auto row_ptr = [&](int yy) { return base + (int64_t)min(max(yy, 0), H - 1) * rs; };
+    auto load_now = [&](int yy) -> uint4 {
+        return aligned ? fix16_rep(__ldg((const uint4 *)(row_ptr(yy) + xl)), x, W) : load16_rep(row_ptr(yy), x, W, false);
+    };
+    auto issue_async = [&](int yy, int slot) {           // yy may run past the band: the row index is clamped
+        if (aligned) cp_async16(ring + slot * 32, row_ptr(yy) + xl);
+        cp_async_commit();
+    };
     auto build_hrow = [&](HRow &h, const uint4 v) {
         const uint32_t wl = __shfl_up_sync(FULL, v.w, 1), wr = __shfl_down_sync(FULL, v.x, 1);
         make_hrow(h, v, wl, wr);
@@ -194,20 +208,26 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 
     HRow HX, HY, HZ;
     {
-        const uint4 v0 = load_raw(y0 - 2), v1 = load_raw(y0 - 1), v2 = load_raw(y0), v3 = load_raw(y0 + 1);
+        const uint4 v0 = load_now(y0 - 2), v1 = load_now(y0 - 1), v2 = load_now(y0), v3 = load_now(y0 + 1);
         build_hrow(HX, v0); build_hrow(HY, v1); build_hrow(HZ, v2);
         produce_row(R, st, (y0 + 2) % 3, lane, HX, HY, HZ, y0 - 1 >= 0);        // magnitude row y0 - 1
         build_hrow(HX, v3);
     }
     uint32_t cand_cur = produce_row(R, st, y0 % 3, lane, HY, HZ, HX, true);      // magnitude row y0
-    uint4 vnext = load_raw(y0 + 2);                                              // software pipeline: one row ahead
+#pragma unroll
+    for (int d = 0; d < CN_DEPTH; ++d) issue_async(y0 + 2 + d, d);               // rows y0+2 .. y0+2+CN_DEPTH-1 in flight
 
     int y = y0;
     // A = partials of grey row y, B = row y+1, C = free (receives row y+2)
 #define CANNY_STEP(A, B, C)                                                                                    \
     if (y < y1) {                                                                                              \
-        const uint4 vcur = vnext;                                                                              \
-        vnext = load_raw(y + 3);                                                                               \
+        uint4 vcur;                                                                                            \
+        if (aligned) {                                                                                         \
+            cp_async_wait<CN_DEPTH - 1>();                                                                     \
+            const int slot = (y - y0) % CN_DEPTH;                                                              \
+            vcur = fix16_rep(ring[slot * 32], x, W);                                                           \
+            issue_async(y + 2 + CN_DEPTH, slot);                                                               \
+        } else vcur = load16_rep(row_ptr(y + 2), x, W, false);                                                 \
         build_hrow(C, vcur);                                                                                   \
         const uint32_t cand_next = produce_row(R, st, (y + 1) % 3, lane, A, B, C, y + 1 < H);                  \
         __syncwarp();                                                                                          \

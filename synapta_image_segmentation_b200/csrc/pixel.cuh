@@ -45,32 +45,39 @@ __device__ __forceinline__ bool hsv_mask_px(uint32_t r, uint32_t g, uint32_t b, 
     return s > 30u && v > 40u && v < 240u;
 }
 
-// 16 consecutive grey pixels of a row starting at column x (any x), replicated outside [0, W)
-// (BORDER_REPLICATE).  `aligned` (kernel-uniform): row base and stride are 16-byte aligned and x is a multiple
-// of 16.  The aligned path issues exactly ONE 128-bit load per call for every lane (no divergent loads): the
-// address is clamped to the row's first / last 16-byte unit and the edge pixel is replicated with register
-// arithmetic.  It may read (never write) up to 15 bytes past column W-1 inside the row stride.
+// ---- 16 consecutive grey pixels of a row starting at column x (any x), BORDER_REPLICATE ------------------------
+// Aligned rows (base and stride 16-byte aligned, x a multiple of 16) are read with exactly ONE 128-bit load per
+// call for every lane: the address is clamped to the row's first / last 16-byte unit (clamp16_x) and the edge pixel
+// is replicated afterwards with register arithmetic (fix16_rep), so the load itself never depends on loaded data
+// and can be issued far ahead (registers or cp.async).  The vector path may read (never write) up to 15 bytes past
+// column W-1 inside the row stride.
+__device__ __forceinline__ int clamp16_x(int x, int W) { return min(max(x, 0), (W - 1) & ~15); }
+
+// v = the 16 bytes at column clamp16_x(x, W); returns the replicated-border pixels of columns x .. x+15
+__device__ __forceinline__ uint4 fix16_rep(uint4 v, int x, int W)
+{
+    const int xl = clamp16_x(x, W);
+    const int nv = W - xl;                             // valid bytes from xl on (>= 1)
+    if (x == xl && nv >= 16) return v;
+    const int bi = (x < 0) ? 0 : (min(nv, 16) - 1);    // byte that is replicated
+    const int lq = bi >> 2;
+    const uint32_t lw = lq == 0 ? v.x : (lq == 1 ? v.y : (lq == 2 ? v.z : v.w));
+    const uint32_t rep = ((lw >> (8 * (bi & 3))) & 0xFFu) * 0x01010101u;
+    if (x != xl) return make_uint4(rep, rep, rep, rep);                // wholly outside the image
+    const int k1 = nv - 4, k2 = nv - 8, k3 = nv - 12;                  // valid bytes in each word (nv < 16)
+    const uint32_t m0 = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+    const uint32_t m1 = k1 >= 4 ? 0xFFFFFFFFu : (k1 <= 0 ? 0u : ((1u << (8 * k1)) - 1u));
+    const uint32_t m2 = k2 >= 4 ? 0xFFFFFFFFu : (k2 <= 0 ? 0u : ((1u << (8 * k2)) - 1u));
+    const uint32_t m3 = k3 <= 0 ? 0u : ((1u << (8 * k3)) - 1u);
+    v.x = (v.x & m0) | (rep & ~m0); v.y = (v.y & m1) | (rep & ~m1);
+    v.z = (v.z & m2) | (rep & ~m2); v.w = (v.w & m3) | (rep & ~m3);
+    return v;
+}
+
+// generic form: any alignment (byte loads on unaligned rows)
 __device__ __forceinline__ uint4 load16_rep(const uint8_t *row, int x, int W, bool aligned)
 {
-    if (aligned) {
-        const int xl = min(max(x, 0), (W - 1) & ~15);
-        uint4 v = __ldg((const uint4 *)(row + xl));
-        const int nv = W - xl;                             // valid bytes from xl on (>= 1)
-        if (x == xl && nv >= 16) return v;
-        const int bi = (x < 0) ? 0 : (min(nv, 16) - 1);    // byte that is replicated
-        const int lq = bi >> 2;
-        const uint32_t lw = lq == 0 ? v.x : (lq == 1 ? v.y : (lq == 2 ? v.z : v.w));
-        const uint32_t rep = ((lw >> (8 * (bi & 3))) & 0xFFu) * 0x01010101u;
-        if (x != xl) return make_uint4(rep, rep, rep, rep);                // wholly outside the image
-        const int k1 = nv - 4, k2 = nv - 8, k3 = nv - 12;                  // valid bytes in each word (nv < 16)
-        const uint32_t m0 = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
-        const uint32_t m1 = k1 >= 4 ? 0xFFFFFFFFu : (k1 <= 0 ? 0u : ((1u << (8 * k1)) - 1u));
-        const uint32_t m2 = k2 >= 4 ? 0xFFFFFFFFu : (k2 <= 0 ? 0u : ((1u << (8 * k2)) - 1u));
-        const uint32_t m3 = k3 <= 0 ? 0u : ((1u << (8 * k3)) - 1u);
-        v.x = (v.x & m0) | (rep & ~m0); v.y = (v.y & m1) | (rep & ~m1);
-        v.z = (v.z & m2) | (rep & ~m2); v.w = (v.w & m3) | (rep & ~m3);
-        return v;
-    }
+    if (aligned) return fix16_rep(__ldg((const uint4 *)(row + clamp16_x(x, W))), x, W);
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -83,3 +90,12 @@ __device__ __forceinline__ uint4 load16_rep(const uint8_t *row, int x, int W, bo
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
+
+// ---- cp.async (LDGSTS) helpers: 16-byte global -> shared copies that occupy no registers while in flight --------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -67,12 +67,15 @@ __device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
     cs[6] -= __byte_perm(v.w, 0, 0x4240); cs[7] -= __byte_perm(v.w, 0, 0x4341);
 }
 
+constexpr int AD_DEPTH = 4;             // rows in flight per warp (cp.async ring)
+
 __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
 template <bool OUT_BITS>
 __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
 {
     __shared__ uint32_t Psm[AD_WARPS][2][16 * 33];   // [column within lane][lane], padded: conflict-free both ways
+    __shared__ uint4 Ring[AD_WARPS][AD_DEPTH][3][32]; // cp.async row ring: [step][new | old | centre][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t task = (int64_t)blockIdx.x * AD_WARPS + warp;
     if (task >= p.tasks) return;                      // warp-uniform
@@ -85,34 +88,60 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
     const uint8_t *base = p.src.p + img * p.src.bs;
     const bool out_lane = (CPL * lane >= p.lead) && (CPL * lane < p.lead + p.out_w) && (x < W);
-    // warp-uniform: every lane's 16 columns lie inside the image (4 of the 6 strips of a 300-DPI page) -> plain vector loads
-    const bool fast = src_aligned && __all_sync(FULL, x >= 0 && x + 15 < W);
-    auto ldrow = [&](int yy) -> uint4 {                      // yy inside the image
-        const uint8_t *rp = base + (int64_t)yy * p.src.rs;
-        return fast ? __ldg((const uint4 *)(rp + x)) : load16_rep(rp, x, W, src_aligned);
-    };
+    // Aligned rows: every lane reads one 16-byte unit per row at a clamped address (clamp16_x); the edge pixel is
+    // replicated in registers when the row is consumed (fix16_rep; a no-op compare for interior lanes).
+    const int xl = clamp16_x(x, W);
+    auto ldraw = [&](int yy) -> uint4 { return __ldg((const uint4 *)(base + (int64_t)yy * p.src.rs + xl)); };
 
     // running column sums over rows [y - r, y + r] (replicate)
     uint32_t cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 8
-    for (int dy = -r; dy <= r; ++dy) add16(cs, ldrow(min(max(y0 + dy, 0), H - 1)));
+    if (src_aligned) {
+        for (int dy = -r; dy <= r; dy += 8) {            // eight loads in flight, then eight accumulations
+            uint4 t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (dy + q <= r) t[q] = ldraw(min(max(y0 + dy + q, 0), H - 1));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (dy + q <= r) add16(cs, fix16_rep(t[q], x, W));
+        }
+    } else {
+        for (int dy = -r; dy <= r; ++dy) add16(cs, load16_rep(base + (int64_t)min(max(y0 + dy, 0), H - 1) * p.src.rs, x, W, false));
+    }
     const int kx = CPL * lane + r, ky = CPL * lane - r - 1;  // prefix indices of column j: kx + j, ky + j
     uint32_t colmask = 0;                                    // output columns of this lane inside the image
     if (out_lane) colmask = (W - x >= 16) ? 0xFFFFu : ((1u << (W - x)) - 1u);
 
-    // software pipeline: the three row loads of step y + 1 are issued before step y is computed
-    uint4 nnew, nold, ncen;
-    auto issue_loads = [&](int yy) {
-        nnew = ldrow(min(yy + r + 1, H - 1));
-        nold = ldrow(max(yy - r, 0));
-        ncen = ldrow(yy);
+    // Software pipeline (aligned rows): the three row loads of step y + AD_DEPTH are issued with cp.async into a
+    // per-warp shared-memory ring while step y is computed -- four rows of latency cover without a single extra
+    // register (every lane reads back only what it copied itself, so no barrier is needed).
+    uint4 *ring = &Ring[warp][0][0][lane];
+    auto issue_async = [&](int yy, int slot) {
+        if (yy < y1) {
+            cp_async16(ring + (slot * 3 + 0) * 32, base + (int64_t)min(yy + r + 1, H - 1) * p.src.rs + xl);
+            cp_async16(ring + (slot * 3 + 1) * 32, base + (int64_t)max(yy - r, 0) * p.src.rs + xl);
+            cp_async16(ring + (slot * 3 + 2) * 32, base + (int64_t)yy * p.src.rs + xl);
+        }
+        cp_async_commit();
     };
-    issue_loads(y0);
+    if (src_aligned) {
+#pragma unroll
+        for (int d = 0; d < AD_DEPTH; ++d) issue_async(y0 + d, d);
+    }
 
     for (int y = y0; y < y1; ++y) {
         uint32_t *Pb = Psm[warp][y & 1];
-        const uint4 vnew = nnew, vold = nold, vcen = ncen;
-        if (y + 1 < y1) issue_loads(y + 1);
+        uint4 vnew, vold, vcen;
+        if (src_aligned) {
+            cp_async_wait<AD_DEPTH - 1>();
+            const int slot = (y - y0) % AD_DEPTH;
+            vnew = fix16_rep(ring[(slot * 3 + 0) * 32], x, W);
+            vold = fix16_rep(ring[(slot * 3 + 1) * 32], x, W);
+            vcen = fix16_rep(ring[(slot * 3 + 2) * 32], x, W);
+            issue_async(y + AD_DEPTH, slot);
+        } else {
+            vnew = load16_rep(base + (int64_t)min(y + r + 1, H - 1) * p.src.rs, x, W, false);
+            vold = load16_rep(base + (int64_t)max(y - r, 0) * p.src.rs, x, W, false);
+            vcen = load16_rep(base + (int64_t)y * p.src.rs, x, W, false);
+        }
 
         // Row shortcut: mean <= 255, so a pixel with g + C > 255 can never satisfy mean >= g + C.  When no output
         // pixel of the whole strip row has g <= 255 - C (blank paper) the result is known without the window sums.
