@@ -192,10 +192,11 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     // registers when the row is consumed (fix16_rep), so loads never wait on data and run CN_DEPTH rows ahead through
     // a cp.async ring in shared memory (no registers in flight; each lane reads back only its own copy).
     const int xl = clamp16_x(x, W);
+    const EdgeFix efix = make_edge_fix(x, W);
     uint4 *ring = &Rows[warp][0][lane];
     auto row_ptr = [&](int yy) { return base + (int64_t)min(max(yy, 0), H - 1) * rs; };
     auto load_now = [&](int yy) -> uint4 {
-        return aligned ? fix16_rep(__ldg((const uint4 *)(row_ptr(yy) + xl)), x, W) : load16_rep(row_ptr(yy), x, W, false);
+        return aligned ? apply_edge_fix(__ldg((const uint4 *)(row_ptr(yy) + xl)), efix) : load16_rep(row_ptr(yy), x, W, false);
     };
     auto issue_async = [&](int yy, int slot) {           // yy may run past the band: the row index is clamped
         if (aligned) cp_async16(ring + slot * 32, row_ptr(yy) + xl);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         if (aligned) {                                                                                         \
             cp_async_wait<CN_DEPTH - 1>();                                                                     \
             const int slot = (y - y0) % CN_DEPTH;                                                              \
-            vcur = fix16_rep(ring[slot * 32], x, W);                                                           \
+            vcur = apply_edge_fix(ring[slot * 32], efix);                                                         \
             issue_async(y + 2 + CN_DEPTH, slot);                                                               \
         } else vcur = load16_rep(row_ptr(y + 2), x, W, false);                                                 \
         build_hrow(C, vcur);                                                                                   \

@@ -53,26 +53,44 @@ __device__ __forceinline__ bool hsv_mask_px(uint32_t r, uint32_t g, uint32_t b, 
 // column W-1 inside the row stride.
 __device__ __forceinline__ int clamp16_x(int x, int W) { return min(max(x, 0), (W - 1) & ~15); }
 
-// v = the 16 bytes at column clamp16_x(x, W); returns the replicated-border pixels of columns x .. x+15
-__device__ __forceinline__ uint4 fix16_rep(uint4 v, int x, int W)
+// Border replication of one lane, prepared once per kernel (it depends on x and W only).
+struct EdgeFix {
+    bool interior;          // all 16 columns inside the image: nothing to do
+    int sel_w, sel_sh;      // word / bit shift of the byte that is replicated
+    uint32_t m0, m1, m2, m3; // bytes kept per word (0 everywhere for a lane wholly outside the image)
+};
+
+__device__ __forceinline__ EdgeFix make_edge_fix(int x, int W)
 {
+    EdgeFix f;
     const int xl = clamp16_x(x, W);
     const int nv = W - xl;                             // valid bytes from xl on (>= 1)
-    if (x == xl && nv >= 16) return v;
+    f.interior = (x == xl && nv >= 16);
     const int bi = (x < 0) ? 0 : (min(nv, 16) - 1);    // byte that is replicated
-    const int lq = bi >> 2;
-    const uint32_t lw = lq == 0 ? v.x : (lq == 1 ? v.y : (lq == 2 ? v.z : v.w));
-    const uint32_t rep = ((lw >> (8 * (bi & 3))) & 0xFFu) * 0x01010101u;
-    if (x != xl) return make_uint4(rep, rep, rep, rep);                // wholly outside the image
-    const int k1 = nv - 4, k2 = nv - 8, k3 = nv - 12;                  // valid bytes in each word (nv < 16)
-    const uint32_t m0 = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
-    const uint32_t m1 = k1 >= 4 ? 0xFFFFFFFFu : (k1 <= 0 ? 0u : ((1u << (8 * k1)) - 1u));
-    const uint32_t m2 = k2 >= 4 ? 0xFFFFFFFFu : (k2 <= 0 ? 0u : ((1u << (8 * k2)) - 1u));
-    const uint32_t m3 = k3 <= 0 ? 0u : ((1u << (8 * k3)) - 1u);
-    v.x = (v.x & m0) | (rep & ~m0); v.y = (v.y & m1) | (rep & ~m1);
-    v.z = (v.z & m2) | (rep & ~m2); v.w = (v.w & m3) | (rep & ~m3);
+    f.sel_w = bi >> 2; f.sel_sh = 8 * (bi & 3);
+    if (x != xl) { f.m0 = f.m1 = f.m2 = f.m3 = 0u; }   // wholly outside the image
+    else {
+        const int k1 = nv - 4, k2 = nv - 8, k3 = nv - 12;
+        f.m0 = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+        f.m1 = k1 >= 4 ? 0xFFFFFFFFu : (k1 <= 0 ? 0u : ((1u << (8 * k1)) - 1u));
+        f.m2 = k2 >= 4 ? 0xFFFFFFFFu : (k2 <= 0 ? 0u : ((1u << (8 * k2)) - 1u));
+        f.m3 = k3 >= 4 ? 0xFFFFFFFFu : (k3 <= 0 ? 0u : ((1u << (8 * k3)) - 1u));
+    }
+    return f;
+}
+
+// v = the 16 bytes at column clamp16_x(x, W); returns the replicated-border pixels of columns x .. x+15
+__device__ __forceinline__ uint4 apply_edge_fix(uint4 v, const EdgeFix &f)
+{
+    if (f.interior) return v;
+    const uint32_t lw = f.sel_w == 0 ? v.x : (f.sel_w == 1 ? v.y : (f.sel_w == 2 ? v.z : v.w));
+    const uint32_t rep = ((lw >> f.sel_sh) & 0xFFu) * 0x01010101u;
+    v.x = (v.x & f.m0) | (rep & ~f.m0); v.y = (v.y & f.m1) | (rep & ~f.m1);
+    v.z = (v.z & f.m2) | (rep & ~f.m2); v.w = (v.w & f.m3) | (rep & ~f.m3);
     return v;
 }
+
+__device__ __forceinline__ uint4 fix16_rep(uint4 v, int x, int W) { return apply_edge_fix(v, make_edge_fix(x, W)); }
 
 // generic form: any alignment (byte loads on unaligned rows)
 __device__ __forceinline__ uint4 load16_rep(const uint8_t *row, int x, int W, bool aligned)

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     // Aligned rows: every lane reads one 16-byte unit per row at a clamped address (clamp16_x); the edge pixel is
     // replicated in registers when the row is consumed (fix16_rep; a no-op compare for interior lanes).
     const int xl = clamp16_x(x, W);
+    const EdgeFix efix = make_edge_fix(x, W);
     auto ldraw = [&](int yy) -> uint4 { return __ldg((const uint4 *)(base + (int64_t)yy * p.src.rs + xl)); };
 
     // running column sums over rows [y - r, y + r] (replicate)
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
 #pragma unroll
             for (int q = 0; q < 8; ++q) if (dy + q <= r) t[q] = ldraw(min(max(y0 + dy + q, 0), H - 1));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) if (dy + q <= r) add16(cs, fix16_rep(t[q], x, W));
+            for (int q = 0; q < 8; ++q) if (dy + q <= r) add16(cs, apply_edge_fix(t[q], efix));
         }
     } else {
         for (int dy = -r; dy <= r; ++dy) add16(cs, load16_rep(base + (int64_t)min(max(y0 + dy, 0), H - 1) * p.src.rs, x, W, false));
@@ -133,9 +134,9 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
         if (src_aligned) {
             cp_async_wait<AD_DEPTH - 1>();
             const int slot = (y - y0) % AD_DEPTH;
-            vnew = fix16_rep(ring[(slot * 3 + 0) * 32], x, W);
-            vold = fix16_rep(ring[(slot * 3 + 1) * 32], x, W);
-            vcen = fix16_rep(ring[(slot * 3 + 2) * 32], x, W);
+            vnew = apply_edge_fix(ring[(slot * 3 + 0) * 32], efix);
+            vold = apply_edge_fix(ring[(slot * 3 + 1) * 32], efix);
+            vcen = apply_edge_fix(ring[(slot * 3 + 2) * 32], efix);
             issue_async(y + AD_DEPTH, slot);
         } else {
             vnew = load16_rep(base + (int64_t)min(y + r + 1, H - 1) * p.src.rs, x, W, false);
