@@ -198,10 +198,18 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     auto load_now = [&](int yy) -> uint4 {
         return aligned ? apply_edge_fix(__ldg((const uint4 *)(row_ptr(yy) + xl)), efix) : load16_rep(row_ptr(yy), x, W, false);
     };
-    auto issue_async = [&](int yy, int slot) {           // yy may run past the band: the row index is clamped
-        if (aligned) cp_async16(ring + slot * 32, row_ptr(yy) + xl);
+    // running pointers (no 64-bit multiplies in the row loop): the row being prefetched and the two output rows
+    int y_pf = y0 + 2;                                              // next row to prefetch (clamped into the image)
+    const uint8_t *p_pf = row_ptr(y_pf) + xl;
+    auto issue_async = [&](int slot) {
+        if (aligned) cp_async16(ring + slot * 32, p_pf);
         cp_async_commit();
+        ++y_pf;
+        if (y_pf >= 1 && y_pf <= H - 1) p_pf += rs;                 // the pointer only moves while the row index is inside [1, H-1]
     };
+    uint32_t *kp = p.kept.p + img * p.kept.bs + (int64_t)y0 * p.kept.wpr + (max(x, 0) >> 5);
+    uint32_t *sp = p.strong.p + img * p.strong.bs + (int64_t)y0 * p.strong.wpr + (max(x, 0) >> 5);
+    const int k_wpr = p.kept.wpr, s_wpr = p.strong.wpr;
     auto build_hrow = [&](HRow &h, const uint4 v) {
         const uint32_t wl = __shfl_up_sync(FULL, v.w, 1), wr = __shfl_down_sync(FULL, v.x, 1);
         make_hrow(h, v, wl, wr);
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     }
     uint32_t cand_cur = produce_row(R, st, y0 % 3, lane, HY, HZ, HX, true);      // magnitude row y0
 #pragma unroll
-    for (int d = 0; d < CN_DEPTH; ++d) issue_async(y0 + 2 + d, d);               // rows y0+2 .. y0+2+CN_DEPTH-1 in flight
+    for (int d = 0; d < CN_DEPTH; ++d) issue_async(d);                           // rows y0+2 .. y0+2+CN_DEPTH-1 in flight
+    int slot = 0;
 
     int y = y0;
     // A = partials of grey row y, B = row y+1, C = free (receives row y+2)
@@ -225,9 +234,9 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         uint4 vcur;                                                                                            \
         if (aligned) {                                                                                         \
             cp_async_wait<CN_DEPTH - 1>();                                                                     \
-            const int slot = (y - y0) % CN_DEPTH;                                                              \
-            vcur = apply_edge_fix(ring[slot * 32], efix);                                                         \
-            issue_async(y + 2 + CN_DEPTH, slot);                                                               \
+            vcur = apply_edge_fix(ring[slot * 32], efix);                                                      \
+            issue_async(slot);                                                                                 \
+            slot = (slot + 1) & (CN_DEPTH - 1);                                                                \
         } else vcur = load16_rep(row_ptr(y + 2), x, W, false);                                                 \
         build_hrow(C, vcur);                                                                                   \
         const uint32_t cand_next = produce_row(R, st, (y + 1) % 3, lane, A, B, C, y + 1 < H);                  \
@@ -250,11 +259,8 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
             kept16 = S.kept[lane]; strong16 = S.strong[lane];                                                  \
         }                                                                                                      \
         const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);   \
-        if (writer) {                                                                                          \
-            const int64_t o = (int64_t)y * p.kept.wpr + (x >> 5);                                              \
-            p.kept.p[img * p.kept.bs + o] = kept16 | (k_up << 16);                                             \
-            p.strong.p[img * p.strong.bs + o] = strong16 | (s_up << 16);                                       \
-        }                                                                                                      \
+        if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }                            \
+        kp += k_wpr; sp += s_wpr;                                                                              \
         cand_cur = cand_next;                                                                                  \
         __syncwarp();                                                                                          \
         ++y;                                                                                                   \

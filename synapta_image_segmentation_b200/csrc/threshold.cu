@@ -115,29 +115,41 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     // per-warp shared-memory ring while step y is computed -- four rows of latency cover without a single extra
     // register (every lane reads back only what it copied itself, so no barrier is needed).
     uint4 *ring = &Ring[warp][0][0][lane];
-    auto issue_async = [&](int yy, int slot) {
-        if (yy < y1) {
-            cp_async16(ring + (slot * 3 + 0) * 32, base + (int64_t)min(yy + r + 1, H - 1) * p.src.rs + xl);
-            cp_async16(ring + (slot * 3 + 1) * 32, base + (int64_t)max(yy - r, 0) * p.src.rs + xl);
-            cp_async16(ring + (slot * 3 + 2) * 32, base + (int64_t)yy * p.src.rs + xl);
+    // running pointers (no 64-bit multiplies in the row loop): rows y+r+1 (clamped to H-1), y-r (clamped to 0) and y
+    int y_pf = y0;                                                    // next step to prefetch
+    const uint8_t *p_new = base + (int64_t)min(y0 + r + 1, H - 1) * p.src.rs + xl;
+    const uint8_t *p_old = base + (int64_t)max(y0 - r, 0) * p.src.rs + xl;
+    const uint8_t *p_cen = base + (int64_t)y0 * p.src.rs + xl;
+    const int64_t rs = p.src.rs;
+    auto issue_async = [&](int slot) {
+        if (y_pf < y1) {
+            cp_async16(ring + (slot * 3 + 0) * 32, p_new);
+            cp_async16(ring + (slot * 3 + 1) * 32, p_old);
+            cp_async16(ring + (slot * 3 + 2) * 32, p_cen);
         }
         cp_async_commit();
+        if (y_pf + r + 1 < H - 1) p_new += rs;                        // row of the next step: min(y_pf + 1 + r + 1, H - 1)
+        if (y_pf - r >= 0) p_old += rs;                               //                       max(y_pf + 1 - r, 0)
+        p_cen += rs;
+        ++y_pf;
     };
     if (src_aligned) {
 #pragma unroll
-        for (int d = 0; d < AD_DEPTH; ++d) issue_async(y0 + d, d);
+        for (int d = 0; d < AD_DEPTH; ++d) issue_async(d);
     }
+    int slot = 0;
+    uint32_t *obits = OUT_BITS ? p.bits.p + img * p.bits.bs + (int64_t)y0 * p.bits.wpr + (max(x, 0) >> 5) : nullptr;
 
     for (int y = y0; y < y1; ++y) {
         uint32_t *Pb = Psm[warp][y & 1];
         uint4 vnew, vold, vcen;
         if (src_aligned) {
             cp_async_wait<AD_DEPTH - 1>();
-            const int slot = (y - y0) % AD_DEPTH;
             vnew = apply_edge_fix(ring[(slot * 3 + 0) * 32], efix);
             vold = apply_edge_fix(ring[(slot * 3 + 1) * 32], efix);
             vcen = apply_edge_fix(ring[(slot * 3 + 2) * 32], efix);
-            issue_async(y + AD_DEPTH, slot);
+            issue_async(slot);
+            slot = (slot + 1) & (AD_DEPTH - 1);
         } else {
             vnew = load16_rep(base + (int64_t)min(y + r + 1, H - 1) * p.src.rs, x, W, false);
             vold = load16_rep(base + (int64_t)max(y - r, 0) * p.src.rs, x, W, false);
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
                 const uint32_t cbits = p.invert ? 0u : colmask;
                 if (OUT_BITS) {
                     const uint32_t other = __shfl_xor_sync(FULL, cbits, 1);
-                    if (out_lane && !(lane & 1)) p.bits.p[img * p.bits.bs + (int64_t)y * p.bits.wpr + (x >> 5)] = cbits | (other << 16);
+                    if (out_lane && !(lane & 1)) obits[(int64_t)(y - y0) * p.bits.wpr] = cbits | (other << 16);
                 } else if (out_lane) {
                     uint8_t *drow = p.dst.p + img * p.dst.bs + (int64_t)y * p.dst.rs + x;
                     const uint32_t fill = p.invert ? 0u : 0xFFFFFFFFu;
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
         }
         if (OUT_BITS) {
             const uint32_t other = __shfl_xor_sync(FULL, bits16, 1);
-            if (out_lane && !(lane & 1)) p.bits.p[img * p.bits.bs + (int64_t)y * p.bits.wpr + (x >> 5)] = bits16 | (other << 16);
+            if (out_lane && !(lane & 1)) obits[(int64_t)(y - y0) * p.bits.wpr] = bits16 | (other << 16);
         } else if (out_lane) {
             uint8_t *drow = p.dst.p + img * p.dst.bs + (int64_t)y * p.dst.rs + x;
             if (dst_aligned && x + 15 < W) {
