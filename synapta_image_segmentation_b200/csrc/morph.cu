@@ -20,6 +20,7 @@
 //  * generic 8-bit path: per-thread in-place doubling (sparse-table) over packed bytes in shared
 //    memory with __vmaxu4/__vminu4 -- any grey image, any k.
 #include "internal.cuh"
+#include "pixel.cuh"
 
 namespace {
 
@@ -302,25 +303,46 @@ __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPla
     const uint32_t *sp = src.p + img * src.bs + w;
     uint32_t *dp = dst.p + img * dst.bs + w;
     const int ys = seg * k, u0 = ys - anchor;
+    // first block -> private shared-memory column with 4-byte cp.async copies (all k loads in flight at once, no
+    // registers); rows outside the image hold the identity of the raw domain (0 for dilate, all ones for erode)
+    const uint32_t ident_raw = erode ? 0xffffffffu : 0u;
+    for (int j = 0; j < k; ++j) {
+        const int u = u0 + j;
+        if (u >= 0 && u < height) cp_async4(&sm[j * T + tid], sp + (int64_t)u * src.wpr);
+        else sm[j * T + tid] = ident_raw;
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    {   // suffix ORs in place (erode: on the complemented rows)
+        uint32_t acc = 0;
+        for (int j = k - 1; j >= 0; --j) {
+            uint32_t v = sm[j * T + tid];
+            if (erode) v = ~v & vmask;
+            acc |= v;
+            sm[j * T + tid] = acc;
+        }
+    }
     auto ld = [&](int u) -> uint32_t {
         if (u < 0 || u >= height) return 0u;
-        uint32_t v = __ldg(sp + (int64_t)u * src.wpr);
+        const uint32_t v = __ldg(sp + (int64_t)u * src.wpr);
         return erode ? (~v & vmask) : v;
     };
-#pragma unroll 8
-    for (int j = 0; j < k; ++j) sm[j * T + tid] = ld(u0 + j);
-    {
-        uint32_t acc = sm[(k - 1) * T + tid];
-        for (int j = k - 2; j >= 0; --j) { acc |= sm[j * T + tid]; sm[j * T + tid] = acc; }
-    }
     uint32_t g = 0;
     const int n_out = min(k, height - ys);
-#pragma unroll 4
-    for (int i = 0; i < n_out; ++i) {
-        if (i > 0) g |= ld(u0 + k + i - 1);
-        uint32_t v = sm[i * T + tid] | g;
-        if (erode) v = ~v;
-        dp[(int64_t)(ys + i) * dst.wpr] = v & vmask;
+    for (int i0 = 0; i0 < n_out; i0 += 8) {            // eight loads of the second block in flight per batch
+        uint32_t t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = (i0 + q > 0 && i0 + q < n_out) ? ld(u0 + k + i0 + q - 1) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q;
+            if (i < n_out) {
+                g |= t[q];
+                uint32_t v = sm[i * T + tid] | g;
+                if (erode) v = ~v;
+                dp[(int64_t)(ys + i) * dst.wpr] = v & vmask;
+            }
+        }
     }
 }
 
