@@ -32,31 +32,48 @@ __global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, 
     int y1 = (int)((long long)(i + 1) * h / 32);
     if (y1 <= y0) y1 = y0 + 1;
     const int mode = src_kind == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV;
-    for (int x = tid; x < w; x += 256) {
-        uint32_t s = 0;
-        if (src_kind == 0) {
-            const uint8_t *p = base + (int64_t)(r.y + y0) * src.rs + r.x + x;
-            int y = y0;
-            for (; y + 4 <= y1; y += 4, p += 4 * src.rs)
-                s += (uint32_t)__ldg(p) + __ldg(p + src.rs) + __ldg(p + 2 * src.rs) + __ldg(p + 3 * src.rs);
-            for (; y < y1; ++y, p += src.rs) s += __ldg(p);
-        } else {
-            const uint8_t *p = base + (int64_t)(r.y + y0) * src.rs + 3 * (int64_t)(r.x + x);
-            int y = y0;
-            for (; y + 4 <= y1; y += 4, p += 4 * src.rs) {
-                uint32_t px[4];
+    const int bpp = src_kind == 0 ? 1 : 3;
+    const int64_t row_bytes = (int64_t)width * bpp;                  // bytes of an image row that may be read
+    // Four pixels per thread and row.  Their 4*bpp bytes are fetched as aligned 32-bit words and funnel-shifted by the
+    // byte phase of the row (the same for every thread of the row), a third of the load instructions of a byte loop;
+    // threads whose words would cross the end of the image row take the byte path.
+    for (int x = 4 * tid; x < w; x += 4 * 256) {
+        uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        const int npx = min(4, w - x);
+        const int64_t off = (int64_t)(r.x + x) * bpp;                // byte offset of the first pixel inside the row
+        for (int y = y0; y < y1; ++y) {
+            const uint8_t *row = base + (int64_t)(r.y + y) * src.rs;
+            const uint8_t *pa = row + off;
+            const int ph = (int)((uintptr_t)pa & 3);
+            const uint32_t *wp = (const uint32_t *)(pa - ph);
+            uint32_t px[4];
+            if (npx == 4 && off - ph >= 0 && off - ph + 4 * (bpp + 1) <= row_bytes) {
+                if (bpp == 3) {
+                    const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                    const int sh = 8 * ph;
+                    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+                    px[0] = b0; px[1] = __funnelshift_r(b0, b1, 24); px[2] = __funnelshift_r(b1, b2, 16); px[3] = b2 >> 8;
+                } else {
+                    const uint32_t g4 = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * ph);
+                    px[0] = g4 & 255u; px[1] = (g4 >> 8) & 255u; px[2] = (g4 >> 16) & 255u; px[3] = g4 >> 24;
+                }
+            } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint8_t *q = p + k * src.rs;
-                    px[k] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+                    px[k] = 0;
+                    if (k < npx) {
+                        const uint8_t *q = pa + k * bpp;
+                        px[k] = bpp == 3 ? ((uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16)) : (uint32_t)__ldg(q);
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s += gray_dyn(px[k], mode);
             }
-            for (; y < y1; ++y, p += src.rs)
-                s += gray_dyn((uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16), mode);
+            if (bpp == 3) { s0 += gray_dyn(px[0], mode); s1 += gray_dyn(px[1], mode); s2 += gray_dyn(px[2], mode); s3 += gray_dyn(px[3], mode); }
+            else { s0 += px[0]; s1 += px[1]; s2 += px[2]; s3 += px[3]; }
         }
-        colsum[x] = s;
+        colsum[x] = s0;
+        if (npx > 1) colsum[x + 1] = s1;
+        if (npx > 2) colsum[x + 2] = s2;
+        if (npx > 3) colsum[x + 3] = s3;
     }
     __syncthreads();
     if (tid < 32) {
