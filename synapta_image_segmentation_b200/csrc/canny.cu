@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         return aligned ? apply_edge_fix(__ldg((const uint4 *)(row_ptr(yy) + xl)), efix) : load16_rep(row_ptr(yy), x, W, false);
     };
     // running pointers (no 64-bit multiplies in the row loop): the row being prefetched and the two output rows
-    int y_pf = y0 + 2;                                              // next row to prefetch (clamped into the image)
+    int y_pf = y0;                                                  // next row to prefetch (clamped into the image)
     const uint8_t *p_pf = row_ptr(y_pf) + xl;
     auto issue_async = [&](int slot) {
         if (aligned) cp_async16(ring + slot * 32, p_pf);
@@ -215,62 +215,55 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         make_hrow(h, v, wl, wr);
     };
 
-    HRow HX, HY, HZ;
-    {
-        const uint4 v0 = load_now(y0 - 2), v1 = load_now(y0 - 1), v2 = load_now(y0), v3 = load_now(y0 + 1);
-        build_hrow(HX, v0); build_hrow(HY, v1); build_hrow(HZ, v2);
-        produce_row(R, st, (y0 + 2) % 3, lane, HX, HY, HZ, y0 - 1 >= 0);        // magnitude row y0 - 1
-        build_hrow(HX, v3);
-    }
-    uint32_t cand_cur = produce_row(R, st, y0 % 3, lane, HY, HZ, HX, true);      // magnitude row y0
+    // One loop does everything, including the two priming steps (y = y0-2, y0-1 produce the magnitude rows y0-1, y0
+    // without emitting output): a single copy of the row step keeps the loop body inside the instruction cache
+    // (three unrolled copies were 3800 SASS instructions and 18 % slower).
+    // A = partials of grey row y, B = row y+1, C = free (receives row y+2); rotated by register moves.
+    HRow A, B, C;
+    build_hrow(A, load_now(y0 - 2));
+    build_hrow(B, load_now(y0 - 1));
 #pragma unroll
-    for (int d = 0; d < CN_DEPTH; ++d) issue_async(d);                           // rows y0+2 .. y0+2+CN_DEPTH-1 in flight
+    for (int d = 0; d < CN_DEPTH; ++d) issue_async(d);                           // rows y0 .. y0+CN_DEPTH-1 in flight
     int slot = 0;
-
-    int y = y0;
-    // A = partials of grey row y, B = row y+1, C = free (receives row y+2)
-#define CANNY_STEP(A, B, C)                                                                                    \
-    if (y < y1) {                                                                                              \
-        uint4 vcur;                                                                                            \
-        if (aligned) {                                                                                         \
-            cp_async_wait<CN_DEPTH - 1>();                                                                     \
-            vcur = apply_edge_fix(ring[slot * 32], efix);                                                      \
-            issue_async(slot);                                                                                 \
-            slot = (slot + 1) & (CN_DEPTH - 1);                                                                \
-        } else vcur = load16_rep(row_ptr(y + 2), x, W, false);                                                 \
-        build_hrow(C, vcur);                                                                                   \
-        const uint32_t cand_next = produce_row(R, st, (y + 1) % 3, lane, A, B, C, y + 1 < H);                  \
-        __syncwarp();                                                                                          \
-        uint32_t kept16 = 0, strong16 = 0;                                                                     \
-        const uint32_t mycand = out_lane ? cand_cur : 0u;                                                      \
-        if (__any_sync(FULL, mycand != 0u)) {                                                                   \
-            /* balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes */      \
-            const int cnt = __popc(mycand);                                                                    \
-            int incl = cnt;                                                                                    \
-            _Pragma("unroll")                                                                                  \
-            for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; } \
-            const int total = __shfl_sync(FULL, incl, 31);                                                     \
-            int pos = incl - cnt;                                                                              \
-            for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1)); \
-            S.kept[lane] = 0u; S.strong[lane] = 0u;                                                            \
-            __syncwarp();                                                                                      \
-            for (int q = lane; q < total; q += 32) { const int id = S.list[q]; nms_one(R, st, S, y, id >> 4, id & 15, hi); } \
-            __syncwarp();                                                                                      \
-            kept16 = S.kept[lane]; strong16 = S.strong[lane];                                                  \
-        }                                                                                                      \
-        const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);   \
-        if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }                            \
-        kp += k_wpr; sp += s_wpr;                                                                              \
-        cand_cur = cand_next;                                                                                  \
-        __syncwarp();                                                                                          \
-        ++y;                                                                                                   \
+    uint32_t cand_cur = 0;
+#pragma unroll 1
+    for (int y = y0 - 2; y < y1; ++y) {
+        uint4 vcur;
+        if (aligned) {
+            cp_async_wait<CN_DEPTH - 1>();
+            vcur = apply_edge_fix(ring[slot * 32], efix);
+            issue_async(slot);
+            slot = (slot + 1) & (CN_DEPTH - 1);
+        } else vcur = load16_rep(row_ptr(y + 2), x, W, false);
+        build_hrow(C, vcur);
+        const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
+        __syncwarp();
+        if (y >= y0) {
+            uint32_t kept16 = 0, strong16 = 0;
+            const uint32_t mycand = out_lane ? cand_cur : 0u;
+            if (__any_sync(FULL, mycand != 0u)) {
+                // balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes
+                const int cnt = __popc(mycand);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
+                const int total = __shfl_sync(FULL, incl, 31);
+                int pos = incl - cnt;
+                for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1));
+                S.kept[lane] = 0u; S.strong[lane] = 0u;
+                __syncwarp();
+                for (int q = lane; q < total; q += 32) { const int id = S.list[q]; nms_one(R, st, S, y, id >> 4, id & 15, hi); }
+                __syncwarp();
+                kept16 = S.kept[lane]; strong16 = S.strong[lane];
+            }
+            const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
+            if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }
+            kp += k_wpr; sp += s_wpr;
+        }
+        cand_cur = cand_next;
+        __syncwarp();          // ring row (y+2) mod 3 == (y-1) mod 3 is overwritten next iteration
+        const HRow t = A; A = B; B = C; C = t;
     }
-    while (y < y1) {
-        CANNY_STEP(HZ, HX, HY)
-        CANNY_STEP(HX, HY, HZ)
-        CANNY_STEP(HY, HZ, HX)
-    }
-#undef CANNY_STEP
 }
 
 }  // namespace
