@@ -158,8 +158,11 @@ __device__ __forceinline__ void nms_one(const MagRing &R, const CnState &st, Nms
     }
 }
 
-__global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_classes_kernel(CnParams p, bool aligned)
+// ALIGNED (source rows 16-byte aligned) is a template parameter: the byte-load fallback stays out of the hot code.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_classes_kernel(CnParams p)
 {
+    constexpr bool aligned = ALIGNED;
     __shared__ MagRing rings[CN_WARPS];
     __shared__ NmsStage stages[CN_WARPS];
     __shared__ uint4 Rows[CN_WARPS][CN_DEPTH][32];   // cp.async ring of grey rows: [step][lane]
@@ -286,7 +289,8 @@ int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept,
     p.band_h = band_h;
     p.bands = cdiv(gray->height, band_h);
     p.tasks = (int64_t)gray->batch * p.bands * p.strips;
-    canny_classes_kernel<<<(unsigned)cdiv(p.tasks, CN_WARPS), 32 * CN_WARPS, 0, st>>>(p, plane_aligned(gray, 16));
+    if (plane_aligned(gray, 16)) canny_classes_kernel<true><<<(unsigned)cdiv(p.tasks, CN_WARPS), 32 * CN_WARPS, 0, st>>>(p);
+    else canny_classes_kernel<false><<<(unsigned)cdiv(p.tasks, CN_WARPS), 32 * CN_WARPS, 0, st>>>(p);
     SS_LAUNCH_CHECK(ctx, "canny_classes", st);
     return SYNSEG_OK;
 }

@@ -71,9 +71,12 @@ constexpr int AD_DEPTH = 4;             // rows in flight per warp (cp.async rin
 
 __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
-template <bool OUT_BITS>
-__global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool src_aligned, bool dst_aligned)
+// ALIGNED (source rows 16-byte aligned) is a template parameter so that the byte-load fallback does not sit between
+// the hot instructions of the common case (the loop body has to stay inside the instruction cache).
+template <bool OUT_BITS, bool ALIGNED>
+__global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool dst_aligned)
 {
+    constexpr bool src_aligned = ALIGNED;
     __shared__ uint32_t Psm[AD_WARPS][2][16 * 33];   // [column within lane][lane], padded: conflict-free both ways
     __shared__ uint4 Ring[AD_WARPS][AD_DEPTH][3][32]; // cp.async row ring: [step][new | old | centre][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -274,8 +277,13 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     const bool sal = plane_aligned(gray, 16);
     const bool dal = to_bits ? true : plane_aligned(out_u8, 16);
     const unsigned nblocks = (unsigned)cdiv(p.tasks, AD_WARPS);
-    if (to_bits) adaptive_mean_kernel<true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, sal, dal);
-    else adaptive_mean_kernel<false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, sal, dal);
+    if (to_bits) {
+        if (sal) adaptive_mean_kernel<true, true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else adaptive_mean_kernel<true, false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+    } else {
+        if (sal) adaptive_mean_kernel<false, true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else adaptive_mean_kernel<false, false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+    }
     SS_LAUNCH_CHECK(ctx, "adaptive_mean", st);
     return SYNSEG_OK;
 }
