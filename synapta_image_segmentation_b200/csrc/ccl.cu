@@ -106,6 +106,17 @@ __device__ __forceinline__ u64 next_piece(const Runs &r, int chunk, u64 &rem, in
     return range;
 }
 
+// pixel-column range of the run piece (inside this chunk) that holds the block at even bit position `pos`
+__device__ __forceinline__ u64 piece_range(const Runs &r, int pos)
+{
+    const u64 m = r.startE & ((2ULL << pos) - 1ULL);
+    const int sp = m ? 63 - __clzll((long long)m) : 0;          // a piece without a start in the chunk begins at bit 0
+    const u64 brk = (~r.occE | r.startE) & EVEN;
+    const u64 above = (pos >= 62) ? 0ULL : (brk & (~0ULL << (pos + 2)));
+    const int e = above ? __ffsll((long long)above) - 1 : 64;
+    return ((e >= 64) ? ~0ULL : ((1ULL << e) - 1ULL)) & (~0ULL << sp);
+}
+
 // ---- union-find -----------------------------------------------------------------------------
 // Parents only ever decrease and every value written is an ancestor, so stale reads are harmless;
 // L2-coherent loads because other SMs write concurrently.
@@ -162,8 +173,13 @@ __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall
     }
 }
 
-// unions between the runs of block row `by` and those of block row by - 1
-__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lall)
+// unions between the runs of block row `by` and those of block row by - 1.
+// HYST (hysteresis): a union between two runs that BOTH hold a strong pixel is skipped -- both are kept anyway, and
+// every weak run still reaches a strong run of its component through unions that involve at least one weak run
+// (take a path to the nearest strong run: all its edges but none beyond have a weak end).  The test is made on the
+// run pieces inside this lane's chunk (a subset of the runs), so it only ever skips safely.
+template <bool HYST>
+__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lall, BitPlane strong)
 {
     ROW_PROLOGUE(1)
     if (!row_ok) return;
@@ -185,18 +201,25 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lal
         const u64 tl = (t << 1) | tp, ul = (u << 1) | up;      // tl[x] = t[x-1]
         u64 ev_a = t & ~tl & (u | ul);
         u64 ev_b = u & ~ul & tl;
+        u64 sc = 0, su = 0;                                     // strong pixels of the current / upper block row
+        if (HYST && (ev_a | ev_b)) {
+            const uint32_t *s0 = strong.p + img * strong.bs + (int64_t)(2 * by) * strong.wpr;
+            sc = load_chunk(s0, chunk, g.width) | load_chunk(r1 ? s0 + strong.wpr : nullptr, chunk, g.width);
+            su = load_chunk(s0 - strong.wpr, chunk, g.width) | load_chunk(s0 - 2 * strong.wpr, chunk, g.width);
+        }
         while (ev_a) {
             const int x = __ffsll((long long)ev_a) - 1;
             ev_a &= ev_a - 1;
+            const int ux = ((u >> x) & 1ULL) ? x : x - 1;       // upper pixel of the contact (-1: last pixel of the previous chunk)
+            if (HYST && ux >= 0 && (sc & piece_range(rc, x & ~1)) && (su & piece_range(ru, ux & ~1))) continue;
             const int cs = run_start(rc, chunk, x & ~1);
-            int us;
-            if ((u >> x) & 1ULL) us = run_start(ru, chunk, x & ~1);
-            else us = (x > 0) ? run_start(ru, chunk, (x - 1) & ~1) : ru.carryIn;
+            const int us = (ux >= 0) ? run_start(ru, chunk, ux & ~1) : ru.carryIn;
             uf_union(L, cur_base + cs, up_base + us);
         }
         while (ev_b) {
             const int x = __ffsll((long long)ev_b) - 1;
             ev_b &= ev_b - 1;
+            if (HYST && x > 0 && (sc & piece_range(rc, (x - 1) & ~1)) && (su & piece_range(ru, x & ~1))) continue;
             const int us = run_start(ru, chunk, x & ~1);
             const int cs = (x > 0) ? run_start(rc, chunk, (x - 1) & ~1) : rc.carryIn;
             uf_union(L, cur_base + cs, up_base + us);
@@ -584,12 +607,13 @@ RowGeom geom_of(BitPlane bits, int width, int height)
 inline dim3 row_grid(const RowGeom &g, int batch, int first_row) { return dim3(cdiv(g.bh - first_row, ROWS_PER_CTA), batch); }
 
 // init + merge: after this every run start's parent chain ends at the root of its component
-int run_union_find(synseg_ctx *ctx, const RowGeom &g, int batch, int32_t *L, cudaStream_t st)
+int run_union_find(synseg_ctx *ctx, const RowGeom &g, int batch, int32_t *L, const BitPlane *strong, cudaStream_t st)
 {
     rccl_init_kernel<<<row_grid(g, batch, 0), 256, 0, st>>>(g, L);
     SS_LAUNCH_CHECK(ctx, "ccl_init", st);
     if (g.bh > 1) {
-        rccl_merge_kernel<<<row_grid(g, batch, 1), 256, 0, st>>>(g, L);
+        if (strong) rccl_merge_kernel<true><<<row_grid(g, batch, 1), 256, 0, st>>>(g, L, *strong);
+        else rccl_merge_kernel<false><<<row_grid(g, batch, 1), 256, 0, st>>>(g, L, BitPlane{nullptr, 0, 0});
         SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
     }
     return SYNSEG_OK;
@@ -649,7 +673,7 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
     SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumx = (u64 *)p;
     SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumy = (u64 *)p;
 
-    SS_TRY(run_union_find(ctx, g, batch, L, st));
+    SS_TRY(run_union_find(ctx, g, batch, L, nullptr, st));
     const dim3 grid = row_grid(g, batch, 0);
     rccl_compress_kernel<0><<<grid, 256, 0, st>>>(g, L, rootbits, row_count, BitPlane{nullptr, 0, 0}, nullptr, 0);
     SS_LAUNCH_CHECK(ctx, "ccl_compress", st);
@@ -682,7 +706,7 @@ int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, i
     SS_TRY(arena_alloc(ctx, (size_t)fper * 4 * batch, &p, st));
     uint32_t *flags = (uint32_t *)p;
     SS_CUDA(cudaMemsetAsync(flags, 0, (size_t)fper * 4 * batch, st));
-    SS_TRY(run_union_find(ctx, g, batch, L, st));
+    SS_TRY(run_union_find(ctx, g, batch, L, &strong, st));
     const dim3 grid = row_grid(g, batch, 0);
     rccl_compress_kernel<1><<<grid, 256, 0, st>>>(g, L, nullptr, nullptr, strong, flags, fper);
     SS_LAUNCH_CHECK(ctx, "hyst_flag", st);

@@ -107,6 +107,15 @@ def test_canny_long_weak_chain(ctx):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("passes", [1, 2, 3, 4, 6])
+def test_canny_weak_strong_mixtures(ctx, passes):
+    """Blur strength sweeps the weak / strong ratio of the kept pixels (hysteresis with skipped strong-strong unions)."""
+    for seed, (h, w) in enumerate([(300, 401), (257, 640), (129, 2100)]):
+        g = np.ascontiguousarray(imgs.blurred_noise(h, w, 40 + seed, passes=passes))
+        for lo, hi in ((50, 150), (20, 60), (5, 200)):
+            assert np.array_equal(host(ctx.canny(dev(g), lo, hi)), cv2.Canny(g, lo, hi)), (passes, h, w, lo, hi)
+
+
 def test_canny_batch(ctx):
     g = np.stack([imgs.shapes(333, 517, s) for s in range(4)])
     got = host(ctx.canny(dev(g)))
