@@ -207,7 +207,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SYNSEG_NCCL_DEBUG", "WARN")   # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout; keep stdout to the one JSON line
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION and =WARN; stdout must carry the one JSON line only
+        os.environ["NCCL_DEBUG"] = os.environ.get("SYNSEG_NCCL_DEBUG", "NONE")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = Context(local)

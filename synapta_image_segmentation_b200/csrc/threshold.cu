@@ -259,10 +259,10 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     p.strips = cdiv(p.width, p.out_w);
     // Bands: a band re-reads block_size - 1 rows of its neighbours (L2 hits, cheap: load + accumulate only).  Short
     // bands win because the cost of a band depends on its content (blank rows skip the prefix and the test), so
-    // many small tasks balance the SMs better (measured on B200: 320 rows 1.16 ms, 64 rows 0.81 ms per 50 pages).
+    // many small tasks balance the SMs better (measured on B200: 320 rows 1.16 ms, 64 rows 0.81 ms per 50 pages with the first strip kernel; 64-96 rows stay best).
     const int64_t rows_total = (int64_t)gray->height * gray->batch * p.strips;
     int band_h = (int)(rows_total / (64 * (int64_t)ctx->sm_count));
-    band_h = band_h < 32 ? 32 : (band_h > 64 ? 64 : band_h);
+    band_h = band_h < 32 ? 32 : (band_h > 96 ? 96 : band_h);
     if (ctx->tune_ad_band > 0) band_h = ctx->tune_ad_band;
     if (band_h > gray->height) band_h = gray->height;
     p.band_h = band_h;
