@@ -28,7 +28,13 @@ from synapta_image_segmentation_b200.synth import render_figure  # noqa: E402
 ref = ref_import.load()
 A2 = os.path.join(ref_import.REFERENCE_DIR, "investments_segmented")
 REAL = ["textbook_001_p020_2b1be7d6.png", "textbook_001_p022_3c6ac748.png", "textbook_001_p022_f96abaf9.png",
-        "textbook_001_p023_e2cf5878.png"]
+        "textbook_001_p023_e2cf5878.png",
+        # a spread over the book (RGB and grey, 245..548 rows), each < 40 KB
+        "textbook_001_p169_513ec97a.png", "textbook_001_p183_af3dbb7a.png", "textbook_001_p207_364b0248.png",
+        "textbook_001_p269_7d5d6fda.png", "textbook_001_p405_1ee5f3bc.png", "textbook_001_p457_ee651881.png",
+        "textbook_001_p510_5645a3d3.png", "textbook_001_p553_a84c5fb1.png", "textbook_001_p712_8719d410.png",
+        "textbook_001_p826_62601fad.png", "textbook_001_p971_84e35f5e.png", "textbook_001_p973_d3eae19d.png",
+        "textbook_001_p988_5b5815f5.png"]
 
 
 def helper_record(path):
