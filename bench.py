@@ -334,6 +334,32 @@ def main():
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dt = float(td.item())
+        # the same end-to-end step through the C ABI's HOST-buffer entry point (synseg_detect_pages_host: staging ring,
+        # copy stream and chunking inside the library; no torch copies): results of call i-2 are consumed after call i is queued
+        bs_, c_, k_ = det.cfg.resolved()
+        outs = [(torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty((B, ml, 5), dtype=torch.int32).pin_memory(), None) for _ in range(3)]
+        evs = [torch.cuda.Event() for _ in range(3)]
+
+        def host_entry_run(steps):
+            for i in range(steps + 2):
+                if i < steps:
+                    ctx.detect_pages_host(host_pages, bs_, c_, k_, det.cfg.canny_lo, det.cfg.canny_hi, ml, chunk_pages=10,
+                                          want_centroids=False, out=outs[i % 3])
+                    evs[i % 3].record()
+                if i >= 2:
+                    evs[(i - 2) % 3].synchronize()
+                    on_result(i - 2, outs[(i - 2) % 3][0], outs[(i - 2) % 3][1])
+
+        host_entry_run(max(1, W_ // 2))
+        barrier()
+        t0 = time.perf_counter()
+        host_entry_run(K)
+        torch.cuda.synchronize()
+        dt_c = time.perf_counter() - t0
+        tdc = torch.tensor([dt_c], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdc, op=dist.ReduceOp.MAX)
+        dt_c = float(tdc.item())
         # the PCIe bound of this step: the same pinned batch copied alone (no compute), CUDA events
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         streamer.dev_pages[0].copy_(host_pages, non_blocking=True)
@@ -348,6 +374,8 @@ def main():
                "d2h_bytes_per_step": streamer.d2h_bytes // K, "ms_per_step": 1000.0 * dt / K,
                "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": host_pages.numel() / h2d_ms / 1e6,
                "frac_of_pcie_bound": h2d_ms / (1000.0 * dt / K),
+               "c_abi_host_entry": {"value": world * K * B / dt_c, "unit": UNIT, "ms_per_step": 1000.0 * dt_c / K,
+                                    "call": "synseg_detect_pages_host, 10-page chunks through 3 staging slots inside the library"},
                "host_pages_numa_bound_cpus": numa.applied,
                "includes": "pinned H2D (3 slots, copy stream), fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
         del streamer

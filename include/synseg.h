@@ -163,6 +163,17 @@ typedef struct synseg_detect_params {
 int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *params,
                         const synseg_img *gray_out, int32_t *n_labels, int32_t *stats, double *centroids, void *stream);
 
+/* The same pipeline for pages in HOST memory (the rasterisation handoff of S:3638-3657: RGB u8, `row_stride` bytes per
+ * row, `page_stride` bytes per page; pinned memory gives full PCIe speed and true copy/compute overlap, pageable
+ * memory works but is staged by the driver).  The library copies `chunk_pages` pages at a time through three device
+ * staging slots on its own copy stream, runs synseg_detect_pages on each chunk and copies the tables back to
+ *   n_labels_host int32[n_pages], stats_host int32[n_pages][max_labels][5], centroids_host double[n_pages][max_labels][2] (may be NULL).
+ * It returns when everything is queued; `stream` waits for the last chunk, so synchronising `stream` (or the device)
+ * completes the call and the host buffers must stay valid until then. */
+int synseg_detect_pages_host(synseg_ctx *ctx, const void *host_rgb, int32_t width, int32_t height, int64_t row_stride,
+                             int64_t page_stride, int32_t n_pages, const synseg_detect_params *params, int32_t chunk_pages,
+                             int32_t *n_labels_host, int32_t *stats_host, double *centroids_host, void *stream);
+
 /* Device-side selection of candidate component boxes for hashing (no host round trip): for every image,
  * every component k >= 1 of `stats` (as written by synseg_detect_pages / synseg_ccl_stats) with
  * min_area <= w*h <= max_area, w >= min_w, h >= min_h is appended to rois[] (image, x, y, w, h) and

@@ -44,6 +44,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->arena = nullptr; c->arena_bytes = 0; c->arena_top = 0; c->launches = 0; c->phash_basis = nullptr;
     c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
+    memset(&c->hs, 0, sizeof(c->hs));
     const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
     c->tune_ad_band = e1 ? atoi(e1) : 0;
     c->tune_canny_band = e2 ? atoi(e2) : 0;
@@ -66,6 +67,7 @@ extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
     cudaDeviceSynchronize();
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->phash_basis) cudaFree(ctx->phash_basis);
+    host_stream_release(ctx);
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     delete ctx;

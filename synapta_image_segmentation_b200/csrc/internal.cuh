@@ -28,6 +28,17 @@ struct synseg_ctx {
     int32_t *phash_basis; // device int32[8*32]
     int tune_ad_band;     // experiment knobs (env SYNSEG_TUNE_AD_BAND / SYNSEG_TUNE_CANNY_BAND), 0 = automatic
     int tune_canny_band;
+    // host-buffer streaming (synseg_detect_pages_host): device staging ring + copy stream, created on first use
+    struct HostStream {
+        cudaStream_t copy;                 // H2D stream
+        uint8_t *pages[3];                 // staging slots for `slot_pages` pages each
+        int32_t *n_labels[3], *stats[3];
+        double *centroids[3];
+        cudaEvent_t copied[3], done[3];
+        size_t slot_bytes;                 // bytes per page slot buffer
+        int slot_pages, max_labels;
+        bool ready;
+    } hs;
     // optional per-kernel timing (synseg_profile_*): one event after every launch on the profiled stream
     bool prof_on;
     cudaEvent_t prof_start;
@@ -37,6 +48,7 @@ struct synseg_ctx {
 };
 
 void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st);
+void host_stream_release(synseg_ctx *ctx);
 
 void synseg_set_error(const char *fmt, ...);
 int synseg_check_cuda(cudaError_t e, const char *what);

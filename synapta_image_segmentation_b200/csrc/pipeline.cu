@@ -207,3 +207,87 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
     }
     return SYNSEG_OK;
 }
+
+// ---- host-buffer entry point ---------------------------------------------------------------------------------
+void host_stream_release(synseg_ctx *ctx)
+{
+    synseg_ctx::HostStream &h = ctx->hs;
+    if (!h.ready) return;
+    for (int i = 0; i < 3; ++i) {
+        if (h.pages[i]) cudaFree(h.pages[i]);
+        if (h.n_labels[i]) cudaFree(h.n_labels[i]);
+        if (h.stats[i]) cudaFree(h.stats[i]);
+        if (h.centroids[i]) cudaFree(h.centroids[i]);
+        if (h.copied[i]) cudaEventDestroy(h.copied[i]);
+        if (h.done[i]) cudaEventDestroy(h.done[i]);
+    }
+    if (h.copy) cudaStreamDestroy(h.copy);
+    memset(&h, 0, sizeof(h));
+}
+
+static int host_stream_prepare(synseg_ctx *ctx, size_t slot_bytes, int slot_pages, int max_labels)
+{
+    synseg_ctx::HostStream &h = ctx->hs;
+    if (h.ready && h.slot_bytes >= slot_bytes && h.slot_pages >= slot_pages && h.max_labels == max_labels) return SYNSEG_OK;
+    SS_CUDA(cudaSetDevice(ctx->device));
+    SS_CUDA(cudaDeviceSynchronize());
+    host_stream_release(ctx);
+    SS_CUDA(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+        SS_CUDA(cudaMalloc(&h.pages[i], slot_bytes));
+        SS_CUDA(cudaMalloc(&h.n_labels[i], sizeof(int32_t) * slot_pages));
+        SS_CUDA(cudaMalloc(&h.stats[i], sizeof(int32_t) * 5 * (size_t)slot_pages * max_labels));
+        SS_CUDA(cudaMalloc(&h.centroids[i], sizeof(double) * 2 * (size_t)slot_pages * max_labels));
+        SS_CUDA(cudaEventCreateWithFlags(&h.copied[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&h.done[i], cudaEventDisableTiming));
+    }
+    h.slot_bytes = slot_bytes; h.slot_pages = slot_pages; h.max_labels = max_labels; h.ready = true;
+    return SYNSEG_OK;
+}
+
+// Pages in HOST memory (pinned for full PCIe speed and true overlap; pageable works, slower) -> component tables in
+// HOST memory.  The library stages the pages through three device slots of `chunk_pages` pages: a copy stream moves
+// chunk i+1, i+2 while the fused pipeline runs on chunk i and the tables of chunk i-1 travel back.  Returns after
+// everything is queued; `stream` is made to wait for the last chunk, so synchronising `stream` completes the call.
+extern "C" SYNSEG_EXPORT int synseg_detect_pages_host(synseg_ctx *ctx, const void *host_rgb, int32_t width, int32_t height,
+                                        int64_t row_stride, int64_t page_stride, int32_t n_pages, const synseg_detect_params *prm,
+                                        int32_t chunk_pages, int32_t *n_labels_host, int32_t *stats_host, double *centroids_host,
+                                        void *stream)
+{
+    if (!ctx || !prm || !host_rgb || !n_labels_host || !stats_host) { synseg_set_error("synseg_detect_pages_host: NULL argument"); return SYNSEG_E_INVALID; }
+    if (width <= 0 || height <= 0 || n_pages < 0 || chunk_pages <= 0 || row_stride < 3 * (int64_t)width || page_stride < row_stride * height || prm->max_labels < 1) {
+        synseg_set_error("synseg_detect_pages_host: bad shape / strides"); return SYNSEG_E_INVALID;
+    }
+    if (n_pages == 0) return SYNSEG_OK;
+    if (chunk_pages > n_pages) chunk_pages = n_pages;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ml = prm->max_labels;
+    const size_t page_bytes = (size_t)row_stride * height;            // pages are copied with their row stride, tightly per page
+    SS_TRY(host_stream_prepare(ctx, page_bytes * chunk_pages, chunk_pages, ml));
+    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(width, height, chunk_pages, ml, true)));
+    synseg_ctx::HostStream &h = ctx->hs;
+    // the first copies must not overtake work the caller queued on `stream` that still reads the staging slots of a previous call
+    SS_CUDA(cudaEventRecord(h.done[0], st));
+    SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[0], 0));
+    const int n_chunks = cdiv(n_pages, chunk_pages);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % 3;
+        const int p0 = c * chunk_pages, np = (n_pages - p0 < chunk_pages) ? n_pages - p0 : chunk_pages;
+        if (c >= 3) SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[s], 0));       // slot s free again (its chunk c-3 finished)
+        const uint8_t *src = (const uint8_t *)host_rgb + (int64_t)p0 * page_stride;
+        if (page_stride == (int64_t)page_bytes) SS_CUDA(cudaMemcpyAsync(h.pages[s], src, page_bytes * np, cudaMemcpyHostToDevice, h.copy));
+        else SS_CUDA(cudaMemcpy2DAsync(h.pages[s], page_bytes, src, (size_t)page_stride, page_bytes, np, cudaMemcpyHostToDevice, h.copy));
+        SS_CUDA(cudaEventRecord(h.copied[s], h.copy));
+        SS_CUDA(cudaStreamWaitEvent(st, h.copied[s], 0));
+        synseg_img img;
+        img.data = h.pages[s]; img.width = width; img.height = height; img.row_stride = row_stride; img.batch = np; img._pad = 0;
+        img.batch_stride = (int64_t)page_bytes;
+        SS_TRY(synseg_detect_pages(ctx, &img, prm, nullptr, h.n_labels[s], h.stats[s], h.centroids[s], stream));
+        SS_CUDA(cudaMemcpyAsync(n_labels_host + p0, h.n_labels[s], sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
+        SS_CUDA(cudaMemcpyAsync(stats_host + (size_t)p0 * ml * 5, h.stats[s], sizeof(int32_t) * 5 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
+        if (centroids_host)
+            SS_CUDA(cudaMemcpyAsync(centroids_host + (size_t)p0 * ml * 2, h.centroids[s], sizeof(double) * 2 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
+        SS_CUDA(cudaEventRecord(h.done[s], st));
+    }
+    return SYNSEG_OK;
+}

@@ -282,6 +282,26 @@ class Context:
                                            cent.data_ptr(), _stream()), "synseg_detect_pages")
         return n, stats, cent
 
+    def detect_pages_host(self, pages: torch.Tensor, block_size: int, c: int, k: int, canny_lo: int = 50, canny_hi: int = 150,
+                          max_labels: int = 1024, chunk_pages: int = 16, want_centroids: bool = True, out=None):
+        """HOST pages (CPU u8 tensor [N,H,W,3], ideally pinned) -> HOST tables (pinned): (n_labels [N], stats [N,max,5],
+        centroids [N,max,2] | None).  Staging, H2D/compute/D2H overlap and chunking happen inside the library
+        (synseg_detect_pages_host); the call is asynchronous on the current stream -- synchronise before reading."""
+        if pages.is_cuda or pages.dtype != torch.uint8 or pages.dim() != 4 or pages.shape[-1] != 3 or pages.stride(-1) != 1 or pages.stride(-2) != 3:
+            raise ValueError("pages must be a CPU uint8 tensor [N,H,W,3] with interleaved pixels")
+        n, h, w, _ = pages.shape
+        if out is not None:                       # caller-provided (pinned) result tensors, reused across calls
+            n_labels, stats, cent = out
+        else:
+            n_labels = torch.empty(n, dtype=torch.int32).pin_memory()
+            stats = torch.empty((n, max_labels, 5), dtype=torch.int32).pin_memory()
+            cent = torch.empty((n, max_labels, 2), dtype=torch.float64).pin_memory() if want_centroids else None
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels)
+        check(self.lib.synseg_detect_pages_host(self._h, C.c_void_p(pages.data_ptr()), w, h, pages.stride(1), pages.stride(0) if n > 1 else pages.stride(1) * h,
+                                                n, C.byref(prm), chunk_pages, C.c_void_p(n_labels.data_ptr()), C.c_void_p(stats.data_ptr()),
+                                                C.c_void_p(cent.data_ptr()) if cent is not None else None, _stream()), "synseg_detect_pages_host")
+        return n_labels, stats, cent
+
     def hints_crops(self, packed: torch.Tensor, crops, kw: int = 25, kh: int = 25) -> torch.Tensor:
         """Ragged batch of crops packed in one CUDA u8 buffer.  crops = [(offset, width, height, row_stride, channels), ...].
         Returns int64 [n, 8] = h_count, v_count, edge_px, sum, sum_sq, non_zero, mask_px, 0 (see synseg_hints_crops)."""

@@ -363,3 +363,28 @@ def test_raster_segmentation_pipeline_writes_reference_artefacts(ctx, tmp_path):
         assert rec["page_no"] == int(seg.segment_id.split("_p")[1][:3]) + 1
     csv_lines = (tmp_path / "textbook_001_visual_summary.csv").read_text().splitlines()
     assert csv_lines[0] == gold["a1_csv_header"] and len(csv_lines) == len(segs) + 1
+
+
+def test_detect_pages_host_entry_point(ctx):
+    """synseg_detect_pages_host: pages in HOST memory (pinned and pageable, ragged last chunk, strided pages) give the
+    same tables as the device entry point; the staging ring is reused across calls."""
+    bs, c, k = cv2_chain.chain_params(72)
+    pages = synth_pages(11, 72, base_seed=21)
+    want_n, want_s, want_c = ctx.detect_pages(torch.from_numpy(pages).cuda(), bs, c, k, max_labels=256)
+    torch.cuda.synchronize()
+    for host in (torch.from_numpy(pages).pin_memory(), torch.from_numpy(pages.copy())):          # pinned, pageable
+        for chunk in (4, 16):
+            n, s, ce = ctx.detect_pages_host(host, bs, c, k, max_labels=256, chunk_pages=chunk)
+            torch.cuda.synchronize()
+            assert torch.equal(n, want_n.cpu())
+            for j in range(11):
+                m = int(n[j])
+                assert torch.equal(s[j, :m], want_s[j, :m].cpu()) and torch.equal(ce[j, :m], want_c[j, :m].cpu())
+    # strided: every second page of a larger pinned buffer
+    big = torch.from_numpy(np.repeat(pages[:6], 2, axis=0)).pin_memory()
+    n, s, _ = ctx.detect_pages_host(big[::2], bs, c, k, max_labels=256, chunk_pages=2, want_centroids=False)
+    torch.cuda.synchronize()
+    assert torch.equal(n, want_n[:6].cpu())
+    one = ctx.detect_pages_host(torch.from_numpy(pages[:1]).pin_memory(), bs, c, k, max_labels=256)
+    torch.cuda.synchronize()
+    assert int(one[0][0]) == int(want_n[0])
