@@ -41,9 +41,14 @@ struct RowGeom {
     int width, height;
     int bw, bh;        // blocks per block row, block rows
     int64_t bper;      // parent-array entries per image
-    int nseg;          // 2048-pixel segments per row (32 lanes x 64 pixels)
+    int nseg;          // segments per row: G lanes x 64 pixels each (G = lanes per block row, 32 or 16)
     int cpr;           // 64-pixel chunks per row = cdiv(width, 64)
 };
+
+// Lanes per block row.  G = 32: one warp per block row.  G = 16: a warp owns two consecutive block rows, one per
+// half-warp (shuffles with width 16, ballots split per half) -- a 2550-pixel row (40 chunks) then needs 3 segments of
+// 16 lanes instead of 2 of 32, i.e. 25 % fewer warp instructions per row.  Every *_sync intrinsic is still executed
+// by the full warp.
 
 // 64 pixels of one row; bits at x >= width (and rows outside the image) read as 0
 __device__ __forceinline__ u64 load_chunk(const uint32_t *row, int chunk, int width)
@@ -64,24 +69,27 @@ struct Runs {
     int carryIn;   // first block (column index) of the run that holds the last block of the previous chunk
 };
 
-// v = OR of the two pixel rows of the block row (this lane's chunk).  All 32 lanes must call.
-__device__ __forceinline__ Runs analyze_runs(u64 v, int chunk, int lane, RunCarry &c)
+// v = OR of the two pixel rows of the block row (this lane's chunk).  All 32 lanes must call; `gl` = lane within
+// its group of G lanes (one group per block row).
+template <int G>
+__device__ __forceinline__ Runs analyze_runs(u64 v, int chunk, int gl, RunCarry &c)
 {
     const uint32_t hi = (uint32_t)(v >> 63);
-    uint32_t pb = __shfl_up_sync(FULL, hi, 1);
-    if (lane == 0) pb = c.topbit;
+    uint32_t pb = __shfl_up_sync(FULL, hi, 1, G);
+    if (gl == 0) pb = c.topbit;
     const u64 vprev = (v << 1) | pb;                   // vprev[x] = v[x-1]
     Runs r;
     r.occE = (v | (v >> 1)) & EVEN;
     r.startE = r.occE & ~(v & vprev);                  // not linked to the previous block
-    const unsigned has = __ballot_sync(FULL, r.startE != 0);
+    unsigned has = __ballot_sync(FULL, r.startE != 0);
+    if (G == 16) has = (has >> (threadIdx.x & 16)) & 0xFFFFu;      // this half-warp's lanes
     const int my_last = r.startE ? chunk * 32 + ((63 - __clzll((long long)r.startE)) >> 1) : -1;
-    const unsigned below = has & ((1u << lane) - 1u);
-    const int from_lane = __shfl_sync(FULL, my_last, below ? 31 - __clz((int)below) : 0);
+    const unsigned below = has & ((1u << gl) - 1u);
+    const int from_lane = __shfl_sync(FULL, my_last, below ? 31 - __clz((int)below) : 0, G);
     r.carryIn = below ? from_lane : c.start;
-    const int last_all = __shfl_sync(FULL, my_last, has ? 31 - __clz((int)has) : 0);
+    const int last_all = __shfl_sync(FULL, my_last, has ? 31 - __clz((int)has) : 0, G);
     if (has) c.start = last_all;
-    c.topbit = __shfl_sync(FULL, hi, 31);
+    c.topbit = __shfl_sync(FULL, hi, G - 1, G);
     return r;
 }
 
@@ -144,26 +152,30 @@ __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
     } while (!done);
 }
 
+// lane = lane within the group (0..G-1); rows outside the image read as empty (null row pointers) so that a half-warp
+// whose block row does not exist still takes part in the warp-wide intrinsics
 #define ROW_PROLOGUE(first_row)                                                             \
-    const int lane = threadIdx.x & 31;                                                       \
-    const int by = (first_row) + blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);             \
+    const int lane = threadIdx.x & (G - 1);                                                  \
+    const int by = (first_row) + (blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5)) * (32 / G) + ((threadIdx.x & 31) / G); \
     const int img = blockIdx.y;                                                              \
     const bool row_ok = by < g.bh;                                                           \
+    const bool warp_ok = (by - ((threadIdx.x & 31) / G)) < g.bh;     /* first row of this warp exists */ \
     const uint32_t *pbase = g.bits + img * g.wbs;                                            \
-    const uint32_t *r0 = pbase + (int64_t)(2 * by) * g.wpr;                                  \
-    const uint32_t *r1 = (2 * by + 1 < g.height) ? r0 + g.wpr : nullptr;
+    const uint32_t *r0 = row_ok ? pbase + (int64_t)(2 * by) * g.wpr : nullptr;               \
+    const uint32_t *r1 = (row_ok && 2 * by + 1 < g.height) ? r0 + g.wpr : nullptr;
 
 // every run start becomes its own parent
+template <int G>
 __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall)
 {
     ROW_PROLOGUE(0)
-    if (!row_ok) return;
+    if (!warp_ok) return;
     int32_t *L = Lall + img * g.bper + (int64_t)by * g.bw;
     RunCarry c{0u, -1};
     for (int s = 0; s < g.nseg; ++s) {
-        const int chunk = s * 32 + lane;
+        const int chunk = s * G + lane;
         const u64 v = load_chunk(r0, chunk, g.width) | load_chunk(r1, chunk, g.width);
-        const Runs r = analyze_runs(v, chunk, lane, c);
+        const Runs r = analyze_runs<G>(v, chunk, lane, c);
         u64 st = r.startE;
         while (st) {
             const int bx = chunk * 32 + ((__ffsll((long long)st) - 1) >> 1);
@@ -178,26 +190,26 @@ __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall
 // every weak run still reaches a strong run of its component through unions that involve at least one weak run
 // (take a path to the nearest strong run: all its edges but none beyond have a weak end).  The test is made on the
 // run pieces inside this lane's chunk (a subset of the runs), so it only ever skips safely.
-template <bool HYST>
+template <bool HYST, int G>
 __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lall, BitPlane strong)
 {
     ROW_PROLOGUE(1)
-    if (!row_ok) return;
-    const uint32_t *u1 = r0 - g.wpr, *u0 = u1 - g.wpr;    // pixel rows 2by-1, 2by-2
+    if (!warp_ok) return;
+    const uint32_t *u1 = row_ok ? r0 - g.wpr : nullptr, *u0 = row_ok ? u1 - g.wpr : nullptr;    // pixel rows 2by-1, 2by-2
     int32_t *L = Lall + img * g.bper;
     const int cur_base = by * g.bw, up_base = (by - 1) * g.bw;
     RunCarry cc{0u, -1}, cu{0u, -1};
     uint32_t t_top = 0, u_top = 0;
     for (int s = 0; s < g.nseg; ++s) {
-        const int chunk = s * 32 + lane;
+        const int chunk = s * G + lane;
         const u64 t = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
         const u64 u = load_chunk(u1, chunk, g.width), b0 = load_chunk(u0, chunk, g.width);
-        const Runs rc = analyze_runs(t | a1, chunk, lane, cc);
-        const Runs ru = analyze_runs(u | b0, chunk, lane, cu);
+        const Runs rc = analyze_runs<G>(t | a1, chunk, lane, cc);
+        const Runs ru = analyze_runs<G>(u | b0, chunk, lane, cu);
         const uint32_t th = (uint32_t)(t >> 63), uh = (uint32_t)(u >> 63);
-        uint32_t tp = __shfl_up_sync(FULL, th, 1), up = __shfl_up_sync(FULL, uh, 1);
+        uint32_t tp = __shfl_up_sync(FULL, th, 1, G), up = __shfl_up_sync(FULL, uh, 1, G);
         if (lane == 0) { tp = t_top; up = u_top; }
-        t_top = __shfl_sync(FULL, th, 31); u_top = __shfl_sync(FULL, uh, 31);
+        t_top = __shfl_sync(FULL, th, G - 1, G); u_top = __shfl_sync(FULL, uh, G - 1, G);
         const u64 tl = (t << 1) | tp, ul = (u << 1) | up;      // tl[x] = t[x-1]
         u64 ev_a = t & ~tl & (u | ul);
         u64 ev_b = u & ~ul & tl;
@@ -231,25 +243,25 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lal
 //  MODE 0 (labelling): the roots of the block row go to a bit plane (even-bit layout, one u64 per chunk)
 //                      and their number to row_count.
 //  MODE 1 (hysteresis): the root of every run piece that holds a strong pixel is flagged.
-template <int MODE>
+template <int MODE, int G>
 __global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g, int32_t *Lall, u64 *rootbits, int32_t *row_count,
                                                             BitPlane strong, uint32_t *flags, int64_t fper)
 {
     ROW_PROLOGUE(0)
-    if (!row_ok) return;
+    if (!warp_ok) return;
     int32_t *L = Lall + img * g.bper;
     const int cur_base = by * g.bw;
     RunCarry c{0u, -1};
     int nroots = 0;
     const uint32_t *s0 = nullptr, *s1 = nullptr;
-    if (MODE == 1) {
+    if (MODE == 1 && row_ok) {
         s0 = strong.p + img * strong.bs + (int64_t)(2 * by) * strong.wpr;
         s1 = (2 * by + 1 < g.height) ? s0 + strong.wpr : nullptr;
     }
     for (int s = 0; s < g.nseg; ++s) {
-        const int chunk = s * 32 + lane;
+        const int chunk = s * G + lane;
         const u64 v = load_chunk(r0, chunk, g.width) | load_chunk(r1, chunk, g.width);
-        const Runs r = analyze_runs(v, chunk, lane, c);
+        const Runs r = analyze_runs<G>(v, chunk, lane, c);
         u64 st = r.startE, rootE = 0;
         while (st) {
             const int p = __ffsll((long long)st) - 1;
@@ -259,7 +271,7 @@ __global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g, int32_t *
             if (root != b) L[b] = root; else rootE |= 1ULL << p;
         }
         if (MODE == 0) {
-            if (chunk < g.cpr) rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] = rootE;
+            if (row_ok && chunk < g.cpr) rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] = rootE;
             nroots += __popcll(rootE);
         } else {
             const u64 sv = load_chunk(s0, chunk, g.width) | load_chunk(s1, chunk, g.width);
@@ -277,8 +289,8 @@ __global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g, int32_t *
         }
     }
     if (MODE == 0) {
-        nroots = __reduce_add_sync(FULL, nroots);
-        if (lane == 0) row_count[(int64_t)img * g.bh + by] = nroots;
+        nroots = __reduce_add_sync(G == 32 ? FULL : (0xFFFFu << (threadIdx.x & 16)), nroots);      // over the lanes of this block row
+        if (lane == 0 && row_ok) row_count[(int64_t)img * g.bh + by] = nroots;
     }
 }
 
@@ -311,20 +323,21 @@ __global__ void __launch_bounds__(256) ccl_scan_kernel(int n, int32_t *cnt, int3
 }
 
 // roots get L[root] = -(label) - 1 with label = 1 + rank in block raster order
+template <int G>
 __global__ void __launch_bounds__(256) rccl_assign_kernel(RowGeom g, int32_t *Lall, const u64 *rootbits, const int32_t *row_off)
 {
     ROW_PROLOGUE(0)
     (void)r0; (void)r1; (void)pbase;
-    if (!row_ok) return;
+    if (!warp_ok) return;
     int32_t *L = Lall + img * g.bper + (int64_t)by * g.bw;
-    int base = row_off[(int64_t)img * g.bh + by];
+    int base = row_ok ? row_off[(int64_t)img * g.bh + by] : 0;
     for (int s = 0; s < g.nseg; ++s) {
-        const int chunk = s * 32 + lane;
-        u64 rb = (chunk < g.cpr) ? rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] : 0ULL;
+        const int chunk = s * G + lane;
+        u64 rb = (row_ok && chunk < g.cpr) ? rootbits[((int64_t)img * g.bh + by) * g.cpr + chunk] : 0ULL;
         const int n = __popcll(rb);
         int incl = n;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
+        for (int d = 1; d < G; d <<= 1) { int nb = __shfl_up_sync(FULL, incl, d, G); if (lane >= d) incl += nb; }
         int rank = base + incl - n;
         while (rb) {
             const int bx = chunk * 32 + ((__ffsll((long long)rb) - 1) >> 1);
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(256) rccl_assign_kernel(RowGeom g, int32_t *La
             L[bx] = -(rank + 1) - 1;
             ++rank;
         }
-        base += __shfl_sync(FULL, incl, 31);
+        base += __shfl_sync(FULL, incl, G - 1, G);
     }
 }
 
@@ -412,9 +425,10 @@ __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contri
 // Per-warp staging for the optional label image: block labels and pixel words of one 2048-pixel segment.
 struct LabelStage { int32_t lab[1024]; u64 px[2][32]; };
 
-template <bool WRITE_LABELS>
+template <bool WRITE_LABELS, int G>
 __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
 {
+    static_assert(!WRITE_LABELS || G == 32, "the label image path stages one block row per warp");
     __shared__ SlotCache sc;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     if (threadIdx.x < NSLOT) {
@@ -425,7 +439,7 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_
     __syncthreads();
     ROW_PROLOGUE(0)
     const int64_t img_off = (int64_t)img * a.cap;
-    if (row_ok) {
+    if (warp_ok) {
         const int32_t *L = Lall + img * g.bper;
         const int cur_base = by * g.bw;
         const int y = 2 * by;
@@ -433,13 +447,13 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_
         LabelStage *stage = WRITE_LABELS ? (LabelStage *)dyn_smem + (threadIdx.x >> 5) : nullptr;
         RunCarry c{0u, -1};
         for (int s = 0; s < g.nseg; ++s) {
-            const int chunk = s * 32 + lane;
+            const int chunk = s * G + lane;
             const int x0 = 64 * chunk;
             const u64 a0 = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
-            const Runs r = analyze_runs(a0 | a1, chunk, lane, c);
-            // background (label 0): all lanes reduce together
+            const Runs r = analyze_runs<G>(a0 | a1, chunk, lane, c);
+            // background (label 0): all lanes reduce together (both block rows of a warp belong to the same image)
             {
-                const int remw = g.width - x0;
+                const int remw = row_ok ? g.width - x0 : 0;
                 const u64 vm = remw >= 64 ? ~0ULL : (remw <= 0 ? 0ULL : ((1ULL << remw) - 1ULL));
                 const u64 b0 = ~a0 & vm, b1 = has_row1 ? (~a1 & vm) : 0ULL;
                 Contrib v;
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_
                 if (has) {
                     int fb;
                     const int p = __ffsll((long long)rem) - 1;
+                    (void)p;
                     const u64 range = next_piece(r, chunk, rem, fb);
                     int32_t v = L[cur_base + fb];
                     if (v >= 0) v = L[v];
@@ -535,12 +550,12 @@ __global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int bat
 __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
 // keep the pixels of every run piece whose component was flagged (holds a strong pixel)
-template <bool OUT_BITS>
+template <bool OUT_BITS, int G>
 __global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const int32_t *Lall, const uint32_t *flags, int64_t fper,
                                                               Plane out, bool out_al16, BitPlane obits, bool or_bits)
 {
     ROW_PROLOGUE(0)
-    if (!row_ok) return;
+    if (!warp_ok) return;
     const int32_t *L = Lall + img * g.bper;
     const uint32_t *F = flags + img * fper;
     const int cur_base = by * g.bw;
@@ -548,9 +563,9 @@ __global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const i
     const bool has_row1 = y + 1 < g.height;
     RunCarry c{0u, -1};
     for (int s = 0; s < g.nseg; ++s) {
-        const int chunk = s * 32 + lane;
+        const int chunk = s * G + lane;
         const u64 a0 = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
-        const Runs r = analyze_runs(a0 | a1, chunk, lane, c);
+        const Runs r = analyze_runs<G>(a0 | a1, chunk, lane, c);
         u64 keep = 0, rem = r.occE;
         while (rem) {
             int fb;
@@ -558,7 +573,7 @@ __global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const i
             const int32_t root = L[cur_base + fb];          // fully compressed by rccl_compress_kernel<1>
             if ((F[root >> 5] >> (root & 31)) & 1u) keep |= range;
         }
-        if (chunk >= g.cpr) continue;
+        if (!row_ok || chunk >= g.cpr) continue;
         const u64 o0 = a0 & keep, o1 = a1 & keep;
         if (OUT_BITS) {
             uint2 *p0 = (uint2 *)(obits.p + img * obits.bs + (int64_t)y * obits.wpr) + chunk;
@@ -592,28 +607,47 @@ __global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const i
     }
 }
 
-RowGeom geom_of(BitPlane bits, int width, int height)
+// lanes per block row that waste the fewest lanes on this width (ties -> 32)
+int pick_group(int width)
+{
+    const int chunks = cdiv(width, 64);
+    return (cdiv(chunks, 16) * 16 < cdiv(chunks, 32) * 32) ? 16 : 32;
+}
+
+RowGeom geom_of(BitPlane bits, int width, int height, int G)
 {
     RowGeom g;
     g.bits = bits.p; g.wpr = bits.wpr; g.wbs = bits.bs;
     g.width = width; g.height = height;
     g.bw = (width + 1) / 2; g.bh = (height + 1) / 2;
     g.bper = (int64_t)align_up((size_t)g.bw * g.bh, 4);
-    g.nseg = cdiv(width, 2048);
+    g.nseg = cdiv(width, 64 * G);
     g.cpr = cdiv(width, 64);
     return g;
 }
 
-inline dim3 row_grid(const RowGeom &g, int batch, int first_row) { return dim3(cdiv(g.bh - first_row, ROWS_PER_CTA), batch); }
+inline dim3 row_grid(const RowGeom &g, int batch, int first_row, int G) { return dim3(cdiv(g.bh - first_row, ROWS_PER_CTA * (32 / G)), batch); }
+
+// launch `kernel<..., G>` for G = 16 or 32
+#define LAUNCH_G(G_, kernel16, kernel32, grid, smem, st, ...)                    \
+    do {                                                                         \
+        if ((G_) == 16) kernel16<<<grid, 256, smem, st>>>(__VA_ARGS__);          \
+        else kernel32<<<grid, 256, smem, st>>>(__VA_ARGS__);                     \
+    } while (0)
 
 // init + merge: after this every run start's parent chain ends at the root of its component
-int run_union_find(synseg_ctx *ctx, const RowGeom &g, int batch, int32_t *L, const BitPlane *strong, cudaStream_t st)
+int run_union_find(synseg_ctx *ctx, const RowGeom &g, int G, int batch, int32_t *L, const BitPlane *strong, cudaStream_t st)
 {
-    rccl_init_kernel<<<row_grid(g, batch, 0), 256, 0, st>>>(g, L);
+    LAUNCH_G(G, rccl_init_kernel<16>, rccl_init_kernel<32>, row_grid(g, batch, 0, G), 0, st, g, L);
     SS_LAUNCH_CHECK(ctx, "ccl_init", st);
     if (g.bh > 1) {
-        if (strong) rccl_merge_kernel<true><<<row_grid(g, batch, 1), 256, 0, st>>>(g, L, *strong);
-        else rccl_merge_kernel<false><<<row_grid(g, batch, 1), 256, 0, st>>>(g, L, BitPlane{nullptr, 0, 0});
+        // the union kernel always runs one warp per block row: two rows per warp made its divergent event loops and
+        // the atomics of adjacent rows collide (measured 0.23 -> 0.25 ms), unlike the purely analytic kernels
+        RowGeom g32 = g;
+        g32.nseg = cdiv(g.width, 64 * 32);
+        const dim3 grid = row_grid(g32, batch, 1, 32);
+        if (strong) rccl_merge_kernel<true, 32><<<grid, 256, 0, st>>>(g32, L, *strong);
+        else rccl_merge_kernel<false, 32><<<grid, 256, 0, st>>>(g32, L, BitPlane{nullptr, 0, 0});
         SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
     }
     return SYNSEG_OK;
@@ -653,7 +687,8 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
         bits = BitPlane{(uint32_t *)p, wpr, (int64_t)wpr * m.height};
         SS_TRY(launch_pack_bits(ctx, m.u8, bits, st));
     }
-    const RowGeom g = geom_of(bits, m.width, m.height);
+    const int G = labels ? 32 : pick_group(m.width);          // the label-image path stages one block row per warp
+    const RowGeom g = geom_of(bits, m.width, m.height, G);
     SS_TRY(arena_alloc(ctx, (size_t)g.bper * batch * 4, &p, st));
     int32_t *L = (int32_t *)p;
     SS_TRY(arena_alloc(ctx, (size_t)g.bh * g.cpr * 8 * batch, &p, st));
@@ -673,21 +708,22 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
     SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumx = (u64 *)p;
     SS_TRY(arena_alloc(ctx, nacc * 8, &p, st)); a.sumy = (u64 *)p;
 
-    SS_TRY(run_union_find(ctx, g, batch, L, nullptr, st));
-    const dim3 grid = row_grid(g, batch, 0);
-    rccl_compress_kernel<0><<<grid, 256, 0, st>>>(g, L, rootbits, row_count, BitPlane{nullptr, 0, 0}, nullptr, 0);
+    SS_TRY(run_union_find(ctx, g, G, batch, L, nullptr, st));
+    const dim3 grid = row_grid(g, batch, 0, G);
+    LAUNCH_G(G, (rccl_compress_kernel<0, 16>), (rccl_compress_kernel<0, 32>), grid, 0, st, g, L, rootbits, row_count, BitPlane{nullptr, 0, 0},
+             (uint32_t *)nullptr, (int64_t)0);
     SS_LAUNCH_CHECK(ctx, "ccl_compress", st);
     ccl_scan_kernel<<<batch, 256, 0, st>>>(g.bh, row_count, n_roots);
     SS_LAUNCH_CHECK(ctx, "ccl_scan", st);
-    rccl_assign_kernel<<<grid, 256, 0, st>>>(g, L, rootbits, row_count);
+    LAUNCH_G(G, rccl_assign_kernel<16>, rccl_assign_kernel<32>, grid, 0, st, g, L, rootbits, row_count);
     SS_LAUNCH_CHECK(ctx, "ccl_assign", st);
     stats_init_kernel<<<(unsigned)cdiv(nacc, 256), 256, 0, st>>>(a, (int64_t)nacc);
     SS_LAUNCH_CHECK(ctx, "stats_init", st);
     if (labels) {
         const bool al16 = plane_aligned(labels, 16);
-        rccl_final_kernel<true><<<grid, 256, ROWS_PER_CTA * sizeof(LabelStage), st>>>(g, L, plane_of(labels), al16, a);
+        rccl_final_kernel<true, 32><<<grid, 256, ROWS_PER_CTA * sizeof(LabelStage), st>>>(g, L, plane_of(labels), al16, a);
     } else {
-        rccl_final_kernel<false><<<grid, 256, 0, st>>>(g, L, Plane{nullptr, 0, 0}, false, a);
+        LAUNCH_G(G, (rccl_final_kernel<false, 16>), (rccl_final_kernel<false, 32>), grid, 0, st, g, L, Plane{nullptr, 0, 0}, false, a);
     }
     SS_LAUNCH_CHECK(ctx, "ccl_final", st);
     stats_finalize_kernel<<<dim3(cdiv(max_labels, 128), batch), 128, 0, st>>>(a, n_roots, batch, n_labels, stats, centroids);
@@ -698,7 +734,8 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
 int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, int height, int batch, const synseg_img *edges_u8,
                    BitPlane edges_bits, bool or_bits, cudaStream_t st)
 {
-    const RowGeom g = geom_of(kept, width, height);
+    const int G = pick_group(width);
+    const RowGeom g = geom_of(kept, width, height, G);
     void *p;
     SS_TRY(arena_alloc(ctx, (size_t)g.bper * batch * 4, &p, st));
     int32_t *L = (int32_t *)p;
@@ -706,15 +743,16 @@ int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, i
     SS_TRY(arena_alloc(ctx, (size_t)fper * 4 * batch, &p, st));
     uint32_t *flags = (uint32_t *)p;
     SS_CUDA(cudaMemsetAsync(flags, 0, (size_t)fper * 4 * batch, st));
-    SS_TRY(run_union_find(ctx, g, batch, L, &strong, st));
-    const dim3 grid = row_grid(g, batch, 0);
-    rccl_compress_kernel<1><<<grid, 256, 0, st>>>(g, L, nullptr, nullptr, strong, flags, fper);
+    SS_TRY(run_union_find(ctx, g, G, batch, L, &strong, st));
+    const dim3 grid = row_grid(g, batch, 0, G);
+    LAUNCH_G(G, (rccl_compress_kernel<1, 16>), (rccl_compress_kernel<1, 32>), grid, 0, st, g, L, (u64 *)nullptr, (int32_t *)nullptr, strong, flags, fper);
     SS_LAUNCH_CHECK(ctx, "hyst_flag", st);
     if (edges_u8)
-        rccl_hyst_final_kernel<false><<<grid, 256, 0, st>>>(g, L, flags, fper, plane_of(edges_u8), plane_aligned(edges_u8, 16),
-                                                             BitPlane{nullptr, 0, 0}, false);
+        LAUNCH_G(G, (rccl_hyst_final_kernel<false, 16>), (rccl_hyst_final_kernel<false, 32>), grid, 0, st, g, L, flags, fper, plane_of(edges_u8),
+                 plane_aligned(edges_u8, 16), BitPlane{nullptr, 0, 0}, false);
     else
-        rccl_hyst_final_kernel<true><<<grid, 256, 0, st>>>(g, L, flags, fper, Plane{nullptr, 0, 0}, false, edges_bits, or_bits);
+        LAUNCH_G(G, (rccl_hyst_final_kernel<true, 16>), (rccl_hyst_final_kernel<true, 32>), grid, 0, st, g, L, flags, fper, Plane{nullptr, 0, 0}, false,
+                 edges_bits, or_bits);
     SS_LAUNCH_CHECK(ctx, "hyst_final", st);
     return SYNSEG_OK;
 }
