@@ -17,7 +17,8 @@ constexpr int PH_MAXW = 8192;
 
 // Stage 1: cell means.  grid = (32 row groups, regions): CTA (i, r) reduces row group i of region r to its
 // 32 cell values q[i][0..31] (thread per column, rows of the group unrolled by 4 for memory-level parallelism).
-__global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, int height, int src_kind, const synseg_roi *rois,
+template <int SRC_KIND>
+__global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, int height, const synseg_roi *rois,
                                                           int32_t *qbuf, const int32_t *count)
 {
     if (count && (int)blockIdx.y >= *count) return;
@@ -31,44 +32,48 @@ __global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, 
     const int y0 = (int)((long long)i * h / 32);
     int y1 = (int)((long long)(i + 1) * h / 32);
     if (y1 <= y0) y1 = y0 + 1;
-    const int mode = src_kind == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV;
-    const int bpp = src_kind == 0 ? 1 : 3;
+    constexpr int bpp = SRC_KIND == 0 ? 1 : 3;
+    constexpr int MODE = SRC_KIND == 1 ? SYNSEG_GRAY_PIL : SYNSEG_GRAY_CV;
     const int64_t row_bytes = (int64_t)width * bpp;                  // bytes of an image row that may be read
     // Four pixels per thread and row.  Their 4*bpp bytes are fetched as aligned 32-bit words and funnel-shifted by the
-    // byte phase of the row (the same for every thread of the row), a third of the load instructions of a byte loop;
-    // threads whose words would cross the end of the image row take the byte path.
+    // byte phase of the row (the same for every thread of the row): a third of the load instructions of a byte loop.
+    // The row loop of the word path is branch-free, so its loads are issued four rows ahead of their use.  Threads
+    // whose words could cross the ends of the image row (any phase) take the byte path.
     for (int x = 4 * tid; x < w; x += 4 * 256) {
         uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         const int npx = min(4, w - x);
         const int64_t off = (int64_t)(r.x + x) * bpp;                // byte offset of the first pixel inside the row
-        for (int y = y0; y < y1; ++y) {
-            const uint8_t *row = base + (int64_t)(r.y + y) * src.rs;
-            const uint8_t *pa = row + off;
-            const int ph = (int)((uintptr_t)pa & 3);
-            const uint32_t *wp = (const uint32_t *)(pa - ph);
-            uint32_t px[4];
-            if (npx == 4 && off - ph >= 0 && off - ph + 4 * (bpp + 1) <= row_bytes) {
+        const uint8_t *p0 = base + (int64_t)(r.y + y0) * src.rs + off;
+        if (npx == 4 && off >= 3 && off + 4 * (bpp + 1) <= row_bytes) {
+#pragma unroll 4
+            for (int y = y0; y < y1; ++y, p0 += src.rs) {
+                const int ph = (int)((uintptr_t)p0 & 3);
+                const uint32_t *wp = (const uint32_t *)(p0 - ph);
+                const int sh = 8 * ph;
                 if (bpp == 3) {
                     const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
-                    const int sh = 8 * ph;
                     const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
-                    px[0] = b0; px[1] = __funnelshift_r(b0, b1, 24); px[2] = __funnelshift_r(b1, b2, 16); px[3] = b2 >> 8;
+                    s0 += gray1<MODE>(b0); s1 += gray1<MODE>(__funnelshift_r(b0, b1, 24));
+                    s2 += gray1<MODE>(__funnelshift_r(b1, b2, 16)); s3 += gray1<MODE>(b2 >> 8);
                 } else {
-                    const uint32_t g4 = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * ph);
-                    px[0] = g4 & 255u; px[1] = (g4 >> 8) & 255u; px[2] = (g4 >> 16) & 255u; px[3] = g4 >> 24;
+                    const uint32_t g4 = __funnelshift_r(__ldg(wp), __ldg(wp + 1), sh);
+                    s0 += g4 & 255u; s1 += (g4 >> 8) & 255u; s2 += (g4 >> 16) & 255u; s3 += g4 >> 24;
                 }
-            } else {
+            }
+        } else {
+            for (int y = y0; y < y1; ++y, p0 += src.rs) {
+                uint32_t px[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     px[k] = 0;
                     if (k < npx) {
-                        const uint8_t *q = pa + k * bpp;
+                        const uint8_t *q = p0 + k * bpp;
                         px[k] = bpp == 3 ? ((uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16)) : (uint32_t)__ldg(q);
                     }
                 }
+                if (bpp == 3) { s0 += gray1<MODE>(px[0]); s1 += gray1<MODE>(px[1]); s2 += gray1<MODE>(px[2]); s3 += gray1<MODE>(px[3]); }
+                else { s0 += px[0]; s1 += px[1]; s2 += px[2]; s3 += px[3]; }
             }
-            if (bpp == 3) { s0 += gray_dyn(px[0], mode); s1 += gray_dyn(px[1], mode); s2 += gray_dyn(px[2], mode); s3 += gray_dyn(px[3], mode); }
-            else { s0 += px[0]; s1 += px[1]; s2 += px[2]; s3 += px[3]; }
         }
         colsum[x] = s0;
         if (npx > 1) colsum[x + 1] = s1;
@@ -184,7 +189,9 @@ static int run_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const
     void *p;
     SS_TRY(arena_alloc(ctx, (size_t)n * 1024 * sizeof(int32_t), &p, st));
     int32_t *qbuf = (int32_t *)p;
-    phash_cells_kernel<<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, src_kind, rois, qbuf, count);
+    if (src_kind == 0) phash_cells_kernel<0><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
+    else if (src_kind == 1) phash_cells_kernel<1><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
+    else phash_cells_kernel<2><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
     SS_LAUNCH_CHECK(ctx, "phash_cells", st);
     phash_dct_kernel<<<n, 256, 0, st>>>(qbuf, ctx->phash_basis, (unsigned long long *)out, count);
     SS_LAUNCH_CHECK(ctx, "phash_dct", st);
