@@ -277,8 +277,8 @@ def main():
         ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
 
     def dedup_exchange():
-        ctx.phash_indirect(pages, 1, rois, count, hashes)      # all candidate boxes of the K steps share `pages`
-        n_valid = int(count.item())
+        n_valid = int(count.item())                            # one host sync; also sizes the hashing grid exactly
+        ctx.phash_indirect(pages, 1, rois[:max(n_valid, 1)], count, hashes)      # all candidate boxes of the K steps share `pages`
         k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4)
         return k_all, int(keep.sum().item())
 
