@@ -144,6 +144,19 @@ def test_morph_binary_ops(ctx, hw, kw, kh):
                 assert np.array_equal(got, cv2.morphologyEx(src, cvop, se, iterations=it)), (hw, kw, kh, op, it)
 
 
+@pytest.mark.parametrize("kw,kh", [(251, 1), (1, 401), (300, 400), (227, 385), (226, 384), (99, 191)])
+def test_morph_binary_huge_kernels(ctx, kw, kh):
+    """Kernel sizes around and beyond the limits of the register row pass (k <= 226) and the van Herk column pass
+    (k <= 384): the shared-memory fallback kernels and the 12-word / 128-thread variants."""
+    m = imgs.random_mask(450, 613, 77, 0.97)
+    se = cv2.getStructuringElement(cv2.MORPH_RECT, (kw, kh))
+    d = dev(m)
+    assert np.array_equal(host(ctx.morph(d, 1, kw, kh, binary=True)), cv2.dilate(m, se))
+    assert np.array_equal(host(ctx.morph(d, 0, kw, kh, binary=True)), cv2.erode(m, se))
+    inv = 255 - m
+    assert np.array_equal(host(ctx.morph(dev(inv), 3, kw, kh, binary=True)), cv2.morphologyEx(inv, cv2.MORPH_CLOSE, se))
+
+
 @pytest.mark.parametrize("hw", [(1, 1), (5, 7), (40, 33), (97, 131), (200, 300)])
 @pytest.mark.parametrize("kw,kh", [(3, 3), (1, 25), (25, 1), (21, 21), (20, 1), (4, 6), (49, 1)])
 def test_morph_grey(ctx, hw, kw, kh):
