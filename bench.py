@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -276,11 +276,21 @@ def main():
         det.detect_components(pages, out=out)
         ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
 
+    phases = os.environ.get("SYNSEG_BENCH_PHASES") == "1"       # diagnostic: wall-clock of the exchange phases on stderr
+
     def dedup_exchange():
+        t = [time.perf_counter()]
         n_valid = int(count.item())                            # one host sync; also sizes the hashing grid exactly
+        t.append(time.perf_counter())
         ctx.phash_indirect(pages, 1, rois[:max(n_valid, 1)], count, hashes)      # all candidate boxes of the K steps share `pages`
-        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4)
-        return k_all, int(keep.sum().item())
+        if phases:
+            torch.cuda.synchronize(); t.append(time.perf_counter())
+        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4, phases=t if phases else None)
+        n_keep = int(keep.sum().item())
+        if phases:
+            t.append(time.perf_counter())
+            print(f"[rank {rank}] exchange phases ms: " + " ".join(f"{1000 * (b - a):.2f}" for a, b in zip(t, t[1:])), file=sys.stderr)
+        return k_all, n_keep
 
     def barrier():
         if world > 1:
@@ -289,11 +299,15 @@ def main():
 
     for i in range(W_):
         step(i)
-    dedup_exchange()            # warm-up of the exchange too (the first collective creates the NCCL communicator)
+    for _ in range(3):          # warm-up of the exchange too: the first collective creates the NCCL communicator and
+        dedup_exchange()        # the next ones still finish lazy connection set-up (20 ms per call at 8 ranks otherwise)
     barrier()
     count.zero_()
-    sampler = ClockSampler(local)
-    sampler.start()
+    # rank 0 samples its GPU's clocks (NVML calls from 8 processes at once serialise in the driver and showed up as
+    # multi-millisecond launch stalls on the other ranks at N=8)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -379,7 +393,7 @@ def main():
                "host_pages_numa_bound_cpus": numa.applied,
                "includes": "pinned H2D (3 slots, copy stream), fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
         del streamer
-    clocks = sampler.stop()          # sampled over both timed regions (resident steps and end-to-end streaming)
+    clocks = sampler.stop() if sampler is not None else None     # sampled over both timed regions (resident steps and end-to-end streaming)
 
     # ---- per-kernel timing of profiled steps (same run, same stream) -> roofline of the dominant kernel -------
     peak, peak_src = load_peak()

@@ -146,17 +146,23 @@ __global__ void __launch_bounds__(256) phash_dct_kernel(const int32_t *qbuf, con
     }
 }
 
+// keep[i] = 0 iff some j with key[j] < key[i] has popcount(hash[i] ^ hash[j]) <= max_hamming.  All pairs, split over
+// blockIdx.y slices of j so that a few thousand regions still fill the GPU; keep[] is preset to 1 by the launcher.
+// A slice of the (hash, key) pairs is staged in shared memory and scanned by every thread of the CTA.
+constexpr int DEDUP_TILE = 1024;
 __global__ void __launch_bounds__(256) phash_dedup_kernel(const unsigned long long *hashes, const unsigned long long *keys, int n,
                                                           int max_hamming, uint8_t *keep)
 {
+    __shared__ unsigned long long sh[DEDUP_TILE], sk[DEDUP_TILE];
     const int i = blockIdx.x * 256 + threadIdx.x;
+    const int j0 = blockIdx.y * DEDUP_TILE, j1 = min(j0 + DEDUP_TILE, n);
+    for (int j = j0 + threadIdx.x; j < j1; j += 256) { sh[j - j0] = hashes[j]; sk[j - j0] = keys[j]; }
+    __syncthreads();
     if (i >= n) return;
     const unsigned long long h = hashes[i], k = keys[i];
-    uint8_t kp = 1;
-    for (int j = 0; j < n; ++j) {
-        if (keys[j] < k && __popcll(hashes[j] ^ h) <= max_hamming) { kp = 0; break; }
-    }
-    keep[i] = kp;
+    bool dup = false;
+    for (int j = 0; j < j1 - j0; ++j) dup |= (sk[j] < k) && (__popcll(sh[j] ^ h) <= max_hamming);
+    if (dup) keep[i] = 0;
 }
 
 __global__ void __launch_bounds__(256) select_rois_kernel(const int32_t *n_labels, const int32_t *stats, int batch, int max_labels,
@@ -251,8 +257,9 @@ extern "C" SYNSEG_EXPORT int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t 
     if (!ctx) { synseg_set_error("synseg_phash_dedup: ctx is NULL"); return SYNSEG_E_INVALID; }
     if (n <= 0) return SYNSEG_OK;
     if (!hashes || !keys || !keep) { synseg_set_error("synseg_phash_dedup: NULL buffer"); return SYNSEG_E_INVALID; }
-    phash_dedup_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)hashes,
-                                                                       (const unsigned long long *)keys, n, max_hamming, keep);
+    SS_CUDA(cudaMemsetAsync(keep, 1, (size_t)n, (cudaStream_t)stream));
+    phash_dedup_kernel<<<dim3(cdiv(n, 256), cdiv(n, DEDUP_TILE)), 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)hashes,
+                                                                                                  (const unsigned long long *)keys, n, max_hamming, keep);
     SS_LAUNCH_CHECK(ctx, "phash_dedup", (cudaStream_t)stream);
     return SYNSEG_OK;
 }

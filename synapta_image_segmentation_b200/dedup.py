@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-SENTINEL_KEY = -1          # int64 view of 0xFFFF...; real keys are < 2^62
+SENTINEL_KEY = (1 << 63) - 1          # sorts after every real key (real keys are < 2^62)
 
 
 def shard_pages(n_pages: int, rank: int, world: int) -> range:
@@ -34,7 +34,12 @@ def region_key(page_idx: int, region_idx: int) -> int:
 
 def gather_hashes(hashes: torch.Tensor, keys: torch.Tensor, capacity: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-gather (hash, key) int64 pairs from every rank.  Works on CUDA tensors over NCCL and on CPU
-    tensors over gloo (the host-logic tests).  Returns the concatenated valid (hashes, keys), sorted by key."""
+    tensors over gloo (the host-logic tests).  Returns the concatenated valid (hashes, keys), sorted by key.
+
+    Every intermediate has a FIXED shape (capacity x world): the sentinel-padded buffers are sorted by key, the
+    sentinels sort last, and the result is a prefix view.  No data-dependent allocation means the caching allocator
+    never has to cudaMalloc in the steady state -- with eight peer-mapped GPUs one cudaMalloc costs ~20 ms, which is
+    what a boolean-mask compaction of the gathered buffer cost at N=8."""
     n = hashes.numel()
     if n > capacity:
         raise ValueError(f"rank holds {n} regions, more than the gather capacity {capacity}")
@@ -47,15 +52,20 @@ def gather_hashes(hashes: torch.Tensor, keys: torch.Tensor, capacity: int, group
         dist.all_gather_into_tensor(out, buf, group=group)
     else:
         out = buf
-    valid = out[:, 1] != SENTINEL_KEY
-    out = out[valid]
-    order = torch.argsort(out[:, 1])
-    out = out[order]
-    return out[:, 0].contiguous(), out[:, 1].contiguous()
+    k_sorted, order = torch.sort(out[:, 1].contiguous())
+    h_sorted = out[:, 0].contiguous()[order]
+    n_valid = int((k_sorted != SENTINEL_KEY).sum().item())
+    return h_sorted[:n_valid], k_sorted[:n_valid]
 
 
-def cross_page_dedup(ctx, hashes: torch.Tensor, keys: torch.Tensor, capacity: int, max_hamming: int = 4, group=None):
-    """Returns (all_keys int64 [N] sorted, keep uint8 [N]) -- identical on every rank."""
+def cross_page_dedup(ctx, hashes: torch.Tensor, keys: torch.Tensor, capacity: int, max_hamming: int = 4, group=None, phases=None):
+    """Returns (all_keys int64 [N] sorted, keep uint8 [N]) -- identical on every rank.
+    phases: optional list that receives wall-clock stamps after the gather and after the dedup kernel (diagnostics)."""
     h, k = gather_hashes(hashes, keys, capacity, group)
+    if phases is not None:
+        import time
+        torch.cuda.synchronize(); phases.append(time.perf_counter())
     keep = ctx.phash_dedup(h, k, max_hamming)
+    if phases is not None:
+        torch.cuda.synchronize(); phases.append(time.perf_counter())
     return k, keep
