@@ -296,3 +296,30 @@ def test_phash_matches_oracle_and_dedup(ctx):
     keys = np.array([5, 1, 9, 7, 3], dtype=np.uint64)
     keep = host(ctx.phash_dedup(dev(h.view(np.int64)), dev(keys.view(np.int64)), 4))
     assert keep.tolist() == [1, 1, 0, 0, 1]
+
+
+def test_strided_and_offset_planes(ctx):
+    """Views into larger buffers: row stride != width (aligned and unaligned strides), base pointers off by 1..3 bytes,
+    pitched outputs -- for the stencils with vector paths -- and the grey plane handed back by the fused pipeline."""
+    h, w = 150, 203
+    big = imgs.blurred_noise(h + 4, 256, 9, passes=2)
+    for x0 in (0, 1, 3, 16):
+        g = big[2:2 + h, x0:x0 + w]
+        t = dev(big)[2:2 + h, x0:x0 + w]                       # row stride 256 (16-byte aligned), base offset x0
+        assert not t.is_contiguous()
+        assert np.array_equal(host(ctx.canny(t, 50, 150)), cv2.Canny(np.ascontiguousarray(g), 50, 150)), x0
+        got = host(ctx.adaptive_mean(t, 25, 10, True))
+        want = cv2.adaptiveThreshold(np.ascontiguousarray(g), 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, 25, 10)
+        assert np.array_equal(got, want), x0
+        m = (g > 128).astype(np.uint8) * 255
+        tm = dev(np.where(big > 128, 255, 0).astype(np.uint8))[2:2 + h, x0:x0 + w]
+        n, lab, st, ce = ctx.ccl_stats(tm, 4096)
+        n_w, lab_w, st_w, ce_w = cv2.connectedComponentsWithStats(np.ascontiguousarray(m), 8, cv2.CV_32S)
+        assert int(n[0]) == n_w and np.array_equal(host(lab[0]), lab_w) and np.array_equal(host(st[0, :n_w]), st_w)
+    # fused pipeline with the grey plane handed back (cv2 grey, kept for downstream features)
+    rgb = imgs.rgb_noise(97, 131, 3)
+    gray_out = torch.empty((1, 97, 144), dtype=torch.uint8, device="cuda")[:, :, :131]
+    n, st, ce = ctx.detect_pages(dev(rgb)[None], 15, 5, 5, max_labels=4096, gray_out=gray_out)
+    assert np.array_equal(host(gray_out[0]), cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+    n2, st2, _ = ctx.detect_pages(dev(rgb)[None], 15, 5, 5, max_labels=4096)
+    assert int(n[0]) == int(n2[0]) and torch.equal(st[0, :int(n[0])], st2[0, :int(n[0])])
