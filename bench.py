@@ -303,8 +303,7 @@ def main():
         dedup_exchange()        # the next ones still finish lazy connection set-up (20 ms per call at 8 ranks otherwise)
     barrier()
     count.zero_()
-    # rank 0 samples its GPU's clocks (NVML calls from 8 processes at once serialise in the driver and showed up as
-    # multi-millisecond launch stalls on the other ranks at N=8)
+    # rank 0 samples its GPU's clocks (one NVML client per box is enough and keeps the other ranks' driver calls quiet)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()
