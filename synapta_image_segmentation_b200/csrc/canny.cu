@@ -31,7 +31,7 @@ constexpr int CN_OUT_W = 480;           // output columns per warp strip (lanes 
 #endif
 constexpr int CN_WARPS = SYNSEG_CN_WARPS;   // independent warps per CTA (1: a finished warp frees its registers at once)
 #ifndef SYNSEG_CN_MINBLOCKS
-#define SYNSEG_CN_MINBLOCKS (16 / SYNSEG_CN_WARPS)
+#define SYNSEG_CN_MINBLOCKS (19 / SYNSEG_CN_WARPS)   // resident warps per SM the register allocation aims at (17..20 measured equal, 21 slower)
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int CN_DEPTH = 4;             // grey rows in flight per warp (cp.async ring)
@@ -81,7 +81,9 @@ __device__ __forceinline__ void make_hrow(HRow &h, const uint4 v, uint32_t wl, u
     }
 }
 
-struct MagRing { uint32_t mag[3][8][32], dx[3][8][32], dy[3][8][32]; };   // [ring row][pair register][lane]
+// magnitudes of three rows (NMS looks one row up and down); dx / dy only of the row being suppressed and the row being
+// produced (two slots, row parity)
+struct MagRing { uint32_t mag[3][8][32], dx[2][8][32], dy[2][8][32]; };   // [ring row][pair register][lane]
 
 __device__ __forceinline__ int col_pr(int c) { return 2 * (c >> 2) + (c & 1); }
 __device__ __forceinline__ int col_half(int c) { return (c >> 1) & 1; }
@@ -102,7 +104,7 @@ struct CnState {
 
 // Magnitude row (middle row B) -> ring slot.  Returns the candidate mask in gather order:
 // bit 4t + i <-> pair register 2i + (t >> 1), half t & 1  <->  column 4i + (t >> 1) + 2 (t & 1).
-__device__ __forceinline__ uint32_t produce_row(MagRing &R, CnState &st, int slot, int lane, const HRow &A, const HRow &B, const HRow &C,
+__device__ __forceinline__ uint32_t produce_row(MagRing &R, CnState &st, int slot, int par, int lane, const HRow &A, const HRow &B, const HRow &C,
                                                 bool row_in)
 {
     const bool blank = A.uni & B.uni & C.uni & (A.rep == B.rep) & (B.rep == C.rep);
@@ -119,7 +121,7 @@ __device__ __forceinline__ uint32_t produce_row(MagRing &R, CnState &st, int slo
             const int c0 = 4 * (i >> 1) + (i & 1);
             mag &= (((st.cv16 >> c0) & 1u) ? 0xFFFFu : 0u) | (((st.cv16 >> (c0 + 2)) & 1u) ? 0xFFFF0000u : 0u);
         }
-        R.mag[slot][i][lane] = mag; R.dx[slot][i][lane] = dx; R.dy[slot][i][lane] = dy;
+        R.mag[slot][i][lane] = mag; R.dx[par][i][lane] = dx; R.dy[par][i][lane] = dy;
         cm[i] = __vadd2(mag, st.kpair);
     }
     uint32_t z = 0;
@@ -140,7 +142,7 @@ __device__ __forceinline__ void nms_one(const MagRing &R, const CnState &st, Nms
     const int pr = 2 * i + (t >> 1), sh = 16 * (t & 1);
     const int col = 4 * i + (t >> 1) + 2 * (t & 1);
     const int m = (int)((R.mag[sc][pr][owner] >> sh) & 0xFFFFu);
-    const int dx = (int)(short)(R.dx[sc][pr][owner] >> sh), dy = (int)(short)(R.dy[sc][pr][owner] >> sh);
+    const int dx = (int)(short)(R.dx[y & 1][pr][owner] >> sh), dy = (int)(short)(R.dy[y & 1][pr][owner] >> sh);
     const int ax = abs(dx), ay = abs(dy) << 15, tg22 = ax * 13573;
     bool keep;
     if (ay < tg22) keep = m > ring_mag(R, st.zmask, sc, owner, col - 1) && m >= ring_mag(R, st.zmask, sc, owner, col + 1);
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
             slot = (slot + 1) & (CN_DEPTH - 1);
         } else vcur = load16_rep(row_ptr(y + 2), x, W, false);
         build_hrow(C, vcur);
-        const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
+        const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, (y + 1) & 1, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
         __syncwarp();
         if (y >= y0) {
             uint32_t kept16 = 0, strong16 = 0;
