@@ -11,7 +11,8 @@
 //     foreground pixel in the two pixel rows of the block row (any such pair is 8-adjacent);
 //   * a block run is a maximal chain of linked blocks; it is identified by its first block, and only
 //     that block owns an entry in the parent array L (int32 per block, touched sparsely).
-// One warp owns one block row; a lane owns a 64-pixel chunk (one 64-bit word per pixel row); runs are
+// A group of 32 or 16 lanes owns one block row (half-warp rows where a row wastes fewer lanes; the union kernel
+// always uses a full warp); a lane owns a 64-pixel chunk (one 64-bit word per pixel row); runs are
 // found with bit arithmetic and a ballot-based carry across lanes.  Vertical contacts between block
 // rows are unions between runs, issued once per touching (run, run) pair:
 //   t = top pixel row of the block row, u = pixel row above it

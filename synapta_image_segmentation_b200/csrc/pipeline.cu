@@ -10,13 +10,15 @@
 // HBM plan per page: the RGB page is read once (3 B/px) and the grey page written once (1 B/px);
 // every mask after that is a bit plane (1/8 B/px): the adaptive threshold writes bits directly, the
 // Canny hysteresis ORs its result into the same plane, the dilate (folded with the close's dilate into
-// one (2k-1) pass) and the erode run on bit planes, and the labelling reads bits.  Intermediates are
-// sized so that a sub-batch stays in the 126 MB L2.
+// one (2k-1) pass) and the erode run on bit planes, and the labelling reads bits.  The bit planes of a
+// 50-page batch (53 MB each) stay in the 126 MB L2; the grey plane (420 MB) is re-read from HBM by the two stencils.
 //
 // synseg_grid_counts: per crop, grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2)
 //   -> non-zero counts, i.e. _detect_grid (pdf_image_segmentation.py:1546-1564) and the visual part of
 //   _detect_chart_subtype (:1365-1376); the Canny map can be handed back for the host-side consumers
 //   (HoughLinesP :1327,1387,1701 and findContours :1762).
+// synseg_hints_crops: the same per crop plus grey moments and the HSV mask count for a ragged batch of crops.
+// synseg_detect_pages_host: pages in host memory -> tables in host memory (staging ring + copy stream inside).
 #include "internal.cuh"
 
 static size_t detect_scratch_bytes(int W, int H, int B, int max_labels, bool need_gray)
