@@ -177,7 +177,13 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     MagRing &R = rings[warp];
     NmsStage &S = stages[warp];
 
-    const int W = p.width, H = p.height, hi = p.hi;
+    int W = p.width, H = p.height;
+    const int hi = p.hi;
+    if (p.kept.dims) {                                // ragged batch: the grid covers the canvas, this image may be smaller
+        const int2 d = p.kept.dims[img];
+        W = d.x; H = d.y;
+        if (strip * CN_OUT_W >= W || band * p.band_h >= H) return;   // warp-uniform (one task per warp)
+    }
     const int x = strip * CN_OUT_W - 16 + 16 * lane;  // first of this lane's 16 columns
     const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
     const uint8_t *base = p.src.p + img * p.src.bs;
@@ -310,9 +316,9 @@ int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u
     const size_t plane_bytes = (size_t)wpr * H * B * 4;
     void *p;
     SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
-    BitPlane kept{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    BitPlane kept{(uint32_t *)p, wpr, (int64_t)wpr * H, edges_bits.dims};      // a ragged batch hands its dims on
     SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
-    BitPlane strong{(uint32_t *)p, wpr, (int64_t)wpr * H};
+    BitPlane strong{(uint32_t *)p, wpr, (int64_t)wpr * H, edges_bits.dims};
     SS_TRY(launch_canny_classes(ctx, gray, kept, strong, lo, hi, st));
     return run_hysteresis(ctx, kept, strong, W, H, B, edges_u8, edges_bits, or_bits, st);
 }

@@ -44,6 +44,7 @@ struct RowGeom {
     int64_t bper;      // parent-array entries per image
     int nseg;          // segments per row: G lanes x 64 pixels each (G = lanes per block row, 32 or 16)
     int cpr;           // 64-pixel chunks per row = cdiv(width, 64)
+    const int2 *dims;  // ragged batch (internal.cuh): per-image width / height; everything above then describes the canvas
 };
 
 // Lanes per block row.  G = 32: one warp per block row.  G = 16: a warp owns two consecutive block rows, one per
@@ -156,6 +157,8 @@ __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
 // lane = lane within the group (0..G-1); rows outside the image read as empty (null row pointers) so that a half-warp
 // whose block row does not exist still takes part in the warp-wide intrinsics
 #define ROW_PROLOGUE(first_row)                                                             \
+    RowGeom g = g_;                                                                          \
+    if (g_.dims) { const int2 d_ = g_.dims[blockIdx.y]; g.width = d_.x; g.height = d_.y; g.bh = (d_.y + 1) >> 1; } \
     const int lane = threadIdx.x & (G - 1);                                                  \
     const int by = (first_row) + (blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5)) * (32 / G) + ((threadIdx.x & 31) / G); \
     const int img = blockIdx.y;                                                              \
@@ -167,7 +170,7 @@ __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
 
 // every run start becomes its own parent
 template <int G>
-__global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall)
+__global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g_, int32_t *Lall)
 {
     ROW_PROLOGUE(0)
     if (!warp_ok) return;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g, int32_t *Lall
 // (take a path to the nearest strong run: all its edges but none beyond have a weak end).  The test is made on the
 // run pieces inside this lane's chunk (a subset of the runs), so it only ever skips safely.
 template <bool HYST, int G>
-__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lall, BitPlane strong)
+__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g_, int32_t *Lall, BitPlane strong)
 {
     ROW_PROLOGUE(1)
     if (!warp_ok) return;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g, int32_t *Lal
 //                      and their number to row_count.
 //  MODE 1 (hysteresis): the root of every run piece that holds a strong pixel is flagged.
 template <int MODE, int G>
-__global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g, int32_t *Lall, u64 *rootbits, int32_t *row_count,
+__global__ void __launch_bounds__(256) rccl_compress_kernel(RowGeom g_, int32_t *Lall, u64 *rootbits, int32_t *row_count,
                                                             BitPlane strong, uint32_t *flags, int64_t fper)
 {
     ROW_PROLOGUE(0)
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(256) ccl_scan_kernel(int n, int32_t *cnt, int3
 
 // roots get L[root] = -(label) - 1 with label = 1 + rank in block raster order
 template <int G>
-__global__ void __launch_bounds__(256) rccl_assign_kernel(RowGeom g, int32_t *Lall, const u64 *rootbits, const int32_t *row_off)
+__global__ void __launch_bounds__(256) rccl_assign_kernel(RowGeom g_, int32_t *Lall, const u64 *rootbits, const int32_t *row_off)
 {
     ROW_PROLOGUE(0)
     (void)r0; (void)r1; (void)pbase;
@@ -427,7 +430,7 @@ __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contri
 struct LabelStage { int32_t lab[1024]; u64 px[2][32]; };
 
 template <bool WRITE_LABELS, int G>
-__global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
+__global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g_, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
 {
     static_assert(!WRITE_LABELS || G == 32, "the label image path stages one block row per warp");
     __shared__ SlotCache sc;
@@ -552,7 +555,7 @@ __device__ __forceinline__ uint32_t bytes_of_nibble(uint32_t nib) { return ((nib
 
 // keep the pixels of every run piece whose component was flagged (holds a strong pixel)
 template <bool OUT_BITS, int G>
-__global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g, const int32_t *Lall, const uint32_t *flags, int64_t fper,
+__global__ void __launch_bounds__(256) rccl_hyst_final_kernel(RowGeom g_, const int32_t *Lall, const uint32_t *flags, int64_t fper,
                                                               Plane out, bool out_al16, BitPlane obits, bool or_bits)
 {
     ROW_PROLOGUE(0)
@@ -624,6 +627,7 @@ RowGeom geom_of(BitPlane bits, int width, int height, int G)
     g.bper = (int64_t)align_up((size_t)g.bw * g.bh, 4);
     g.nseg = cdiv(width, 64 * G);
     g.cpr = cdiv(width, 64);
+    g.dims = bits.dims;
     return g;
 }
 

@@ -98,7 +98,147 @@ __global__ void __launch_bounds__(GRAY_THREADS) rgb2gray_kernel(Plane src, Plane
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ragged crop front end: ONE pass over a packed batch of crops of different sizes produces
+//   * the PIL grey of every crop in a canvas batch (what Canny reads; pdf_image_segmentation.py:1549),
+//   * the exact grey moments sum / sum of squares / non-zero count (np.var at :1805, :2989, :3073),
+//   * the HSV mask count S>30 & V>40 & V<240 of RGB crops (:1571-1577),
+// so the source (3 B/px) is read once instead of three times.  blockIdx.y = crop, a warp owns a row (four rows per
+// warp and CTA), a lane 16
+// consecutive pixels: 48 source bytes as the aligned superset (like rgb2gray), the moments of the 16 grey bytes with
+// dp4a (sum: dot with 0x01010101, sum of squares: dot with itself), one 128-bit store into the canvas.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load48(const uint8_t *sp, uint32_t (&v)[12])
+{
+    const uintptr_t a = (uintptr_t)sp;
+    const uint4 *ap = (const uint4 *)(a & ~(uintptr_t)15);
+    const int s = (int)(a & 15);
+    const uint4 q0 = __ldg(ap), q1 = __ldg(ap + 1), q2 = __ldg(ap + 2);
+    if (s == 0) {
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+        return;
+    }
+    const uint4 q3 = __ldg(ap + 3);        // holds valid bytes whenever the start is misaligned
+    const uint32_t w[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, 0u};
+    const int ws = s >> 2, bs = (s & 3) * 8;
+    switch (ws) {
+    case 0:
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], bs);
+        break;
+    case 1:
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 1], w[i + 2], bs);
+        break;
+    case 2:
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 2], w[i + 3], bs);
+        break;
+    default:
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 3], w[i + 4], bs);
+        break;
+    }
+}
+
+// grey byte and HSV mask bit of the four pixels held by three words
+__device__ __forceinline__ uint32_t gray_mask4(uint32_t w0, uint32_t w1, uint32_t w2, const uint32_t *sdiv, uint32_t &mask_cnt)
+{
+    const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = px[j] & 0xFFu, g = (px[j] >> 8) & 0xFFu, b = (px[j] >> 16) & 0xFFu;
+        mask_cnt += hsv_mask_px(r, g, b, sdiv) ? 1u : 0u;
+        out |= gray1<SYNSEG_GRAY_PIL>(px[j]) << (8 * j);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256) crop_front_kernel(const uint8_t *base, const CropTask *tasks, Plane dst, unsigned long long *res)
+{
+    __shared__ uint32_t sdiv[256];
+    __shared__ unsigned long long sh[8][4];
+    const CropTask t = tasks[blockIdx.y];
+    if ((int)blockIdx.x * 8 >= t.height) return;                     // the grid covers the tallest crop of the batch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sdiv[threadIdx.x] = hsv_sdiv(threadIdx.x);
+    __syncthreads();
+    const uint8_t *src = base + t.offset;
+    uint8_t *dimg = dst.p + (int64_t)blockIdx.y * dst.bs;
+    const int W = t.width;
+    unsigned long long s = 0, ss = 0, nz = 0, mk = 0;
+    for (int y = blockIdx.x * 8 + warp; y < t.height; y += gridDim.x * 8) {
+        const uint8_t *srow = src + (int64_t)y * t.row_stride;
+        uint8_t *drow = dimg + (int64_t)y * dst.rs;
+        uint32_t rs = 0, rss = 0, rnz = 0, rmk = 0;                  // per lane and row: <= 65025 * 16 * 64 fits 32 bits
+        for (int x0 = 16 * lane; x0 < W; x0 += 512) {
+            uint4 o;
+            if (x0 + 16 <= W) {
+                if (t.channels == 3) {
+                    uint32_t v[12];
+                    load48(srow + 3 * (int64_t)x0, v);
+                    o.x = gray_mask4(v[0], v[1], v[2], sdiv, rmk); o.y = gray_mask4(v[3], v[4], v[5], sdiv, rmk);
+                    o.z = gray_mask4(v[6], v[7], v[8], sdiv, rmk); o.w = gray_mask4(v[9], v[10], v[11], sdiv, rmk);
+                } else {
+                    const uint8_t *sp = srow + x0;
+                    if (((uintptr_t)sp & 15) == 0) o = __ldg((const uint4 *)sp);
+                    else {
+                        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[i >> 2] |= (uint32_t)__ldg(sp + i) << (8 * (i & 3));
+                        o = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                *(uint4 *)(drow + x0) = o;                           // canvas rows are 16-byte aligned
+            } else {                                                 // last, partial group of the row
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int i = 0; x0 + i < W; ++i) {
+                    uint32_t gv;
+                    if (t.channels == 3) {
+                        const uint8_t *p = srow + 3 * (int64_t)(x0 + i);
+                        const uint32_t r = __ldg(p), g = __ldg(p + 1), b = __ldg(p + 2);
+                        rmk += hsv_mask_px(r, g, b, sdiv) ? 1u : 0u;
+                        gv = gray1<SYNSEG_GRAY_PIL>(r | (g << 8) | (b << 16));
+                    } else gv = __ldg(srow + x0 + i);
+                    drow[x0 + i] = (uint8_t)gv;
+                    w[i >> 2] |= gv << (8 * (i & 3));
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);              // bytes beyond the row stay zero: they add nothing below
+            }
+            rs = __dp4a(o.x, 0x01010101u, rs); rs = __dp4a(o.y, 0x01010101u, rs); rs = __dp4a(o.z, 0x01010101u, rs); rs = __dp4a(o.w, 0x01010101u, rs);
+            rss = __dp4a(o.x, o.x, rss); rss = __dp4a(o.y, o.y, rss); rss = __dp4a(o.z, o.z, rss); rss = __dp4a(o.w, o.w, rss);
+            rnz += __popc(__vcmpne4(o.x, 0u) & 0x01010101u) + __popc(__vcmpne4(o.y, 0u) & 0x01010101u) +
+                   __popc(__vcmpne4(o.z, 0u) & 0x01010101u) + __popc(__vcmpne4(o.w, 0u) & 0x01010101u);
+        }
+        s += rs; ss += rss; nz += rnz; mk += rmk;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, d); ss += __shfl_down_sync(0xffffffffu, ss, d);
+        nz += __shfl_down_sync(0xffffffffu, nz, d); mk += __shfl_down_sync(0xffffffffu, mk, d);
+    }
+    if (lane == 0) { sh[warp][0] = s; sh[warp][1] = ss; sh[warp][2] = nz; sh[warp][3] = mk; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < 8; ++w) tot += sh[w][threadIdx.x];
+        if (tot) atomicAdd(res + 8 * (int64_t)blockIdx.y + 3 + threadIdx.x, tot);
+    }
+}
+
 }  // namespace
+
+int launch_crop_front(synseg_ctx *ctx, const void *base, const CropTask *tasks, int n, const synseg_img *gray_canvas, uint64_t *res,
+                      cudaStream_t st)
+{
+    if (!plane_aligned(gray_canvas, 16)) { synseg_set_error("crop_front: the grey canvas must be 16-byte aligned"); return SYNSEG_E_INVALID; }
+    crop_front_kernel<<<dim3(cdiv(gray_canvas->height, 32), n), 256, 0, st>>>((const uint8_t *)base, tasks, plane_of(gray_canvas),
+                                                                            (unsigned long long *)res);
+    SS_LAUNCH_CHECK(ctx, "crop_front", st);
+    return SYNSEG_OK;
+}
 
 int launch_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, int mode, cudaStream_t st)
 {

@@ -104,10 +104,15 @@ static inline bool plane_aligned(const synseg_img *im, int a)
 
 // Bit-packed masks: one bit per pixel, LSB = leftmost pixel, `wpr` 32-bit words per row
 // (multiple of 4 so rows are 16-byte aligned), bits at x >= width are always 0.
+// Ragged batches (crops of different sizes processed by ONE launch per stage): the planes of a batch share one canvas
+// geometry (wpr / bs sized for the widest / tallest image) and `dims` gives the real width and height of every image;
+// a kernel that finds dims != NULL takes its width / height from there and skips tasks that lie outside the image.
+// Words at or beyond cdiv(width, 32) and rows at or beyond height are then undefined and never read.
 struct BitPlane {
     uint32_t *p;
     int wpr;        // words per row
     int64_t bs;     // words per image
+    const int2 *dims;   // per-image (width, height) of a ragged batch, or NULL: every image has the launch's width x height
 };
 static inline int bit_wpr(int width) { return (int)align_up((size_t)cdiv(width, 32), 4); }
 
@@ -164,6 +169,15 @@ size_t ccl_label_scratch_bytes(int width, int height, int batch);
 size_t hysteresis_scratch_bytes(int width, int height, int batch);
 size_t canny_scratch_bytes(int width, int height, int batch);
 size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels);
+
+// Ragged crop front end (gray.cu): packed crops -> PIL-grey canvas + grey moments + HSV mask count in one pass over the
+// source.  tasks / res are DEVICE arrays; res[8*j + 3..6] += {sum, sum_sq, non_zero, mask_px} of crop j.
+struct CropTask {
+    int64_t offset, row_stride;     // bytes from `base`
+    int32_t width, height, channels, out_index;
+};
+int launch_crop_front(synseg_ctx *ctx, const void *base, const CropTask *tasks, int n, const synseg_img *gray_canvas, uint64_t *res,
+                      cudaStream_t st);
 
 int launch_moments(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois,
                    uint64_t *out, cudaStream_t st);

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) unpack_bits_kernel(BitPlane src, Plane ds
 __global__ void __launch_bounds__(256) count_bits_kernel(BitPlane src, int nw, int height, unsigned long long *out, int out_stride)
 {
     const int img = blockIdx.y;
+    if (src.dims) { const int2 d = src.dims[img]; nw = (d.x + 31) >> 5; height = d.y; }     // ragged batch
     const int64_t total = (int64_t)nw * height;
     unsigned cnt = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -217,6 +218,11 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
     const int img = (int)(row / height);
     const int y = (int)(row - (int64_t)img * height);
     const int w0 = 4 * q4;
+    if (src.dims) {                                                   // ragged batch: this image may be smaller than the canvas
+        const int2 d = src.dims[img];
+        width = d.x; nw = (d.x + 31) >> 5;
+        if (y >= d.y || w0 >= nw) return;
+    }
     const int aw = (anchor + 31) >> 5, sft = 32 * aw - anchor;        // window of output bit b of word w0+q starts at bit 32q + b + sft of D
     const uint32_t last_mask = (width & 31) ? ((1u << (width & 31)) - 1u) : 0xffffffffu;
     const uint32_t *sp = src.p + img * src.bs + (int64_t)y * src.wpr;
@@ -298,6 +304,11 @@ __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPla
     const int w = (int)(id % nw);
     const int seg = (int)((id / nw) % nseg);
     const int img = (int)(id / ((int64_t)nw * nseg));
+    if (src.dims) {                                                   // ragged batch: this image may be smaller than the canvas
+        const int2 d = src.dims[img];
+        width = d.x; height = d.y; nw = (d.x + 31) >> 5;
+        if (w >= nw || seg * k >= height) return;                     // no block-level synchronisation below
+    }
     const uint32_t last_mask = (width & 31) ? ((1u << (width & 31)) - 1u) : 0xffffffffu;
     const uint32_t vmask = (w == nw - 1) ? last_mask : 0xffffffffu;
     const uint32_t *sp = src.p + img * src.bs + w;
@@ -506,6 +517,7 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
         SS_LAUNCH_CHECK(ctx, "bitmorph_h", st);
         return SYNSEG_OK;
     }
+    if (src.dims) { synseg_set_error("bitmorph_h: ragged batches need k <= 226 and distinct planes"); return SYNSEG_E_INVALID; }
     const int padw = cdiv(k, 32) + 1;
     const size_t smem = (size_t)8 * 2 * (nw + 2 * padw + 1) * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_h: row too wide for shared memory"); return SYNSEG_E_INVALID; }
@@ -535,6 +547,7 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
         SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
         return SYNSEG_OK;
     }
+    if (src.dims) { synseg_set_error("bitmorph_v: ragged batches need k <= 384"); return SYNSEG_E_INVALID; }
     const size_t smem = (size_t)(BV_TH + k - 1) * 32 * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_v: kernel height %d too large", k); return SYNSEG_E_INVALID; }
     static bool attr_set = false;

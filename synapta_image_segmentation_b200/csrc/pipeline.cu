@@ -21,6 +21,10 @@
 // synseg_detect_pages_host: pages in host memory -> tables in host memory (staging ring + copy stream inside).
 #include "internal.cuh"
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 static size_t detect_scratch_bytes(int W, int H, int B, int max_labels, bool need_gray)
 {
     const size_t gray = need_gray ? (size_t)align_up((size_t)W, 16) * H * B + 256 : 0;
@@ -177,6 +181,108 @@ extern "C" SYNSEG_EXPORT int synseg_grid_counts(synseg_ctx *ctx, const synseg_im
     return SYNSEG_OK;
 }
 
+// ---- ragged batches of crops ------------------------------------------------------------------------------------
+// The crops are sorted by size and cut into chunks; a chunk is processed by ONE launch per stage on a canvas batch
+// (planes sized for the tallest / widest crop of the chunk, per-crop width / height in a device table that the
+// kernels consult: BitPlane::dims).  16 launches per chunk instead of ~25 per crop.
+__global__ void __launch_bounds__(256) scatter_results_kernel(const uint64_t *sorted, const CropTask *tasks, int n, uint64_t *out)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 8 * n) return;
+    out[8 * (int64_t)tasks[i >> 3].out_index + (i & 7)] = sorted[i];
+}
+
+static size_t ragged_chunk_bytes(int wc, int hc, int n)
+{
+    const size_t gray = (size_t)align_up((size_t)wc, 16) * hc * n + 256;
+    const size_t plane = (size_t)bit_wpr(wc) * hc * n * 4 + 256;
+    return gray + 3 * plane + canny_scratch_bytes(wc, hc, n) + 4096;
+}
+
+constexpr size_t RAGGED_CHUNK_BUDGET = (size_t)1 << 30;    // scratch per chunk
+constexpr int RAGGED_CHUNK_MAX = 1024;                      // crops per chunk
+
+static int hints_crops_ragged(synseg_ctx *ctx, const void *base, const synseg_crop *crops, int n, int kw, int kh, uint64_t *out, cudaStream_t st)
+{
+    // order: by height, then width (chunks of similar crops waste few canvas rows)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (crops[a].height != crops[b].height) return crops[a].height < crops[b].height;
+        if (crops[a].width != crops[b].width) return crops[a].width < crops[b].width;
+        return a < b;
+    });
+    std::vector<CropTask> tasks(n);
+    std::vector<int2> dims(n);
+    for (int j = 0; j < n; ++j) {
+        const synseg_crop &c = crops[order[j]];
+        tasks[j] = CropTask{(int64_t)c.offset, c.row_stride, c.width, c.height, c.channels, order[j]};
+        dims[j] = make_int2(c.width, c.height);
+    }
+    // chunks: consecutive crops while the canvas fits the scratch budget
+    struct Chunk { int first, count, wc, hc; };
+    std::vector<Chunk> chunks;
+    size_t worst = 0;
+    int chunk_max = RAGGED_CHUNK_MAX;
+    if (const char *e = getenv("SYNSEG_RAGGED_CHUNK")) { const int v = atoi(e); if (v >= 1 && v < chunk_max) chunk_max = v; }
+    for (int j = 0; j < n;) {
+        Chunk ch{j, 0, 0, 0};
+        while (j < n && ch.count < chunk_max) {
+            const int wc = tasks[j].width > ch.wc ? tasks[j].width : ch.wc, hc = tasks[j].height > ch.hc ? tasks[j].height : ch.hc;
+            if (ch.count > 0 && ragged_chunk_bytes(wc, hc, ch.count + 1) > RAGGED_CHUNK_BUDGET) break;
+            ch.wc = wc; ch.hc = hc; ++ch.count; ++j;
+        }
+        const size_t need = ragged_chunk_bytes(ch.wc, ch.hc, ch.count);
+        if (need > worst) worst = need;
+        chunks.push_back(ch);
+    }
+    const size_t table_bytes = align_up(sizeof(CropTask) * (size_t)n, 256) + align_up(sizeof(int2) * (size_t)n, 256) + align_up(64 * (size_t)n, 256);
+    SS_TRY(arena_ensure(ctx, table_bytes + worst + 4096));
+    arena_begin(ctx);
+    void *p;
+    SS_TRY(arena_alloc(ctx, sizeof(CropTask) * (size_t)n, &p, st)); CropTask *d_tasks = (CropTask *)p;
+    SS_TRY(arena_alloc(ctx, sizeof(int2) * (size_t)n, &p, st)); int2 *d_dims = (int2 *)p;
+    SS_TRY(arena_alloc(ctx, 64 * (size_t)n, &p, st)); uint64_t *res = (uint64_t *)p;
+    // pageable sources: the driver stages the bytes before cudaMemcpyAsync returns, so the vectors may die with this call
+    SS_CUDA(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(CropTask) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(d_dims, dims.data(), sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaMemsetAsync(res, 0, 64 * (size_t)n, st));
+    const int fkw = 2 * (kw - 1) + 1, fkh = 2 * (kh - 1) + 1, fax = 2 * (kw / 2), fay = 2 * (kh / 2);      // OPEN, iterations = 2, folded
+    const size_t mark = arena_mark(ctx);
+    for (const Chunk &ch : chunks) {
+        arena_release(ctx, mark);
+        const int W = ch.wc, H = ch.hc, B = ch.count;
+        synseg_img gray;
+        gray.width = W; gray.height = H; gray.batch = B; gray._pad = 0;
+        gray.row_stride = (int64_t)align_up((size_t)W, 16); gray.batch_stride = gray.row_stride * H;
+        SS_TRY(arena_alloc(ctx, (size_t)gray.batch_stride * B, &p, st)); gray.data = p;
+        const int wpr = bit_wpr(W);
+        const size_t pb = (size_t)wpr * H * B * 4;
+        const int2 *dm = d_dims + ch.first;
+        uint64_t *r = res + 8 * (size_t)ch.first;
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane edges{(uint32_t *)p, wpr, (int64_t)wpr * H, dm};
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane a{(uint32_t *)p, wpr, (int64_t)wpr * H, dm};
+        SS_TRY(arena_alloc(ctx, pb, &p, st)); BitPlane b{(uint32_t *)p, wpr, (int64_t)wpr * H, dm};
+        SS_TRY(launch_crop_front(ctx, base, d_tasks + ch.first, B, &gray, r, st));
+        SS_TRY(run_canny(ctx, &gray, nullptr, edges, false, 50, 150, st));
+        SS_TRY(launch_count_bits(ctx, edges, W, H, B, r + 2, 8, st));
+        // horizontal lines: erode then dilate with (fkw x 1); vertical lines with (1 x fkh); `edges` is never written
+        if (fkw > 1) {
+            SS_TRY(launch_bitmorph_h(ctx, edges, a, W, H, B, SYNSEG_MORPH_ERODE, fkw, fax, st));
+            SS_TRY(launch_bitmorph_h(ctx, a, b, W, H, B, SYNSEG_MORPH_DILATE, fkw, fax, st));
+        }
+        SS_TRY(launch_count_bits(ctx, fkw > 1 ? b : edges, W, H, B, r + 0, 8, st));
+        if (fkh > 1) {
+            SS_TRY(launch_bitmorph_v(ctx, edges, a, W, H, B, SYNSEG_MORPH_ERODE, fkh, fay, st));
+            SS_TRY(launch_bitmorph_v(ctx, a, b, W, H, B, SYNSEG_MORPH_DILATE, fkh, fay, st));
+        }
+        SS_TRY(launch_count_bits(ctx, fkh > 1 ? b : edges, W, H, B, r + 1, 8, st));
+    }
+    scatter_results_kernel<<<cdiv(8 * (int64_t)n, 256), 256, 0, st>>>(res, d_tasks, n, out);
+    SS_LAUNCH_CHECK(ctx, "scatter_results", st);
+    return SYNSEG_OK;
+}
+
 // Batched per-crop hint quantities for n crops of different sizes packed in one device buffer (config 4:
 // 10k cropped figure regions).  No host synchronisation: everything is queued on `stream`.
 extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
@@ -195,6 +301,11 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
         if (c.width > mw) mw = c.width;
         if (c.height > mh) mh = c.height;
     }
+    if (mw > 32766 || mh > 32766) { synseg_set_error("synseg_hints_crops: crop larger than 32766"); return SYNSEG_E_INVALID; }
+    // fixed structuring elements within the register / van Herk kernels' range: ragged batches, one launch per stage and chunk
+    if (kw >= 1 && kh >= 1 && 2 * (kw - 1) + 1 <= 226 && 2 * (kh - 1) + 1 <= 384 && !getenv("SYNSEG_HINTS_PER_CROP"))
+        return hints_crops_ragged(ctx, base, crops_host, n, kw, kh, out, st);
+    // per-image structuring elements (kw / kh <= 0: the chart rule max(20, W / 20)) or very long ones: crop by crop
     SS_TRY(arena_ensure(ctx, grid_counts_scratch(mw, mh)));
     SS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t) * 8 * (size_t)n, st));
     for (int i = 0; i < n; ++i) {

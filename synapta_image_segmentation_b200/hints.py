@@ -330,16 +330,15 @@ class FeatureHints:
 
     # ---- batched form for many crops (config 4) -----------------------------------------------------
     @staticmethod
-    def hints_batch(crops) -> List[Dict[str, Any]]:
-        """One dict per crop with the deterministic GPU hint quantities: h_count, v_count, edge_px,
-        grid_detected, variance, mask_px, data_points_fallback, image_subtype_visual.
-
-        All crops are packed into ONE pinned host buffer (rows padded to 16 bytes), copied to the device once,
-        processed by one `synseg_hints_crops` call (no host synchronisation between crops) and read back once."""
-        ctx = get_context()
+    def pack_crops(crops):
+        """PIL images (or HxW / HxWx3 uint8 arrays) -> (pinned uint8 buffer, [(offset, width, height, row_stride, channels)]):
+        the packed layout `synseg_hints_crops` reads, rows padded to 16 bytes."""
         arrays, descs, off = [], [], 0
         for image in crops:
-            if image.mode == "L":
+            if isinstance(image, np.ndarray):
+                a = image
+                ch = 1 if a.ndim == 2 else 3
+            elif image.mode == "L":
                 a, ch = np.asarray(image), 1
             else:
                 a, ch = np.asarray(image if image.mode == "RGB" else image.convert("RGB")), 3
@@ -349,11 +348,24 @@ class FeatureHints:
             arrays.append(a)
             off += rs * h
         if not descs:
-            return []
+            return None, []
         host = torch.empty(off, dtype=torch.uint8).pin_memory()
         hv = host.numpy()
         for a, (o, w, h, rs, ch) in zip(arrays, descs):
             hv[o:o + rs * h].reshape(h, rs)[:, :w * ch] = a.reshape(h, w * ch)
+        return host, descs
+
+    @staticmethod
+    def hints_batch(crops) -> List[Dict[str, Any]]:
+        """One dict per crop with the deterministic GPU hint quantities: h_count, v_count, edge_px,
+        grid_detected, variance, mask_px, data_points_fallback, image_subtype_visual.
+
+        All crops are packed into ONE pinned host buffer (rows padded to 16 bytes), copied to the device once,
+        processed by one `synseg_hints_crops` call (no host synchronisation between crops) and read back once."""
+        ctx = get_context()
+        host, descs = FeatureHints.pack_crops(crops)
+        if not descs:
+            return []
         dev = host.to(ctx.device, non_blocking=True)
         res = ctx.hints_crops(dev, descs).cpu().numpy()
         out = []

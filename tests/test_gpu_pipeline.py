@@ -212,6 +212,36 @@ def test_config4_ragged_crop_batch(ctx):
     assert FeatureHints.hints_batch([]) == []
 
 
+def test_ragged_crop_batch_chunks_and_tiny_crops(ctx, monkeypatch):
+    """The ragged (one launch per stage and chunk) path of synseg_hints_crops: tiny and degenerate crops, chunk
+    boundaries (SYNSEG_RAGGED_CHUNK=3), and equality with the crop-by-crop path and the cv2 / PIL / numpy chain."""
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    from synapta_image_segmentation_b200.synth import render_figure
+    shapes = [(1, 1), (1, 40), (40, 1), (2, 2), (3, 17), (16, 16), (15, 33), (64, 64), (65, 129), (31, 511), (130, 481), (97, 1025),
+              (300, 480), (301, 961), (7, 2049)]
+    crops = []
+    for i, (h, w) in enumerate(shapes):
+        if i % 3 == 0:
+            a = imgs.rgb_noise(h, w, 500 + i)
+        elif i % 3 == 1:
+            a = imgs.shapes(max(h, 8), max(w, 8), 600 + i)[:h, :w].copy()
+        else:
+            a = render_figure([8, i], 150, max(h, 40), max(w, 40))[:h, :w].copy()
+        crops.append(np.ascontiguousarray(a))
+    images = [Image.fromarray(c) for c in crops]
+    keys = ("h_count", "v_count", "edge_px", "mask_px", "variance")
+    want = [cv2_chain.crop_features(c) for c in crops]
+    for env in ({}, {"SYNSEG_RAGGED_CHUNK": "3"}, {"SYNSEG_HINTS_PER_CROP": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = FeatureHints.hints_batch(images)
+        for k in env:
+            monkeypatch.delenv(k)
+        for c, g, w_ in zip(crops, got, want):
+            assert tuple(g[k] for k in keys[:4]) == tuple(w_[k] for k in keys[:4]), (env, c.shape)
+            assert abs(g["variance"] - w_["variance"]) <= 1e-9 * max(1.0, w_["variance"]), (env, c.shape)
+
+
 def test_pipeline_edge_cases(ctx):
     """Blank page (background only), all-ink page (one component; cv2 reports an empty background row), 1x1 and
     1-row / 1-column pages, label overflow (n_labels = -(required)), and a ragged last batch through the streamer."""
