@@ -198,8 +198,9 @@ int synseg_grid_counts(synseg_ctx *ctx, const synseg_img *rgb_or_gray, int chann
                        const synseg_roi *rois_host, int32_t n_rois, int kw, int kh, uint64_t *out,
                        const synseg_img *edges_out, void *stream);
 
-/* One crop of a ragged batch: `channels` (1 grey / 3 RGB) x width x height pixels at byte `offset` of a packed
- * device buffer, rows `row_stride` bytes apart. */
+/* One crop of a ragged batch: `channels` (1 grey / 3 RGB / 4 RGBX, fourth byte ignored -- the layout PIL keeps RGB
+ * images in, so a host can hand them over without repacking; offset and row_stride then multiples of 4) x width x
+ * height pixels at byte `offset` of a packed device buffer, rows `row_stride` bytes apart. */
 typedef struct synseg_crop {
     uint64_t offset;
     int32_t width, height;
@@ -213,7 +214,10 @@ typedef struct synseg_crop {
  *                                           sum, sum_sq, non_zero          (PIL grey moments -> np.var: S:1805, 2989, 3073, O:1007),
  *                                           mask_px                        (HSV mask count, S:1574-1577; 0 for grey crops),
  *                                           0 }.
- * crops_host is a HOST array; everything is queued on `stream` without synchronising. */
+ * crops_host is a HOST array; everything is queued on `stream` without synchronising.
+ * With fixed structuring elements (1 <= kw <= 113, 1 <= kh <= 192) the crops are sorted by size, cut into chunks and
+ * every stage runs as ONE launch per chunk over a ragged batch (per-crop width / height in a device table);
+ * kw <= 0 / kh <= 0 (the chart rule max(20, W/20) of S:1368-1373) or longer elements run crop by crop (no RGBX). */
 int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
                        uint64_t *out, void *stream);
 

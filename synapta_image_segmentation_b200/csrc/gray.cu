@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(GRAY_THREADS) rgb2gray_kernel(Plane src, Plane
 // Ragged crop front end: ONE pass over a packed batch of crops of different sizes produces
 //   * the PIL grey of every crop in a canvas batch (what Canny reads; pdf_image_segmentation.py:1549),
 //   * the exact grey moments sum / sum of squares / non-zero count (np.var at :1805, :2989, :3073),
-//   * the HSV mask count S>30 & V>40 & V<240 of RGB crops (:1571-1577),
+//   * the HSV mask count S>30 & V>40 & V<240 of RGB crops (:1571-1577); RGB crops are 3 bytes per pixel or 4 (RGBX,
+//     the layout PIL keeps in memory, so a host can hand its images over without repacking them),
 // so the source (3 B/px) is read once instead of three times.  blockIdx.y = crop, a warp owns a row (four rows per
 // warp and CTA), a lane 16
 // consecutive pixels: 48 source bytes as the aligned superset (like rgb2gray), the moments of the 16 grey bytes with
@@ -156,6 +157,20 @@ __device__ __forceinline__ uint32_t gray_mask4(uint32_t w0, uint32_t w1, uint32_
     return out;
 }
 
+// the same for four RGBX pixels (one word each; the fourth byte is ignored: its grey coefficient is zero)
+__device__ __forceinline__ uint32_t gray_mask4x(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, const uint32_t *sdiv, uint32_t &mask_cnt)
+{
+    const uint32_t px[4] = {p0, p1, p2, p3};
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = px[j] & 0xFFu, g = (px[j] >> 8) & 0xFFu, b = (px[j] >> 16) & 0xFFu;
+        mask_cnt += hsv_mask_px(r, g, b, sdiv) ? 1u : 0u;
+        out |= gray1<SYNSEG_GRAY_PIL>(px[j]) << (8 * j);
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(256) crop_front_kernel(const uint8_t *base, const CropTask *tasks, Plane dst, unsigned long long *res)
 {
     __shared__ uint32_t sdiv[256];
@@ -181,6 +196,18 @@ __global__ void __launch_bounds__(256) crop_front_kernel(const uint8_t *base, co
                     load48(srow + 3 * (int64_t)x0, v);
                     o.x = gray_mask4(v[0], v[1], v[2], sdiv, rmk); o.y = gray_mask4(v[3], v[4], v[5], sdiv, rmk);
                     o.z = gray_mask4(v[6], v[7], v[8], sdiv, rmk); o.w = gray_mask4(v[9], v[10], v[11], sdiv, rmk);
+                } else if (t.channels == 4) {                        // RGBX words (4-byte aligned by contract)
+                    const uint32_t *wp = (const uint32_t *)(srow + 4 * (int64_t)x0);
+                    uint32_t v[16];
+                    if (((uintptr_t)wp & 15) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { const uint4 u = __ldg((const uint4 *)wp + q); v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __ldg(wp + i);
+                    }
+                    o.x = gray_mask4x(v[0], v[1], v[2], v[3], sdiv, rmk); o.y = gray_mask4x(v[4], v[5], v[6], v[7], sdiv, rmk);
+                    o.z = gray_mask4x(v[8], v[9], v[10], v[11], sdiv, rmk); o.w = gray_mask4x(v[12], v[13], v[14], v[15], sdiv, rmk);
                 } else {
                     const uint8_t *sp = srow + x0;
                     if (((uintptr_t)sp & 15) == 0) o = __ldg((const uint4 *)sp);
@@ -196,8 +223,8 @@ __global__ void __launch_bounds__(256) crop_front_kernel(const uint8_t *base, co
                 uint32_t w[4] = {0, 0, 0, 0};
                 for (int i = 0; x0 + i < W; ++i) {
                     uint32_t gv;
-                    if (t.channels == 3) {
-                        const uint8_t *p = srow + 3 * (int64_t)(x0 + i);
+                    if (t.channels >= 3) {
+                        const uint8_t *p = srow + t.channels * (int64_t)(x0 + i);
                         const uint32_t r = __ldg(p), g = __ldg(p + 1), b = __ldg(p + 2);
                         rmk += hsv_mask_px(r, g, b, sdiv) ? 1u : 0u;
                         gv = gray1<SYNSEG_GRAY_PIL>(r | (g << 8) | (b << 16));

@@ -293,10 +293,15 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
     if (!base || !crops_host || !out) { synseg_set_error("synseg_hints_crops: NULL argument"); return SYNSEG_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     int mw = 0, mh = 0;
+    bool has_rgbx = false;
     for (int i = 0; i < n; ++i) {
         const synseg_crop &c = crops_host[i];
-        if (c.width <= 0 || c.height <= 0 || (c.channels != 1 && c.channels != 3) || c.row_stride < (int64_t)c.width * c.channels) {
+        if (c.width <= 0 || c.height <= 0 || (c.channels != 1 && c.channels != 3 && c.channels != 4) || c.row_stride < (int64_t)c.width * c.channels) {
             synseg_set_error("synseg_hints_crops: bad crop %d", i); return SYNSEG_E_INVALID;
+        }
+        if (c.channels == 4) {
+            has_rgbx = true;
+            if ((((uintptr_t)base + c.offset) | (uint64_t)c.row_stride) & 3) { synseg_set_error("synseg_hints_crops: RGBX crop %d is not 4-byte aligned", i); return SYNSEG_E_INVALID; }
         }
         if (c.width > mw) mw = c.width;
         if (c.height > mh) mh = c.height;
@@ -306,6 +311,7 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
     if (kw >= 1 && kh >= 1 && 2 * (kw - 1) + 1 <= 226 && 2 * (kh - 1) + 1 <= 384 && !getenv("SYNSEG_HINTS_PER_CROP"))
         return hints_crops_ragged(ctx, base, crops_host, n, kw, kh, out, st);
     // per-image structuring elements (kw / kh <= 0: the chart rule max(20, W / 20)) or very long ones: crop by crop
+    if (has_rgbx) { synseg_set_error("synseg_hints_crops: RGBX crops need fixed structuring elements (1 <= kw <= 113, 1 <= kh <= 192)"); return SYNSEG_E_INVALID; }
     SS_TRY(arena_ensure(ctx, grid_counts_scratch(mw, mh)));
     SS_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t) * 8 * (size_t)n, st));
     for (int i = 0; i < n; ++i) {

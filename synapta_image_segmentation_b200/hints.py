@@ -22,6 +22,11 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 import torch
 
+try:                                   # Pillow >= 11.2 exports its pixel storage through the Arrow C data interface
+    import pyarrow as _pa
+except Exception:                      # pragma: no cover
+    _pa = None
+
 from .datamodel import ChartSpecificData, DiagramSpecificData, FigureSpecificData, ImageSpecificData, OCRResult
 from .detector import get_context
 from .ops import CLOSE, GRAY_CV, GRAY_PIL, OPEN, Context  # noqa: F401
@@ -330,29 +335,49 @@ class FeatureHints:
 
     # ---- batched form for many crops (config 4) -----------------------------------------------------
     @staticmethod
+    def crop_view(image):
+        """PIL image or uint8 array -> (2-D uint8 view [height, width * channels], width, height, channels, keep-alive).
+        PIL 'RGB' and 'L' images are handed over WITHOUT conversion through Pillow's Arrow export (zero copy): RGB
+        storage is 4 bytes per pixel (RGBX), which `synseg_hints_crops` reads directly (channels = 4).  Images Pillow
+        cannot export that way (multi-block storage of very large images, other modes) go through np.asarray."""
+        if isinstance(image, np.ndarray):
+            if image.dtype != np.uint8 or image.ndim not in (2, 3) or (image.ndim == 3 and image.shape[2] not in (3, 4)):
+                raise ValueError("crops must be uint8 [H, W], [H, W, 3] or [H, W, 4] arrays or PIL images")
+            ch = 1 if image.ndim == 2 else image.shape[2]
+            h, w = image.shape[0], image.shape[1]
+            return image.reshape(h, w * ch), w, h, ch, image
+        if image.mode not in ("RGB", "L"):
+            image = image.convert("RGB")
+        w, h = image.size
+        ch = 1 if image.mode == "L" else 4
+        image.load()                           # lazily opened files; memory-mapped / buffer-backed images stay read-only
+        if _pa is not None and hasattr(image, "__arrow_c_array__") and not image.readonly:   # (Pillow 12.2 crashes exporting those)
+            try:
+                arr = _pa.array(image)
+                flat = (arr.flatten() if ch == 4 else arr).to_numpy(zero_copy_only=True)
+                if flat.size == h * w * ch:
+                    return flat.reshape(h, w * ch), w, h, ch, (arr, image)
+            except Exception:
+                pass
+        a = np.asarray(image)
+        ch = 1 if a.ndim == 2 else 3
+        return a.reshape(h, w * ch), w, h, ch, a
+
+    @staticmethod
     def pack_crops(crops):
-        """PIL images (or HxW / HxWx3 uint8 arrays) -> (pinned uint8 buffer, [(offset, width, height, row_stride, channels)]):
-        the packed layout `synseg_hints_crops` reads, rows padded to 16 bytes."""
-        arrays, descs, off = [], [], 0
-        for image in crops:
-            if isinstance(image, np.ndarray):
-                a = image
-                ch = 1 if a.ndim == 2 else 3
-            elif image.mode == "L":
-                a, ch = np.asarray(image), 1
-            else:
-                a, ch = np.asarray(image if image.mode == "RGB" else image.convert("RGB")), 3
-            h, w = a.shape[0], a.shape[1]
+        """Crops -> (pinned uint8 buffer, [(offset, width, height, row_stride, channels)]): the packed layout
+        `synseg_hints_crops` reads, rows padded to 16 bytes.  One buffer for the whole list (see `hints_batch` for the
+        streamed form)."""
+        views = [FeatureHints.crop_view(c) for c in crops]
+        descs, off = [], 0
+        for v, w, h, ch, _ in views:
             rs = (w * ch + 15) // 16 * 16
             descs.append((off, w, h, rs, ch))
-            arrays.append(a)
             off += rs * h
         if not descs:
             return None, []
-        host = torch.empty(off, dtype=torch.uint8).pin_memory()
-        hv = host.numpy()
-        for a, (o, w, h, rs, ch) in zip(arrays, descs):
-            hv[o:o + rs * h].reshape(h, rs)[:, :w * ch] = a.reshape(h, w * ch)
+        host = torch.empty(off, dtype=torch.uint8, pin_memory=True)
+        _copy_views(host.numpy(), views, descs)
         return host, descs
 
     @staticmethod
@@ -360,16 +385,36 @@ class FeatureHints:
         """One dict per crop with the deterministic GPU hint quantities: h_count, v_count, edge_px,
         grid_detected, variance, mask_px, data_points_fallback, image_subtype_visual.
 
-        All crops are packed into ONE pinned host buffer (rows padded to 16 bytes), copied to the device once,
-        processed by one `synseg_hints_crops` call (no host synchronisation between crops) and read back once."""
+        Streamed: the crops are cut into chunks of <= 256 MB; a chunk is copied (thread pool, no pixel conversion for
+        PIL images) into one of two persistent pinned slots, sent to the device and processed by one
+        `synseg_hints_crops` call while the host fills the other slot; results come back once at the end."""
         ctx = get_context()
-        host, descs = FeatureHints.pack_crops(crops)
-        if not descs:
+        views = [FeatureHints.crop_view(c) for c in crops]
+        if not views:
             return []
-        dev = host.to(ctx.device, non_blocking=True)
-        res = ctx.hints_crops(dev, descs).cpu().numpy()
+        stager = _stager(ctx)
+        chunks, cur, off = [], [], 0
+        for v, w, h, ch, _ in views:
+            rs = (w * ch + 15) // 16 * 16
+            if cur and off + rs * h > stager.slot_bytes:
+                chunks.append((cur, off))
+                cur, off = [], 0
+            cur.append((off, w, h, rs, ch))
+            off += rs * h
+        chunks.append((cur, off))
+        results, first = [], 0
+        for k, (descs, nbytes) in enumerate(chunks):
+            host, dev, ev = stager.slot(k, nbytes)
+            if ev is not None:
+                ev.synchronize()                       # the copy that last read this pinned slot has finished
+            _copy_views(host.numpy(), views[first:first + len(descs)], descs, stager.pool)
+            dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
+            stager.mark(k)
+            results.append(ctx.hints_crops(dev[:nbytes], descs))
+            first += len(descs)
+        res = torch.cat(results).cpu().numpy()
         out = []
-        for (o, w, h, rs, ch), r in zip(descs, res):
+        for (v, w, h, ch, _), r in zip(views, res):
             n = w * h
             s1, s2 = int(r[3]), int(r[4])
             var = (n * s2 - s1 * s1) / (n * n)
@@ -377,3 +422,55 @@ class FeatureHints:
                             variance=var, mask_px=int(r[6]), data_points_fallback=min(int(r[2]) // 150, 500),
                             image_subtype_visual="photo" if var > 1500 else "illustration"))
         return out
+
+
+def _copy_views(hv: np.ndarray, views, descs, pool=None) -> None:
+    """Copies every crop view into its place of the packed buffer (numpy releases the GIL for these copies)."""
+    def one(i):
+        v = views[i][0]
+        o, w, h, rs, ch = descs[i]
+        hv[o:o + rs * h].reshape(h, rs)[:, :w * ch] = v
+    if pool is None or len(descs) < 4:
+        for i in range(len(descs)):
+            one(i)
+    else:
+        list(pool.map(one, range(len(descs)), chunksize=max(1, len(descs) // (4 * pool._max_workers))))
+
+
+class _CropStager:
+    """Two persistent pinned slots + device buffers for `hints_batch` (no allocation in the steady state)."""
+
+    def __init__(self, ctx: Context, slot_bytes: int = 256 << 20):
+        import concurrent.futures as cf
+        import os
+        self.device = ctx.device
+        self.slot_bytes = slot_bytes
+        self.host = [None, None]
+        self.dev = [None, None]
+        self.events = [None, None]
+        self.pool = cf.ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)))
+
+    def slot(self, k: int, nbytes: int):
+        s = k & 1
+        if self.host[s] is None or self.host[s].numel() < nbytes:
+            n = max(nbytes, self.slot_bytes)
+            if self.events[s] is not None:
+                self.events[s].synchronize()
+            self.host[s] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            self.dev[s] = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self.host[s], self.dev[s], self.events[s]
+
+    def mark(self, k: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k & 1] = ev
+
+
+_STAGERS: Dict[int, "_CropStager"] = {}
+
+
+def _stager(ctx: Context) -> _CropStager:
+    st = _STAGERS.get(id(ctx))
+    if st is None:
+        st = _STAGERS[id(ctx)] = _CropStager(ctx)
+    return st

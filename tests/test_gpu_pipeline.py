@@ -231,10 +231,11 @@ def test_ragged_crop_batch_chunks_and_tiny_crops(ctx, monkeypatch):
     images = [Image.fromarray(c) for c in crops]
     keys = ("h_count", "v_count", "edge_px", "mask_px", "variance")
     want = [cv2_chain.crop_features(c) for c in crops]
-    for env in ({}, {"SYNSEG_RAGGED_CHUNK": "3"}, {"SYNSEG_HINTS_PER_CROP": "1"}):
+    # PIL images travel as RGBX (Pillow's own storage, no repacking), arrays as RGB; the crop-by-crop path takes RGB only
+    for env, batch in (({}, images), ({}, crops), ({"SYNSEG_RAGGED_CHUNK": "3"}, images), ({"SYNSEG_HINTS_PER_CROP": "1"}, crops)):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        got = FeatureHints.hints_batch(images)
+        got = FeatureHints.hints_batch(batch)
         for k in env:
             monkeypatch.delenv(k)
         for c, g, w_ in zip(crops, got, want):
