@@ -221,6 +221,19 @@ typedef struct synseg_crop {
 int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
                        uint64_t *out, void *stream);
 
+/* Batched dominant colours of a ragged batch of crops (the batched form of OCRProcessor._extract_dominant_colors,
+ * S:1566-1594; BASELINE.json configs[3]).  Exact: the HSV mask S > 30 & V > 40 & V < 240 (S:1571-1574), the masked
+ * pixel count and the `fewer than min_pixels -> no colours` decision (S:1577, min_pixels = 100).  The clustering is a
+ * deterministic APPROXIMATION of the reference's KMeans over an unseeded random sample (S:1581-1590): exact 4096-bin
+ * (R>>4, G>>4, B>>4) histogram with per-bin channel sums, weighted Lloyd iterations over the bin centroids started
+ * from the heaviest bins (arithmetic spelled out in csrc/colors.cu; bit-identical CPU restatement: oracle/colors_port.py).
+ * out[(2 + n_colors) * i ..] = { mask_px, k, (cluster pixels << 24 | R << 16 | G << 8 | B) for the k <= n_colors
+ * centres (truncated like `.astype(int)`, S:1591), 0 ... }.  hist_out (optional) receives uint32[4096] per crop.
+ * Grey crops (channels 1) have no saturated pixel: mask_px = 0, k = 0.  1 <= n_colors <= 8; a crop holds <= 2^24 pixels.
+ * crops_host is a HOST array; everything is queued on `stream` without synchronising. */
+int synseg_colors_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int32_t n_colors,
+                        int32_t iters, int32_t min_pixels, uint64_t *out, uint32_t *hist_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

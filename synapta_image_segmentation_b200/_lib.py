@@ -60,6 +60,7 @@ SIGNATURES = {
     "synseg_detect_pages_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P(DetectParams), C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_hints_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "synseg_colors_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),
 }
 

@@ -11,6 +11,13 @@
 
 #define SYNSEG_EXPORT __attribute__((visibility("default")))
 
+#ifndef SYNSEG_FORK_DEFAULT
+#define SYNSEG_FORK_DEFAULT 0
+#endif
+#ifndef SYNSEG_OVERLAP_DEFAULT
+#define SYNSEG_OVERLAP_DEFAULT 1
+#endif
+
 #ifndef __CUDA_ARCH__
 #define SYNSEG_HOST 1
 #endif
@@ -28,6 +35,16 @@ struct synseg_ctx {
     int32_t *phash_basis; // device int32[8*32]
     int tune_ad_band;     // experiment knobs (env SYNSEG_TUNE_AD_BAND / SYNSEG_TUNE_CANNY_BAND), 0 = automatic
     int tune_canny_band;
+    // Stage overlap inside synseg_detect_pages (pipeline.cu): side streams owned by the context, forked from and joined
+    // back into the caller's stream with events, so the call stays asynchronous on the caller's stream.
+    int overlap;                            // env SYNSEG_OVERLAP: page chunks per call, alternating between the caller's stream and a side stream (1 = one chain)
+    int fork;                               // env SYNSEG_FORK: 1 = Canny + hysteresis unions on a high-priority side stream beside the threshold
+    cudaStream_t aux;                       // side stream of the odd chunks (created on first use)
+    cudaStream_t aux_hi[2];                 // high-priority side streams of the two chains
+    cudaEvent_t ev_split_fork, ev_split_join, ev_fork[2], ev_join[2];
+    cudaStream_t hyst_final_stream;         // with hyst_join set, run_hysteresis launches its last kernel on this stream
+    cudaEvent_t hyst_join_event;            //   after joining the unions' stream through this event
+    bool hyst_join;
     // host-buffer streaming (synseg_detect_pages_host): device staging ring + copy stream, created on first use
     struct HostStream {
         cudaStream_t copy;                 // H2D stream

@@ -34,25 +34,31 @@ static size_t detect_scratch_bytes(int W, int H, int B, int max_labels, bool nee
     return gray + bits + (canny > ccl ? canny : ccl) + 4096;
 }
 
-extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
-                                   int32_t *n_labels, int32_t *stats, double *centroids, void *stream)
+static int overlap_streams(synseg_ctx *ctx)
 {
-    if (!ctx || !prm) { synseg_set_error("synseg_detect_pages: NULL ctx/params"); return SYNSEG_E_INVALID; }
-    SS_TRY(validate_img(rgb, "rgb", 3));
-    if (gray_out) {
-        SS_TRY(validate_img(gray_out, "gray_out", 1));
-        if (!same_shape(rgb, gray_out)) { synseg_set_error("synseg_detect_pages: gray_out shape mismatch"); return SYNSEG_E_INVALID; }
+    if (ctx->aux) return SYNSEG_OK;
+    int lo = 0, hi = 0;
+    SS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // numerically lower = higher priority
+    for (int i = 0; i < 2; ++i) {
+        SS_CUDA(cudaStreamCreateWithPriority(&ctx->aux_hi[i], cudaStreamNonBlocking, hi));
+        SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
-    if (!n_labels || !stats || !centroids) { synseg_set_error("synseg_detect_pages: NULL result buffer"); return SYNSEG_E_INVALID; }
-    if (prm->block_size < 3 || prm->block_size > 255 || !(prm->block_size & 1) || prm->k < 1 || prm->max_labels < 1 || prm->canny_lo < 0 ||
-        prm->canny_hi < prm->canny_lo) {
-        synseg_set_error("synseg_detect_pages: bad parameters"); return SYNSEG_E_INVALID;
-    }
+    SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_split_fork, cudaEventDisableTiming));
+    SS_CUDA(cudaEventCreateWithFlags(&ctx->ev_split_join, cudaEventDisableTiming));
+    SS_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, lo));
+    return SYNSEG_OK;
+}
+
+// One chain over the pages of `rgb` on stream `st`, scratch from the arena at `arena_base`.
+// fork_lane >= 0: the Canny class kernel and the hysteresis unions run on the context's high-priority side stream
+// `fork_lane` beside the adaptive threshold (issue-bound stencil next to latency-bound union-find); the kernel that ORs
+// the edges into the threshold plane joins both on `st`.
+static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
+                        int32_t *n_labels, int32_t *stats, double *centroids, cudaStream_t st, size_t arena_base, int fork_lane)
+{
     const int W = rgb->width, H = rgb->height, B = rgb->batch;
-    if (W > 32766 || H > 32766 || B > 65535) { synseg_set_error("synseg_detect_pages: image or batch too large"); return SYNSEG_E_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
-    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(W, H, B, prm->max_labels, gray_out == nullptr)));
-    arena_begin(ctx);
+    ctx->arena_top = arena_base;
     void *p;
     synseg_img gray;
     if (gray_out) gray = *gray_out;
@@ -71,9 +77,20 @@ extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_i
     BitPlane other{(uint32_t *)p, wpr, (int64_t)wpr * H};
 
     SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
-    SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
     const size_t mark = arena_mark(ctx);
-    SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
+    if (fork_lane >= 0) {
+        cudaStream_t side = ctx->aux_hi[fork_lane];
+        SS_CUDA(cudaEventRecord(ctx->ev_fork[fork_lane], st));
+        SS_CUDA(cudaStreamWaitEvent(side, ctx->ev_fork[fork_lane], 0));
+        SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
+        ctx->hyst_final_stream = st; ctx->hyst_join_event = ctx->ev_join[fork_lane]; ctx->hyst_join = true;
+        const int rc = run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, side);
+        ctx->hyst_join = false;
+        SS_TRY(rc);
+    } else {
+        SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
+        SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
+    }
     arena_release(ctx, mark);
     // dilate(k) then close(k) = dilate(k), dilate(k), erode(k) = dilate(2k-1, anchor 2*(k/2)), erode(k)
     const int k = prm->k;
@@ -81,6 +98,52 @@ extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_i
     SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_ERODE, k, k, k / 2, k / 2, 1, st));
     CclMask m; m.u8 = nullptr; m.bits = cur; m.width = W; m.height = H; m.batch = B;
     return run_ccl_stats(ctx, m, nullptr, n_labels, stats, centroids, prm->max_labels, st);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
+                                   int32_t *n_labels, int32_t *stats, double *centroids, void *stream)
+{
+    if (!ctx || !prm) { synseg_set_error("synseg_detect_pages: NULL ctx/params"); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(rgb, "rgb", 3));
+    if (gray_out) {
+        SS_TRY(validate_img(gray_out, "gray_out", 1));
+        if (!same_shape(rgb, gray_out)) { synseg_set_error("synseg_detect_pages: gray_out shape mismatch"); return SYNSEG_E_INVALID; }
+    }
+    if (!n_labels || !stats || !centroids) { synseg_set_error("synseg_detect_pages: NULL result buffer"); return SYNSEG_E_INVALID; }
+    if (prm->block_size < 3 || prm->block_size > 255 || !(prm->block_size & 1) || prm->k < 1 || prm->max_labels < 1 || prm->canny_lo < 0 ||
+        prm->canny_hi < prm->canny_lo) {
+        synseg_set_error("synseg_detect_pages: bad parameters"); return SYNSEG_E_INVALID;
+    }
+    const int W = rgb->width, H = rgb->height, B = rgb->batch;
+    if (W > 32766 || H > 32766 || B > 65535) { synseg_set_error("synseg_detect_pages: image or batch too large"); return SYNSEG_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-kernel profiling needs every kernel alone on one stream
+    const int chunks = ctx->prof_on ? 1 : ctx->overlap;
+    const bool fork = !ctx->prof_on && ctx->fork != 0;
+    const int ml = prm->max_labels;
+    if (chunks >= 2 || fork) SS_TRY(overlap_streams(ctx));
+    if (chunks >= 2 && B >= 2 * chunks) {
+        // page chunks alternate between the caller's stream and a side stream, each with its own half of the arena:
+        // the latency-bound labelling of one chunk runs beside the issue- / HBM-bound front end of the next
+        const int per = cdiv(B, chunks);
+        const size_t region = align_up(detect_scratch_bytes(W, H, per, ml, gray_out == nullptr), 256);
+        SS_TRY(arena_ensure(ctx, 2 * region));
+        SS_CUDA(cudaEventRecord(ctx->ev_split_fork, st));
+        SS_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_split_fork, 0));
+        for (int c = 0, p0 = 0; p0 < B; ++c, p0 += per) {
+            const int np = B - p0 < per ? B - p0 : per;
+            synseg_img v = *rgb, g;
+            v.data = (uint8_t *)rgb->data + (int64_t)p0 * rgb->batch_stride; v.batch = np;
+            if (gray_out) { g = *gray_out; g.data = (uint8_t *)gray_out->data + (int64_t)p0 * gray_out->batch_stride; g.batch = np; }
+            SS_TRY(detect_chain(ctx, &v, prm, gray_out ? &g : nullptr, n_labels + p0, stats + (size_t)p0 * ml * 5, centroids + (size_t)p0 * ml * 2,
+                                (c & 1) ? ctx->aux : st, (c & 1) ? region : 0, fork ? (c & 1) : -1));
+        }
+        SS_CUDA(cudaEventRecord(ctx->ev_split_join, ctx->aux));
+        SS_CUDA(cudaStreamWaitEvent(st, ctx->ev_split_join, 0));
+        return SYNSEG_OK;
+    }
+    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(W, H, B, ml, gray_out == nullptr)));
+    return detect_chain(ctx, rgb, prm, gray_out, n_labels, stats, centroids, st, 0, fork ? 0 : -1);
 }
 
 // grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2) -> counts of ONE image (view->batch == 1).

@@ -180,32 +180,23 @@ class FeatureHints:
             return []
 
     @staticmethod
+    def decode_colors(row) -> Dict[str, Any]:
+        """One row of `Context.colors_crops` -> dict(mask_px, dominant_colors ['#rrggbb'], color_weights [pixels])."""
+        k = int(row[1])
+        words = [int(v) for v in row[2:2 + k]]
+        return dict(mask_px=int(row[0]), dominant_colors=["#%06x" % (v & 0xFFFFFF) for v in words],
+                    color_weights=[v >> 24 for v in words])
+
+    @staticmethod
     def dominant_colors_histogram(image, n_colors: int = 5, iters: int = 20) -> List[str]:
-        """Deterministic GPU-histogram variant (an APPROXIMATION of the reference's KMeans, labelled as such):
-        weighted k-means over the exact centroids of the 4096 (R>>4,G>>4,B>>4) bins, initialised with the
-        heaviest bins.  No sampling, no randomness."""
+        """Deterministic GPU-histogram variant (an APPROXIMATION of the reference's KMeans over an unseeded random
+        sample, pdf_image_segmentation.py:1581-1590, labelled as such): weighted Lloyd iterations over the exact
+        centroids of the 4096 (R>>4,G>>4,B>>4) bins, started from the heaviest bins, all on the device
+        (`synseg_colors_crops`).  The mask and the `fewer than 100 masked pixels -> []` decision (:1571-1577) are exact."""
         ctx = get_context()
-        if image.mode != "RGB":
-            image = image.convert("RGB")
-        t = torch.from_numpy(np.array(image)).to(ctx.device)
-        res = ctx.hsv_mask_hist(t, None, want_hist=True, want_sums=True)
-        if int(res["count"][0]) < 100:
-            return []
-        hist = res["hist"][0].cpu().numpy().astype(np.float64)
-        sums = res["chan_sum"][0].cpu().numpy().astype(np.float64)
-        nz = hist > 0
-        w = hist[nz]
-        pts = sums[nz] / w[:, None]
-        k = min(n_colors, len(w))
-        centres = pts[np.argsort(-w)[:k]].copy()
-        for _ in range(iters):
-            d = ((pts[:, None, :] - centres[None, :, :]) ** 2).sum(-1)
-            a = d.argmin(1)
-            for j in range(k):
-                m = a == j
-                if m.any():
-                    centres[j] = (pts[m] * w[m, None]).sum(0) / w[m].sum()
-        return ["#%02x%02x%02x" % tuple(c) for c in centres.astype(int)]
+        host, descs = FeatureHints.pack_crops([image])
+        out, _ = ctx.colors_crops(host.to(ctx.device, non_blocking=True), descs, n_colors, iters)
+        return FeatureHints.decode_colors(out[0].cpu().numpy())["dominant_colors"]
 
     @staticmethod
     def _detect_image_subtype(image, ocr_result: Optional[OCRResult]) -> Optional[str]:
@@ -383,7 +374,8 @@ class FeatureHints:
     @staticmethod
     def hints_batch(crops) -> List[Dict[str, Any]]:
         """One dict per crop with the deterministic GPU hint quantities: h_count, v_count, edge_px,
-        grid_detected, variance, mask_px, data_points_fallback, image_subtype_visual.
+        grid_detected, variance, mask_px, data_points_fallback, image_subtype_visual, dominant_colors
+        (deterministic histogram clustering, see `dominant_colors_histogram`) and color_weights.
 
         Streamed: the crops are cut into chunks of <= 256 MB; a chunk is copied (thread pool, no pixel conversion for
         PIL images) into one of two persistent pinned slots, sent to the device and processed by one
@@ -402,7 +394,7 @@ class FeatureHints:
             cur.append((off, w, h, rs, ch))
             off += rs * h
         chunks.append((cur, off))
-        results, first = [], 0
+        results, colours, first = [], [], 0
         for k, (descs, nbytes) in enumerate(chunks):
             host, dev, ev = stager.slot(k, nbytes)
             if ev is not None:
@@ -411,16 +403,20 @@ class FeatureHints:
             dev[:nbytes].copy_(host[:nbytes], non_blocking=True)
             stager.mark(k)
             results.append(ctx.hints_crops(dev[:nbytes], descs))
+            colours.append(ctx.colors_crops(dev[:nbytes], descs)[0])
             first += len(descs)
         res = torch.cat(results).cpu().numpy()
+        col = torch.cat(colours).cpu().numpy()
         out = []
-        for (v, w, h, ch, _), r in zip(views, res):
+        for (v, w, h, ch, _), r, cr in zip(views, res, col):
             n = w * h
             s1, s2 = int(r[3]), int(r[4])
             var = (n * s2 - s1 * s1) / (n * n)
             out.append(dict(h_count=int(r[0]), v_count=int(r[1]), edge_px=int(r[2]), grid_detected=bool(r[0] > 300 and r[1] > 300),
                             variance=var, mask_px=int(r[6]), data_points_fallback=min(int(r[2]) // 150, 500),
                             image_subtype_visual="photo" if var > 1500 else "illustration"))
+            c = FeatureHints.decode_colors(cr)
+            out[-1].update(dominant_colors=c["dominant_colors"], color_weights=c["color_weights"])
         return out
 
 

@@ -321,6 +321,33 @@ class Context:
               "synseg_hints_crops")
         return out
 
+    def _crop_array(self, packed: torch.Tensor, crops):
+        if not packed.is_cuda or packed.dtype != torch.uint8 or not packed.is_contiguous():
+            raise ValueError("packed must be a contiguous CUDA uint8 tensor")
+        n = len(crops)
+        arr = (Crop * n)()
+        total = packed.numel()
+        for i, (off, w, h, rs, ch) in enumerate(crops):
+            if off < 0 or w <= 0 or h <= 0 or rs < w * ch or off + rs * (h - 1) + w * ch > total:
+                raise ValueError(f"crop {i} lies outside the packed buffer")
+            arr[i] = Crop(int(off), int(w), int(h), int(rs), int(ch), 0)
+        return arr
+
+    def colors_crops(self, packed: torch.Tensor, crops, n_colors: int = 5, iters: int = 20, min_pixels: int = 100,
+                     want_hist: bool = False):
+        """Dominant colours of a ragged batch of crops (see synseg_colors_crops).  crops as for `hints_crops`.
+        Returns (int64 [n, 2 + n_colors] = mask_px, k, (cluster pixels << 24 | R << 16 | G << 8 | B) x k; hist int32 [n, 4096] | None)."""
+        n = len(crops)
+        out = torch.empty((n, 2 + n_colors), dtype=torch.int64, device=packed.device)
+        hist = torch.empty((n, HIST_BINS), dtype=torch.int32, device=packed.device) if want_hist else None
+        if n == 0:
+            return out, hist
+        arr = self._crop_array(packed, crops)
+        check(self.lib.synseg_colors_crops(self._h, C.c_void_p(packed.data_ptr()), arr, n, n_colors, iters, min_pixels,
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(hist.data_ptr()) if hist is not None else None, _stream()),
+              "synseg_colors_crops")
+        return out, hist
+
     def grid_counts(self, src: torch.Tensor, rois=None, gray_mode: int = GRAY_PIL, kw: int = 25, kh: int = 25,
                     want_edges: bool = False, channels: Optional[int] = None):
         """Per region (h_count, v_count, edge_px) int64 [n,3] (+ edges u8 [n,maxH,maxW] when want_edges)."""

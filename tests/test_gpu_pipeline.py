@@ -243,6 +243,83 @@ def test_ragged_crop_batch_chunks_and_tiny_crops(ctx, monkeypatch):
             assert abs(g["variance"] - w_["variance"]) <= 1e-9 * max(1.0, w_["variance"]), (env, c.shape)
 
 
+def _colour_crops():
+    from synapta_image_segmentation_b200.synth import render_figure
+    crops = []
+    flat = np.full((120, 200, 3), 255, np.uint8)                      # three flat, well separated colours on white
+    flat[10:60, 10:90] = (200, 30, 40); flat[70:110, 20:180] = (30, 160, 60); flat[10:60, 100:190] = (40, 60, 210)
+    crops.append(flat)
+    for i, (h, w) in enumerate([(67, 70), (191, 310), (464, 799), (1500, 1191), (33, 517), (1, 1), (9, 11)]):
+        crops.append(np.ascontiguousarray(render_figure([9, i], 150, max(h, 40), max(w, 40))[:h, :w]))
+    for i, (h, w) in enumerate([(64, 64), (130, 481), (301, 257)]):
+        crops.append(imgs.rgb_noise(h, w, 700 + i))                   # thousands of occupied bins
+    few = np.full((40, 40, 3), 128, np.uint8); few[0, :39] = (220, 20, 20); few[1:3, :30] = (220, 20, 20)
+    crops.append(few)                                                 # 60 + 39 = 99 masked pixels: below the threshold
+    few2 = few.copy(); few2[5, 0] = (20, 20, 220)
+    crops.append(few2)                                                # exactly 100: two colours
+    crops.append(imgs.shapes(90, 120, 5))                             # grey (mode L): nothing saturated
+    for name in sorted(os.listdir(GOLD)):
+        if name.endswith(".png"):
+            crops.append(np.array(Image.open(os.path.join(GOLD, name))))  # real crops of the reference's run (RGB and L)
+    return crops
+
+
+def test_colors_crops_bit_exact_vs_port(ctx):
+    """synseg_colors_crops (config 4): masked-pixel count, the `[]` decision, the 4096-bin histogram and
+    the deterministic clustering are bit-identical with oracle/colors_port.py (cv2's HSV mask + numpy float64), for
+    RGB arrays, RGBX (PIL storage) and grey crops, one launch for the ragged batch."""
+    from oracle import colors_port
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    crops = _colour_crops()
+    want = [colors_port.dominant_colors_hist(c) for c in crops]
+    for batch in (crops, [Image.fromarray(c) for c in crops]):
+        host, descs = FeatureHints.pack_crops(batch)
+        out, hist = ctx.colors_crops(host.cuda(), descs, want_hist=True)
+        out, hist = out.cpu().numpy(), hist.cpu().numpy()
+        for i, (c, (n, cols, wts)) in enumerate(zip(crops, want)):
+            g = FeatureHints.decode_colors(out[i])
+            assert g["mask_px"] == n, (i, c.shape)
+            assert g["dominant_colors"] == ["#%02x%02x%02x" % t for t in cols], (i, c.shape, g, cols)
+            assert g["color_weights"] == wts, (i, c.shape)
+            if c.ndim == 3:
+                assert np.array_equal(hist[i].astype(np.int64), colors_port.masked_histogram(c)[1]), (i, c.shape)
+            else:
+                assert not hist[i].any()
+    # the decisions at the reference's threshold (S:1577) and the flat-colour case
+    assert want[0][1] == [(30, 160, 60), (40, 60, 210), (200, 30, 40)] and want[0][2] == [6400, 4500, 4000]
+    assert [w[0] for w in want if w[0] in (99, 100)] == [99, 100]
+    assert [len(w[1]) for w in want if w[0] in (99, 100)] == [0, 2]
+    # other n_colors / iteration counts
+    host, descs = FeatureHints.pack_crops(crops[:6])
+    for nc, it in ((1, 20), (3, 0), (8, 5)):
+        out, _ = ctx.colors_crops(host.cuda(), descs, n_colors=nc, iters=it)
+        for row, c in zip(out.cpu().numpy(), crops[:6]):
+            n, cols, wts = colors_port.dominant_colors_hist(c, nc, it)
+            g = FeatureHints.decode_colors(row)
+            assert (g["mask_px"], g["dominant_colors"], g["color_weights"]) == (n, ["#%02x%02x%02x" % t for t in cols], wts), (nc, it, c.shape)
+
+
+def test_colors_histogram_clustering_close_to_reference_kmeans(ctx):
+    """The deterministic clustering is an approximation of the reference's KMeans (S:1581-1590); on flat, well
+    separated colours both must land on the same centres (sets, within 1 LSB per channel: KMeans runs in float on a
+    seeded 5000-pixel sample)."""
+    from sklearn.cluster import KMeans
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    crop = _colour_crops()[0]
+    got = FeatureHints.dominant_colors_histogram(Image.fromarray(crop), n_colors=3)
+    px = crop[cv2_chain.hsv_mask(crop)].reshape(-1, 3)
+    np.random.seed(7)
+    px = px[np.random.choice(len(px), 5000, replace=False)]
+    ref = KMeans(n_clusters=3, random_state=42, n_init=10).fit(px).cluster_centers_.astype(int)
+    got_rgb = sorted(tuple(int(h[i:i + 2], 16) for i in (1, 3, 5)) for h in got)
+    for a, b in zip(got_rgb, sorted(tuple(int(v) for v in r) for r in ref)):
+        assert max(abs(x - y) for x, y in zip(a, b)) <= 1, (got_rgb, ref)
+    # the batched form carries the same lists
+    res = FeatureHints.hints_batch([Image.fromarray(crop), Image.fromarray(imgs.shapes(90, 120, 5))])
+    assert res[0]["dominant_colors"][:3] == FeatureHints.dominant_colors_histogram(Image.fromarray(crop))[:3]
+    assert res[1]["dominant_colors"] == [] and res[1]["mask_px"] == 0
+
+
 def test_pipeline_edge_cases(ctx):
     """Blank page (background only), all-ink page (one component; cv2 reports an empty background row), 1x1 and
     1-row / 1-column pages, label overflow (n_labels = -(required)), and a ragged last batch through the streamer."""

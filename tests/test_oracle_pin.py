@@ -176,3 +176,35 @@ def test_golden_reference_helpers_match_oracle_chain():
         assert abs(oracle.variance_from_moments(g.size, s, ss) - rec["variance"]) < 1e-9 * max(1.0, rec["variance"])
         if img.ndim == 3:
             assert oracle.hsv_mask(img)[1] == rec["mask_px"]
+
+
+def test_colors_port_pinned_on_reference_outputs():
+    """oracle/colors_port.py vs the imported reference's `_extract_dominant_colors` on the committed crops: the masked
+    pixel count and the `[]` decision (pdf_image_segmentation.py:1574-1577) are identical; the colour lists themselves
+    are a different (deterministic) clustering and are only required to be as long as the reference's."""
+    from oracle import colors_port
+    gold = _golden()
+    for name, rec in gold["crops"].items():
+        img = np.array(Image.open(os.path.join(GOLD, name)))
+        n, cols, wts = colors_port.dominant_colors_hist(img)
+        assert n == rec["mask_px"], name
+        assert (len(cols) == 0) == (len(rec["dominant_colors_seed7"]) == 0), name
+        assert len(cols) == len(rec["dominant_colors_seed7"]), name
+        assert sum(wts) == (n if cols else 0), name
+        if img.ndim == 3:
+            _, hist, sums = colors_port.masked_histogram(img)
+            n_c, hist_c, sums_c = oracle.hsv_hist(img, 4)          # the plain-C restatement of the histogram
+            assert n_c == n and np.array_equal(hist_c.astype(np.int64), hist) and np.array_equal(sums_c.astype(np.int64), sums), name
+
+
+def test_colors_port_known_answers():
+    from oracle import colors_port
+    flat = np.full((120, 200, 3), 255, np.uint8)
+    flat[10:60, 10:90] = (200, 30, 40); flat[70:110, 20:180] = (30, 160, 60); flat[10:60, 100:190] = (40, 60, 210)
+    assert colors_port.dominant_colors_hist(flat) == (14900, [(30, 160, 60), (40, 60, 210), (200, 30, 40)], [6400, 4500, 4000])
+    assert colors_port.dominant_colors_hist(flat, n_colors=1) == (14900, [(78, 94, 99)], [14900])
+    few = np.full((40, 40, 3), 128, np.uint8); few[0, :39] = (220, 20, 20); few[1:3, :30] = (220, 20, 20)
+    assert colors_port.dominant_colors_hist(few) == (99, [], [])
+    few[5, 0] = (20, 20, 220)
+    assert colors_port.dominant_colors_hist(few) == (100, [(220, 20, 20), (20, 20, 220)], [99, 1])
+    assert colors_port.dominant_colors_hist(np.zeros((30, 30), np.uint8)) == (0, [], [])

@@ -76,6 +76,10 @@ def main():
     for name, ms in ctx.profile_end():
         per_kernel[name] = per_kernel.get(name, 0.0) + ms
     per_kernel = {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+    # dominant colours of the same packed batch (synseg_colors_crops: one CTA per crop, histogram + clustering on chip)
+    ctx.colors_crops(dev, descs)
+    ms_col = timed_events(lambda: ctx.colors_crops(dev, descs))
+    col = ctx.colors_crops(dev, descs)[0].cpu().numpy()
     m = min(n, 200)
     host3, descs3 = FeatureHints.pack_crops([np.asarray(c) for c in crops[:m]])      # the crop-by-crop path reads RGB only
     dev3 = host3.to(ctx.device)
@@ -97,6 +101,13 @@ def main():
     ok = all(int(res[i][0]) == ref[i]["h_count"] and int(res[i][1]) == ref[i]["v_count"] and int(res[i][2]) == ref[i]["edge_px"]
              and int(res[i][6]) == ref[i]["mask_px"] for i in range(k))
     same = bool(np.array_equal(res[:m], res_pc))
+    from oracle import colors_port
+    kc = min(n, 12)
+    t0 = time.perf_counter()
+    ref_c = [colors_port.dominant_colors_hist(np.asarray(crops[i])) for i in range(kc)]
+    t_cpu_col = (time.perf_counter() - t0) / kc
+    ok_col = all(FeatureHints.decode_colors(col[i])["dominant_colors"] == ["#%02x%02x%02x" % c for c in ref_c[i][1]]
+                 and int(col[i][0]) == ref_c[i][0] for i in range(kc))
     mpx = sum(h * w for h, w in sizes) / 1e6
     gb = host.numel() / 1e9
     out = dict(n_crops=n, megapixels=round(mpx, 1), packed_gb=round(gb, 3), layout="RGBX" if descs[0][4] == 4 else "RGB",
@@ -106,6 +117,9 @@ def main():
                h2d_ms=round(ms_h2d, 3), h2d_gb_per_s=round(gb / ms_h2d * 1e3, 2),
                one_buffer_pack_s_incl_pinned_alloc=round(t_pack, 3), api_s=round(t_api, 3), api_crops_per_s=round(n / t_api, 1),
                cv2_chain_one_core_ms_per_crop=round(t_cpu * 1e3, 3), cv2_chain_one_core_crops_per_s=round(1 / t_cpu, 1),
+               colors_resident_ms=round(ms_col, 3), colors_crops_per_s=round(n / ms_col * 1e3, 1),
+               colors_gb_per_s=round(gb / ms_col * 1e3, 1), colors_port_one_core_ms_per_crop=round(t_cpu_col * 1e3, 3),
+               colors_parity_vs_port=ok_col,
                parity_vs_cv2_chain=ok, ragged_equals_per_crop_path=same, resident_ms_per_kernel=per_kernel)
     print(json.dumps(out))
     if out_json:
