@@ -7,13 +7,14 @@
 // The mask, the masked-pixel count and the `[]` decision are reproduced exactly.  The clustering is the deterministic
 // histogram form (an APPROXIMATION of the reference's sampled KMeans, labelled as such everywhere): exact 4096-bin
 // (R>>4, G>>4, B>>4) histogram with per-bin channel sums, then weighted Lloyd iterations over the bin centroids,
-// started from the heaviest bins.  No sampling, no randomness; bit-identical with oracle/colors_port.py:
-//   points    p_b = chan_sum_b / count_b                      (IEEE f64 divisions)
+// started from the heaviest bins.  No sampling, no randomness, no floating point (fixed point, Q = 64 = 1/64 of a grey
+// level, so the result does not depend on contraction or summation order); bit-identical with oracle/colors_port.py:
+//   points    p_b = (Q * chan_sum_b + count_b / 2) / count_b          (integer division: bin centroid rounded to 1/64)
 //   start     centres = points of the k heaviest bins (ties: lower bin index first), k = min(n_colors, non-empty bins)
-//   iteration assign every bin to the nearest centre, distance (dr*dr + dg*dg) + db*db in f64 without fused
-//             multiply-add, ties to the lower centre index; centre_j = (integer sum of chan_sum over its bins) /
-//             (integer sum of count) -- empty clusters keep their centre; stop after `iters` rounds or when no
-//             centre moved.
+//   iteration assign every bin to the nearest centre (squared distance in int32, < 2^31; ties to the lower centre index);
+//             centre_j = (sum of count_b * p_b + N_j / 2) / N_j with N_j = sum of count_b over its bins -- empty
+//             clusters keep their centre; stop after `iters` rounds or when no centre moved.
+//   output    centre / Q (truncation, like the reference's `.astype(int)`), cluster pixel counts of the last assignment.
 // One CTA per crop: the histogram lives in shared memory (64 KB: counts + three channel sums) and is filled with
 // warp-aggregated atomics (lanes holding the same bin elect a leader that adds the group's count and channel sums
 // once), so nothing but the crop itself is read from HBM and nothing but the result is written.
@@ -37,20 +38,41 @@ struct ColorSmem {
     uint16_t list[CBINS];         // non-empty bins in ascending order
     uint32_t warp_cnt[CTHREADS / 32];
     u64 red[CTHREADS / 32];
-    double centre[CMAXK][3];
+    int32_t centre[CMAXK][3];     // Q6 fixed point
     u64 acc[CMAXK][4];            // per cluster: count, sum r, sum g, sum b
     u64 picked;
     int n_list, changed;
     u64 total;
 };
 
-__device__ __forceinline__ void add_pixel(ColorSmem &S, bool on, uint32_t rr, uint32_t gg, uint32_t bb, int lane, uint32_t &cnt)
+// Flat colour areas (bars, fills) send the same bin from every lane for thousands of pixels in a row: such warp-uniform
+// groups are accumulated in registers (one open run per warp) and reach shared memory once, when the bin changes or the
+// warp is done -- the shared-memory atomics of 16 warps hammering one address were the bottleneck before.
+struct RunAcc { int bin; uint32_t n, r, g, b; };
+
+__device__ __forceinline__ void flush_run(ColorSmem &S, RunAcc &a, int lane)
+{
+    if (a.bin < 0) return;                                  // warp-uniform
+    const unsigned n = __reduce_add_sync(0xffffffffu, a.n), r = __reduce_add_sync(0xffffffffu, a.r),
+                   g = __reduce_add_sync(0xffffffffu, a.g), b = __reduce_add_sync(0xffffffffu, a.b);
+    if (lane == 0) {
+        atomicAdd(&S.h[a.bin], n);
+        atomicAdd(&S.cs[3 * a.bin], r); atomicAdd(&S.cs[3 * a.bin + 1], g); atomicAdd(&S.cs[3 * a.bin + 2], b);
+    }
+    a.bin = -1; a.n = a.r = a.g = a.b = 0u;
+}
+
+__device__ __forceinline__ void add_pixel(ColorSmem &S, RunAcc &acc, bool on, uint32_t rr, uint32_t gg, uint32_t bb, int lane, uint32_t &cnt)
 {
     const unsigned m = __ballot_sync(0xffffffffu, on);
     if (m == 0u) return;                                   // white / grey / black stretch: nothing to add
     cnt += __popc(m);
-    if (on) {
-        const int bin = ((rr >> 4) << 8) | ((gg >> 4) << 4) | (bb >> 4);
+    const int bin = ((rr >> 4) << 8) | ((gg >> 4) << 4) | (bb >> 4);
+    const int b0 = __shfl_sync(0xffffffffu, bin, __ffs(m) - 1);
+    if (__ballot_sync(0xffffffffu, on && bin != b0) == 0u) {   // one bin for the whole group: extend (or open) the run
+        if (b0 != acc.bin) { flush_run(S, acc, lane); acc.bin = b0; }
+        if (on) { acc.n += 1u; acc.r += rr; acc.g += gg; acc.b += bb; }
+    } else if (on) {                                       // mixed group: lanes holding the same bin elect a leader
         const unsigned peers = __match_any_sync(m, bin);
         const unsigned sr = __reduce_add_sync(peers, rr), sg = __reduce_add_sync(peers, gg), sb = __reduce_add_sync(peers, bb);
         if (lane == __ffs(peers) - 1) {
@@ -100,35 +122,33 @@ __global__ void __launch_bounds__(CTHREADS) crop_colors_kernel(const uint8_t *ba
     if (t.channels >= 3) {
         const uint8_t *src = base + t.offset;
         const int W = t.width;
+        RunAcc acc; acc.bin = -1; acc.n = acc.r = acc.g = acc.b = 0u;
         for (int y = warp; y < t.height; y += CTHREADS / 32) {
             const uint8_t *row = src + (int64_t)y * t.row_stride;
-            if (t.channels == 4) {
-                const uint32_t *wp = (const uint32_t *)row;                 // RGBX words (4-byte aligned by contract)
-                for (int x0 = 0; x0 < W; x0 += 32) {
-                    const int x = x0 + lane;
-                    bool on = false;
-                    uint32_t rr = 0, gg = 0, bb = 0;
+            // four groups of 32 pixels per step: the loads of a step are issued before any of them is consumed
+            for (int x0 = 0; x0 < W; x0 += 128) {
+                uint32_t v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = x0 + 32 * q + lane;
+                    v[q] = 0u;                                       // outside the row: black, never masked in
                     if (x < W) {
-                        const uint32_t v = __ldg(wp + x);
-                        rr = v & 255u; gg = (v >> 8) & 255u; bb = (v >> 16) & 255u;
-                        on = hsv_mask_px(rr, gg, bb, S.sdiv);
+                        if (t.channels == 4) v[q] = __ldg((const uint32_t *)row + x);      // RGBX words (4-byte aligned by contract)
+                        else {
+                            const uint8_t *p = row + 3 * x;
+                            v[q] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+                        }
                     }
-                    add_pixel(S, on, rr, gg, bb, lane, cnt);
                 }
-            } else {
-                for (int x0 = 0; x0 < W; x0 += 32) {
-                    const int x = x0 + lane;
-                    bool on = false;
-                    uint32_t rr = 0, gg = 0, bb = 0;
-                    if (x < W) {
-                        const uint8_t *p = row + 3 * x;
-                        rr = __ldg(p); gg = __ldg(p + 1); bb = __ldg(p + 2);
-                        on = hsv_mask_px(rr, gg, bb, S.sdiv);
-                    }
-                    add_pixel(S, on, rr, gg, bb, lane, cnt);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (x0 + 32 * q >= W) break;                     // warp-uniform
+                    const uint32_t rr = v[q] & 255u, gg = (v[q] >> 8) & 255u, bb = (v[q] >> 16) & 255u;
+                    add_pixel(S, acc, hsv_mask_px(rr, gg, bb, S.sdiv), rr, gg, bb, lane, cnt);
                 }
             }
         }
+        flush_run(S, acc, lane);
     }
     if (lane == 0 && cnt) atomicAdd(&S.total, (u64)cnt);
     __syncthreads();
@@ -159,6 +179,15 @@ __global__ void __launch_bounds__(CTHREADS) crop_colors_kernel(const uint8_t *ba
     const int nb = S.n_list;
     const int k = n_colors < nb ? n_colors : nb;
 
+    // ---- bin centroids in fixed point, in place of the channel sums (the sums are not needed any more) -----------
+    for (int i = threadIdx.x; i < nb; i += CTHREADS) {
+        const int bin = S.list[i];
+        const u64 w = S.h[bin];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S.cs[3 * bin + c] = (uint32_t)((64ull * S.cs[3 * bin + c] + w / 2) / w);
+    }
+    __syncthreads();
+
     // ---- start: the k heaviest bins, ties to the lower bin index (keys are unique) ----------------------------
     u64 below = ~0ull;
     for (int j = 0; j < k; ++j) {
@@ -171,34 +200,56 @@ __global__ void __launch_bounds__(CTHREADS) crop_colors_kernel(const uint8_t *ba
         below = block_max_u64(S, best);
         if (threadIdx.x < 3) {
             const int bin = CBINS - 1 - (int)(below & (CBINS - 1));
-            S.centre[j][threadIdx.x] = (double)S.cs[3 * bin + threadIdx.x] / (double)S.h[bin];
+            S.centre[j][threadIdx.x] = (int32_t)S.cs[3 * bin + threadIdx.x];
         }
     }
     __syncthreads();
 
     // ---- weighted Lloyd iterations over the bin centroids -------------------------------------------------------
+    // A lane owns a bin, lane j of every warp collects cluster j: per cluster the warp reduces the members' count and
+    // count * point (split into 20-bit halves so the 32-lane sums fit 32 bits) with REDUX and lane j keeps the totals
+    // in registers; shared memory sees 4 atomics per warp, cluster and round.
     for (int it = 0; it < iters; ++it) {
         if (threadIdx.x < 4 * CMAXK) ((u64 *)S.acc)[threadIdx.x] = 0ull;
         if (threadIdx.x == 0) S.changed = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += CTHREADS) {
-            const int bin = S.list[i];
-            const uint32_t w = S.h[bin], sr = S.cs[3 * bin], sg = S.cs[3 * bin + 1], sb = S.cs[3 * bin + 2];
-            const double pr = (double)sr / (double)w, pg = (double)sg / (double)w, pb = (double)sb / (double)w;
-            int a = 0;
-            double dbest = 0.0;
-            for (int j = 0; j < k; ++j) {
-                const double dr = __dsub_rn(pr, S.centre[j][0]), dg = __dsub_rn(pg, S.centre[j][1]), db = __dsub_rn(pb, S.centre[j][2]);
-                const double d = __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db));
-                if (j == 0 || d < dbest) { dbest = d; a = j; }
+        u64 myN = 0, myT0 = 0, myT1 = 0, myT2 = 0;
+        for (int i0 = warp * 32; i0 < nb; i0 += CTHREADS) {
+            const int i = i0 + lane;
+            const bool valid = i < nb;
+            uint32_t w = 0;
+            int p0 = 0, p1 = 0, p2 = 0, a = -1;
+            if (valid) {
+                const int bin = S.list[i];
+                w = S.h[bin]; p0 = (int)S.cs[3 * bin]; p1 = (int)S.cs[3 * bin + 1]; p2 = (int)S.cs[3 * bin + 2];
+                int dbest = 0x7fffffff;
+                for (int j = 0; j < k; ++j) {
+                    const int d0 = p0 - S.centre[j][0], d1 = p1 - S.centre[j][1], d2 = p2 - S.centre[j][2];
+                    const int d = d0 * d0 + d1 * d1 + d2 * d2;
+                    if (d < dbest) { dbest = d; a = j; }
+                }
             }
-            atomicAdd(&S.acc[a][0], (u64)w); atomicAdd(&S.acc[a][1], (u64)sr); atomicAdd(&S.acc[a][2], (u64)sg); atomicAdd(&S.acc[a][3], (u64)sb);
+            for (int j = 0; j < k; ++j) {
+                const bool in = a == j;
+                if (__ballot_sync(0xffffffffu, in) == 0u) continue;      // warp-uniform
+                const uint32_t wv = in ? w : 0u;
+                const u64 t0 = (u64)wv * (uint32_t)p0, t1 = (u64)wv * (uint32_t)p1, t2 = (u64)wv * (uint32_t)p2;
+                const uint32_t n = __reduce_add_sync(0xffffffffu, wv);
+                const u64 s0 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t0 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t0 & 0xFFFFFu));
+                const u64 s1 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t1 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t1 & 0xFFFFFu));
+                const u64 s2 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t2 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t2 & 0xFFFFFu));
+                if (lane == j) { myN += n; myT0 += s0; myT1 += s1; myT2 += s2; }
+            }
+        }
+        if (lane < k && myN) {
+            atomicAdd(&S.acc[lane][0], myN); atomicAdd(&S.acc[lane][1], myT0); atomicAdd(&S.acc[lane][2], myT1); atomicAdd(&S.acc[lane][3], myT2);
         }
         __syncthreads();
         if (threadIdx.x < 3 * k) {
             const int j = threadIdx.x / 3, c = threadIdx.x % 3;
-            if (S.acc[j][0]) {
-                const double nc = (double)S.acc[j][1 + c] / (double)S.acc[j][0];
+            const u64 N = S.acc[j][0];
+            if (N) {
+                const int32_t nc = (int32_t)((S.acc[j][1 + c] + N / 2) / N);
                 if (nc != S.centre[j][c]) { S.centre[j][c] = nc; S.changed = 1; }
             }
         }
@@ -209,7 +260,7 @@ __global__ void __launch_bounds__(CTHREADS) crop_colors_kernel(const uint8_t *ba
     }
     if (threadIdx.x < k) {
         const int j = threadIdx.x;
-        const u64 r = (u64)(int)S.centre[j][0], g = (u64)(int)S.centre[j][1], b = (u64)(int)S.centre[j][2];
+        const u64 r = (u64)(S.centre[j][0] >> 6), g = (u64)(S.centre[j][1] >> 6), b = (u64)(S.centre[j][2] >> 6);
         o[2 + j] = (S.acc[j][0] << 24) | (r << 16) | (g << 8) | b;
     }
     if (threadIdx.x == 0) o[1] = (u64)k;

@@ -183,64 +183,74 @@ __global__ void __launch_bounds__(256) crop_front_kernel(const uint8_t *base, co
     const uint8_t *src = base + t.offset;
     uint8_t *dimg = dst.p + (int64_t)blockIdx.y * dst.bs;
     const int W = t.width;
-    unsigned long long s = 0, ss = 0, nz = 0, mk = 0;
-    for (int y = blockIdx.x * 8 + warp; y < t.height; y += gridDim.x * 8) {
+    // The rows of this warp (y_first, y_first + ystep, ...) are cut into groups of 16 pixels and the (row, group) pairs
+    // are dealt out to the lanes as ONE sequence: a 699-pixel row has 44 groups, which would fill 32 + 12 lanes row by
+    // row, but four such rows fill 5.5 rounds of 32 lanes.  The partial last group of a row runs in the same round as
+    // the full groups of its neighbours: only its loads differ (pixel by pixel, nothing beyond column W-1 is touched;
+    // pixels outside the row enter as black: grey 0, not masked in, nothing added to the moments).
+    const int G = (W + 15) >> 4;
+    const int ystep = gridDim.x * 8, y_first = blockIdx.x * 8 + warp;
+    const int nrows = y_first < t.height ? (t.height - 1 - y_first) / ystep + 1 : 0;
+    const int total = nrows * G;
+    int r = 0, gi = lane;
+    while (gi >= G) { gi -= G; ++r; }
+    uint32_t rs = 0, rss = 0, rnz = 0, rmk = 0;     // per lane: <= (4 rows * 2048 groups / 32 + 1) * 16 px * 65025 fits 32 bits
+    for (int q = lane; q < total; q += 32) {
+        const int y = y_first + r * ystep, x0 = gi << 4;
         const uint8_t *srow = src + (int64_t)y * t.row_stride;
         uint8_t *drow = dimg + (int64_t)y * dst.rs;
-        uint32_t rs = 0, rss = 0, rnz = 0, rmk = 0;                  // per lane and row: <= 65025 * 16 * 64 fits 32 bits
-        for (int x0 = 16 * lane; x0 < W; x0 += 512) {
-            uint4 o;
-            if (x0 + 16 <= W) {
-                if (t.channels == 3) {
-                    uint32_t v[12];
-                    load48(srow + 3 * (int64_t)x0, v);
-                    o.x = gray_mask4(v[0], v[1], v[2], sdiv, rmk); o.y = gray_mask4(v[3], v[4], v[5], sdiv, rmk);
-                    o.z = gray_mask4(v[6], v[7], v[8], sdiv, rmk); o.w = gray_mask4(v[9], v[10], v[11], sdiv, rmk);
-                } else if (t.channels == 4) {                        // RGBX words (4-byte aligned by contract)
-                    const uint32_t *wp = (const uint32_t *)(srow + 4 * (int64_t)x0);
-                    uint32_t v[16];
-                    if (((uintptr_t)wp & 15) == 0) {
+        const bool full = x0 + 16 <= W;
+        uint4 o;
+        if (t.channels >= 3) {                                       // warp-uniform (one crop per CTA)
+            uint32_t v[16];                                          // one word per pixel: R | G << 8 | B << 16 | (ignored) << 24
+            if (t.channels == 4) {                                   // RGBX words (4-byte aligned by contract)
+                const uint32_t *wp = (const uint32_t *)(srow + 4 * (int64_t)x0);
+                if (full && ((uintptr_t)wp & 15) == 0) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { const uint4 u = __ldg((const uint4 *)wp + q); v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w; }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __ldg(wp + i);
-                    }
-                    o.x = gray_mask4x(v[0], v[1], v[2], v[3], sdiv, rmk); o.y = gray_mask4x(v[4], v[5], v[6], v[7], sdiv, rmk);
-                    o.z = gray_mask4x(v[8], v[9], v[10], v[11], sdiv, rmk); o.w = gray_mask4x(v[12], v[13], v[14], v[15], sdiv, rmk);
+                    for (int k = 0; k < 4; ++k) { const uint4 u = __ldg((const uint4 *)wp + k); v[4 * k] = u.x; v[4 * k + 1] = u.y; v[4 * k + 2] = u.z; v[4 * k + 3] = u.w; }
                 } else {
-                    const uint8_t *sp = srow + x0;
-                    if (((uintptr_t)sp & 15) == 0) o = __ldg((const uint4 *)sp);
-                    else {
-                        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) w[i >> 2] |= (uint32_t)__ldg(sp + i) << (8 * (i & 3));
-                        o = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int i = 0; i < 16; ++i) v[i] = (x0 + i < W) ? __ldg(wp + i) : 0u;
+                }
+            } else if (full) {
+                uint32_t w[12];
+                load48(srow + 3 * (int64_t)x0, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[4 * k] = w[3 * k]; v[4 * k + 1] = __funnelshift_r(w[3 * k], w[3 * k + 1], 24);
+                    v[4 * k + 2] = __funnelshift_r(w[3 * k + 1], w[3 * k + 2], 16); v[4 * k + 3] = w[3 * k + 2] >> 8;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = 0u;
+                    if (x0 + i < W) {
+                        const uint8_t *p = srow + 3 * (int64_t)(x0 + i);
+                        v[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
                     }
                 }
-                *(uint4 *)(drow + x0) = o;                           // canvas rows are 16-byte aligned
-            } else {                                                 // last, partial group of the row
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (int i = 0; x0 + i < W; ++i) {
-                    uint32_t gv;
-                    if (t.channels >= 3) {
-                        const uint8_t *p = srow + t.channels * (int64_t)(x0 + i);
-                        const uint32_t r = __ldg(p), g = __ldg(p + 1), b = __ldg(p + 2);
-                        rmk += hsv_mask_px(r, g, b, sdiv) ? 1u : 0u;
-                        gv = gray1<SYNSEG_GRAY_PIL>(r | (g << 8) | (b << 16));
-                    } else gv = __ldg(srow + x0 + i);
-                    drow[x0 + i] = (uint8_t)gv;
-                    w[i >> 2] |= gv << (8 * (i & 3));
-                }
-                o = make_uint4(w[0], w[1], w[2], w[3]);              // bytes beyond the row stay zero: they add nothing below
             }
-            rs = __dp4a(o.x, 0x01010101u, rs); rs = __dp4a(o.y, 0x01010101u, rs); rs = __dp4a(o.z, 0x01010101u, rs); rs = __dp4a(o.w, 0x01010101u, rs);
-            rss = __dp4a(o.x, o.x, rss); rss = __dp4a(o.y, o.y, rss); rss = __dp4a(o.z, o.z, rss); rss = __dp4a(o.w, o.w, rss);
-            rnz += __popc(__vcmpne4(o.x, 0u) & 0x01010101u) + __popc(__vcmpne4(o.y, 0u) & 0x01010101u) +
-                   __popc(__vcmpne4(o.z, 0u) & 0x01010101u) + __popc(__vcmpne4(o.w, 0u) & 0x01010101u);
+            o.x = gray_mask4x(v[0], v[1], v[2], v[3], sdiv, rmk); o.y = gray_mask4x(v[4], v[5], v[6], v[7], sdiv, rmk);
+            o.z = gray_mask4x(v[8], v[9], v[10], v[11], sdiv, rmk); o.w = gray_mask4x(v[12], v[13], v[14], v[15], sdiv, rmk);
+        } else {
+            const uint8_t *sp = srow + x0;
+            if (full && ((uintptr_t)sp & 15) == 0) o = __ldg((const uint4 *)sp);
+            else {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i >> 2] |= ((x0 + i < W) ? (uint32_t)__ldg(sp + i) : 0u) << (8 * (i & 3));
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        s += rs; ss += rss; nz += rnz; mk += rmk;
+        *(uint4 *)(drow + x0) = o;                                   // canvas rows are 16-byte aligned and padded; columns >= W are never read
+        rs = __dp4a(o.x, 0x01010101u, rs); rs = __dp4a(o.y, 0x01010101u, rs); rs = __dp4a(o.z, 0x01010101u, rs); rs = __dp4a(o.w, 0x01010101u, rs);
+        rss = __dp4a(o.x, o.x, rss); rss = __dp4a(o.y, o.y, rss); rss = __dp4a(o.z, o.z, rss); rss = __dp4a(o.w, o.w, rss);
+        rnz += __popc(__vcmpne4(o.x, 0u) & 0x01010101u) + __popc(__vcmpne4(o.y, 0u) & 0x01010101u) +
+               __popc(__vcmpne4(o.z, 0u) & 0x01010101u) + __popc(__vcmpne4(o.w, 0u) & 0x01010101u);
+        gi += 32;
+        while (gi >= G) { gi -= G; ++r; }
     }
+    unsigned long long s = rs, ss = rss, nz = rnz, mk = rmk;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         s += __shfl_down_sync(0xffffffffu, s, d); ss += __shfl_down_sync(0xffffffffu, ss, d);

@@ -15,7 +15,7 @@
 #define SYNSEG_FORK_DEFAULT 0
 #endif
 #ifndef SYNSEG_OVERLAP_DEFAULT
-#define SYNSEG_OVERLAP_DEFAULT 1
+#define SYNSEG_OVERLAP_DEFAULT 2
 #endif
 
 #ifndef __CUDA_ARCH__

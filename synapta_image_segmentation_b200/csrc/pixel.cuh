@@ -40,9 +40,11 @@ __device__ __forceinline__ uint32_t hsv_sdiv(uint32_t v) { return v ? (2u * 1044
 // The reference's dominant-colour mask: S > 30 && V > 40 && V < 240 (pdf_image_segmentation.py:1574)
 __device__ __forceinline__ bool hsv_mask_px(uint32_t r, uint32_t g, uint32_t b, const uint32_t *sdiv_tab)
 {
-    const uint32_t v = max(r, max(g, b)), mn = min(r, min(g, b));
-    const uint32_t s = ((v - mn) * sdiv_tab[v] + 2048u) >> 12;
-    return s > 30u && v > 40u && v < 240u;
+    const uint32_t v = max(r, max(g, b)), mn = min(r, min(g, b)), diff = v - mn;
+    // greys and near-greys need no table look-up: 9 diff < v  =>  diff * sdiv[v] + 2048 < 1044480 / 9 + 128 + 2048  =>  S <= 28
+    if (9u * diff < v || v <= 40u || v >= 240u) return false;
+    const uint32_t s = (diff * sdiv_tab[v] + 2048u) >> 12;
+    return s > 30u;
 }
 
 // ---- 16 consecutive grey pixels of a row starting at column x (any x), BORDER_REPLICATE ------------------------
