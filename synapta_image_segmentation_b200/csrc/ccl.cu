@@ -752,13 +752,6 @@ int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, i
     const dim3 grid = row_grid(g, batch, 0, G);
     LAUNCH_G(G, (rccl_compress_kernel<1, 16>), (rccl_compress_kernel<1, 32>), grid, 0, st, g, L, (u64 *)nullptr, (int32_t *)nullptr, strong, flags, fper);
     SS_LAUNCH_CHECK(ctx, "hyst_flag", st);
-    if (ctx->hyst_join) {
-        // the unions ran on a side stream beside the kernel that fills `edges_bits`; the last kernel ORs into that plane
-        // and goes back to the caller's stream
-        SS_CUDA(cudaEventRecord(ctx->hyst_join_event, st));
-        st = ctx->hyst_final_stream;
-        SS_CUDA(cudaStreamWaitEvent(st, ctx->hyst_join_event, 0));
-    }
     if (edges_u8)
         LAUNCH_G(G, (rccl_hyst_final_kernel<false, 16>), (rccl_hyst_final_kernel<false, 32>), grid, 0, st, g, L, flags, fper, plane_of(edges_u8),
                  plane_aligned(edges_u8, 16), BitPlane{nullptr, 0, 0}, false);

@@ -50,12 +50,13 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->tune_canny_band = e2 ? atoi(e2) : 0;
     c->sm_count = prop.multiProcessorCount;
     const char *e3 = getenv("SYNSEG_OVERLAP");
-    const char *e4 = getenv("SYNSEG_FORK");
+    const char *e4 = getenv("SYNSEG_STREAMS");
     c->overlap = e3 ? atoi(e3) : SYNSEG_OVERLAP_DEFAULT;
-    c->fork = e4 ? atoi(e4) : SYNSEG_FORK_DEFAULT;
-    c->aux = nullptr; c->ev_split_fork = c->ev_split_join = nullptr;
-    for (int i = 0; i < 2; ++i) { c->aux_hi[i] = nullptr; c->ev_fork[i] = c->ev_join[i] = nullptr; }
-    c->hyst_final_stream = nullptr; c->hyst_join_event = nullptr; c->hyst_join = false;
+    c->overlap_streams = e4 ? atoi(e4) : 2;
+    if (c->overlap_streams < 2) c->overlap_streams = 2;
+    if (c->overlap_streams > 4) c->overlap_streams = 4;
+    c->ev_split_fork = nullptr;
+    for (int i = 0; i < 3; ++i) { c->aux[i] = nullptr; c->ev_split_join[i] = nullptr; }
     // integer DCT basis of the perceptual hash (same formula as oracle/synseg_oracle.c:orc_phash_basis)
     int32_t basis[8 * 32];
     for (int u = 0; u < 8; ++u)
@@ -75,13 +76,10 @@ extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->phash_basis) cudaFree(ctx->phash_basis);
     host_stream_release(ctx);
-    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->ev_split_fork) cudaEventDestroy(ctx->ev_split_fork);
-    if (ctx->ev_split_join) cudaEventDestroy(ctx->ev_split_join);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->aux_hi[i]) cudaStreamDestroy(ctx->aux_hi[i]);
-        if (ctx->ev_fork[i]) cudaEventDestroy(ctx->ev_fork[i]);
-        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->ev_split_join[i]) cudaEventDestroy(ctx->ev_split_join[i]);
     }
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);

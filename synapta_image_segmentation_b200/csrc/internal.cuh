@@ -11,9 +11,6 @@
 
 #define SYNSEG_EXPORT __attribute__((visibility("default")))
 
-#ifndef SYNSEG_FORK_DEFAULT
-#define SYNSEG_FORK_DEFAULT 0
-#endif
 #ifndef SYNSEG_OVERLAP_DEFAULT
 #define SYNSEG_OVERLAP_DEFAULT 2
 #endif
@@ -37,14 +34,10 @@ struct synseg_ctx {
     int tune_canny_band;
     // Stage overlap inside synseg_detect_pages (pipeline.cu): side streams owned by the context, forked from and joined
     // back into the caller's stream with events, so the call stays asynchronous on the caller's stream.
-    int overlap;                            // env SYNSEG_OVERLAP: page chunks per call, alternating between the caller's stream and a side stream (1 = one chain)
-    int fork;                               // env SYNSEG_FORK: 1 = Canny + hysteresis unions on a high-priority side stream beside the threshold
-    cudaStream_t aux;                       // side stream of the odd chunks (created on first use)
-    cudaStream_t aux_hi[2];                 // high-priority side streams of the two chains
-    cudaEvent_t ev_split_fork, ev_split_join, ev_fork[2], ev_join[2];
-    cudaStream_t hyst_final_stream;         // with hyst_join set, run_hysteresis launches its last kernel on this stream
-    cudaEvent_t hyst_join_event;            //   after joining the unions' stream through this event
-    bool hyst_join;
+    int overlap;                            // env SYNSEG_OVERLAP: page chunks per call, dealt round-robin to `overlap_streams` streams (1 = one chain)
+    int overlap_streams;                    // env SYNSEG_STREAMS: the caller's stream + up to 3 side streams (default 2)
+    cudaStream_t aux[3];                    // side streams (created on first use)
+    cudaEvent_t ev_split_fork, ev_split_join[3];
     // host-buffer streaming (synseg_detect_pages_host): device staging ring + copy stream, created on first use
     struct HostStream {
         cudaStream_t copy;                 // H2D stream
