@@ -35,11 +35,12 @@ struct ColorSmem {
     uint32_t h[CBINS];            // masked pixels per bin
     uint32_t cs[3 * CBINS];       // channel sums per bin (<= 255 * 2^24 pixels per crop)
     uint32_t sdiv[256];
-    uint16_t list[CBINS];         // non-empty bins in ascending order
+    uint16_t list[CBINS];         // non-empty bins in ascending order (bits 0-11; bits 12-15: cluster of the bin)
     uint32_t warp_cnt[CTHREADS / 32];
     u64 red[CTHREADS / 32];
     int32_t centre[CMAXK][3];     // Q6 fixed point
-    u64 acc[CMAXK][4];            // per cluster: count, sum r, sum g, sum b
+    u64 acc[CMAXK][4];            // per cluster: [0] = pixels of the last assignment
+    u64 part[CTHREADS / 32][4];   // per warp: count, sum of count * point (r, g, b) of its cluster in this round
     u64 picked;
     int n_list, changed;
     u64 total;
@@ -206,50 +207,52 @@ __global__ void __launch_bounds__(CTHREADS) crop_colors_kernel(const uint8_t *ba
     __syncthreads();
 
     // ---- weighted Lloyd iterations over the bin centroids -------------------------------------------------------
-    // A lane owns a bin, lane j of every warp collects cluster j: per cluster the warp reduces the members' count and
-    // count * point (split into 20-bit halves so the 32-lane sums fit 32 bits) with REDUX and lane j keeps the totals
-    // in registers; shared memory sees 4 atomics per warp, cluster and round.
+    // Two passes per round.  Assign: a thread owns a bin and writes the index of its nearest centre into the four spare
+    // bits of the bin's 16-bit list entry.  Accumulate, cluster-major: the 16 warps split into k groups, the warps of a
+    // group share the list; a lane adds the members of its cluster it meets to 64-bit registers, the warp folds them
+    // with shuffles once per round and leaves one partial per warp -- no atomics, no `redux` (the per-cluster REDUX
+    // form spent 58 % of the kernel's stall samples on the uniform-register round trips).
+    const int nparts = (CTHREADS / 32) / k;                // warps per cluster (>= 2 for k <= 8)
     for (int it = 0; it < iters; ++it) {
-        if (threadIdx.x < 4 * CMAXK) ((u64 *)S.acc)[threadIdx.x] = 0ull;
         if (threadIdx.x == 0) S.changed = 0;
+        for (int i = threadIdx.x; i < nb; i += CTHREADS) {
+            const int bin = S.list[i] & (CBINS - 1);
+            const int p0 = (int)S.cs[3 * bin], p1 = (int)S.cs[3 * bin + 1], p2 = (int)S.cs[3 * bin + 2];
+            int a = 0, dbest = 0x7fffffff;
+            for (int j = 0; j < k; ++j) {
+                const int d0 = p0 - S.centre[j][0], d1 = p1 - S.centre[j][1], d2 = p2 - S.centre[j][2];
+                const int d = d0 * d0 + d1 * d1 + d2 * d2;
+                if (d < dbest) { dbest = d; a = j; }
+            }
+            S.list[i] = (uint16_t)(bin | (a << 12));
+        }
         __syncthreads();
-        u64 myN = 0, myT0 = 0, myT1 = 0, myT2 = 0;
-        for (int i0 = warp * 32; i0 < nb; i0 += CTHREADS) {
-            const int i = i0 + lane;
-            const bool valid = i < nb;
-            uint32_t w = 0;
-            int p0 = 0, p1 = 0, p2 = 0, a = -1;
-            if (valid) {
-                const int bin = S.list[i];
-                w = S.h[bin]; p0 = (int)S.cs[3 * bin]; p1 = (int)S.cs[3 * bin + 1]; p2 = (int)S.cs[3 * bin + 2];
-                int dbest = 0x7fffffff;
-                for (int j = 0; j < k; ++j) {
-                    const int d0 = p0 - S.centre[j][0], d1 = p1 - S.centre[j][1], d2 = p2 - S.centre[j][2];
-                    const int d = d0 * d0 + d1 * d1 + d2 * d2;
-                    if (d < dbest) { dbest = d; a = j; }
+        if (warp < k * nparts) {
+            const int j = warp % k, part = warp / k;
+            u64 N = 0, T0 = 0, T1 = 0, T2 = 0;
+            for (int i = part * 32 + lane; i < nb; i += 32 * nparts) {
+                const int e = S.list[i];
+                if ((e >> 12) == j) {
+                    const int bin = e & (CBINS - 1);
+                    const uint32_t w = S.h[bin];
+                    N += w; T0 += (u64)w * S.cs[3 * bin]; T1 += (u64)w * S.cs[3 * bin + 1]; T2 += (u64)w * S.cs[3 * bin + 2];
                 }
             }
-            for (int j = 0; j < k; ++j) {
-                const bool in = a == j;
-                if (__ballot_sync(0xffffffffu, in) == 0u) continue;      // warp-uniform
-                const uint32_t wv = in ? w : 0u;
-                const u64 t0 = (u64)wv * (uint32_t)p0, t1 = (u64)wv * (uint32_t)p1, t2 = (u64)wv * (uint32_t)p2;
-                const uint32_t n = __reduce_add_sync(0xffffffffu, wv);
-                const u64 s0 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t0 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t0 & 0xFFFFFu));
-                const u64 s1 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t1 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t1 & 0xFFFFFu));
-                const u64 s2 = ((u64)__reduce_add_sync(0xffffffffu, (uint32_t)(t2 >> 20)) << 20) + __reduce_add_sync(0xffffffffu, (uint32_t)(t2 & 0xFFFFFu));
-                if (lane == j) { myN += n; myT0 += s0; myT1 += s1; myT2 += s2; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                N += __shfl_down_sync(0xffffffffu, N, d); T0 += __shfl_down_sync(0xffffffffu, T0, d);
+                T1 += __shfl_down_sync(0xffffffffu, T1, d); T2 += __shfl_down_sync(0xffffffffu, T2, d);
             }
-        }
-        if (lane < k && myN) {
-            atomicAdd(&S.acc[lane][0], myN); atomicAdd(&S.acc[lane][1], myT0); atomicAdd(&S.acc[lane][2], myT1); atomicAdd(&S.acc[lane][3], myT2);
+            if (lane == 0) { S.part[warp][0] = N; S.part[warp][1] = T0; S.part[warp][2] = T1; S.part[warp][3] = T2; }
         }
         __syncthreads();
         if (threadIdx.x < 3 * k) {
             const int j = threadIdx.x / 3, c = threadIdx.x % 3;
-            const u64 N = S.acc[j][0];
+            u64 N = 0, T = 0;
+            for (int q = 0; q < nparts; ++q) { N += S.part[j + k * q][0]; T += S.part[j + k * q][1 + c]; }
+            if (c == 0) S.acc[j][0] = N;
             if (N) {
-                const int32_t nc = (int32_t)((S.acc[j][1 + c] + N / 2) / N);
+                const int32_t nc = (int32_t)((T + N / 2) / N);
                 if (nc != S.centre[j][c]) { S.centre[j][c] = nc; S.changed = 1; }
             }
         }
@@ -300,11 +303,7 @@ extern "C" SYNSEG_EXPORT int synseg_colors_crops(synseg_ctx *ctx, const void *ba
     SS_TRY(arena_alloc(ctx, sizeof(CropTask) * (size_t)n, &p, st));
     // pageable source: the driver stages the bytes before cudaMemcpyAsync returns, so the vector may die with this call
     SS_CUDA(cudaMemcpyAsync(p, tasks.data(), sizeof(CropTask) * (size_t)n, cudaMemcpyHostToDevice, st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        SS_CUDA(cudaFuncSetAttribute(crop_colors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColorSmem)));
-        attr_set = true;
-    }
+    SS_CUDA(cudaFuncSetAttribute(crop_colors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColorSmem)));   // per device; cheap
     crop_colors_kernel<<<n, CTHREADS, sizeof(ColorSmem), st>>>((const uint8_t *)base, (const CropTask *)p, n_colors, iters, min_pixels,
                                                              (u64 *)out, hist_out);
     SS_LAUNCH_CHECK(ctx, "crop_colors", st);
