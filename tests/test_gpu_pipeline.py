@@ -64,6 +64,40 @@ def test_pipeline_odd_sizes_and_noise(ctx):
         assert np.array_equal(cent[0, :n_w].cpu().numpy(), ce_w, equal_nan=True)
 
 
+def test_page_chunks_on_side_streams_equal_one_chain(ctx, monkeypatch):
+    """synseg_detect_pages cuts a batch into chunks that run as independent chains on the caller's stream and the
+    context's side streams (SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams; default 2 on 2).  Every setting must give
+    the tables of the single chain -- ragged last chunk, more chunks than streams, repeated calls on one context (the
+    arena parts are re-used), a grey plane handed back -- and the cv2 chain's."""
+    from synapta_image_segmentation_b200.ops import Context
+    pages = synth_pages(7, 100, start=40)
+    dev_pages = torch.from_numpy(pages).cuda()
+    bs, c, k = cv2_chain.chain_params(100)
+    want = None
+    for chunks, streams in ((1, 2), (2, 2), (3, 3), (3, 2), (3, 4)):
+        monkeypatch.setenv("SYNSEG_OVERLAP", str(chunks))
+        monkeypatch.setenv("SYNSEG_STREAMS", str(streams))
+        cx = Context(0)
+        try:
+            for rep in range(2):
+                gray = torch.empty(pages.shape[:3], dtype=torch.uint8, device="cuda") if rep else None
+                n, stats, cent = cx.detect_pages(dev_pages, bs, c, k, max_labels=512, gray_out=gray)
+                got = (n.cpu().numpy(), stats.cpu().numpy(), cent.cpu().numpy())
+                if want is None:
+                    want = got
+                    for i in range(pages.shape[0]):
+                        r = cv2_chain.page_chain(pages[i], 100)
+                        assert got[0][i] == r["n"] and np.array_equal(got[1][i, :r["n"]], r["stats"])
+                assert np.array_equal(got[0], want[0]), (chunks, streams, rep)
+                for i in range(pages.shape[0]):
+                    m = int(want[0][i])
+                    assert np.array_equal(got[1][i, :m], want[1][i, :m]) and np.array_equal(got[2][i, :m], want[2][i, :m], equal_nan=True), (chunks, streams, rep, i)
+                if gray is not None:
+                    assert np.array_equal(gray.cpu().numpy(), np.stack([cv2.cvtColor(p_, cv2.COLOR_RGB2GRAY) for p_ in pages]))
+        finally:
+            cx.close()
+
+
 def test_detector_regions_cover_figures(ctx):
     from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
     det = RasterRegionDetector(DetectConfig(dpi=150), ctx=ctx)
