@@ -71,9 +71,16 @@ class RasterRegionDetector:
         return self.ctx.detect_pages(pages, bs, c, k, self.cfg.canny_lo, self.cfg.canny_hi, self.cfg.max_labels, out=out)
 
     # ---- host stage --------------------------------------------------------------------------
-    def candidate_regions(self, stats: np.ndarray, n_labels: int, page_width_pt: float, page_height_pt: float) -> List[Dict]:
+    def candidate_regions(self, stats: np.ndarray, n_labels: int, page_width_pt: float, page_height_pt: float,
+                          priors: Optional[Sequence[Dict]] = None) -> List[Dict]:
         """Component stats of one page ([n,5] = x,y,w,h,area in px; row 0 = background) -> region dicts
-        (bbox in points) before validation."""
+        (bbox in points) before validation.
+
+        priors: regions a PDF object model produced for this page (the reference's caption-based regions,
+        `_detect_by_captions`, pdf_image_segmentation.py:3148-3254: dicts with 'bbox' and, when known, 'caption_bbox').
+        They take the place `caption_regions` has in `_detect_visual_regions` (:3114-3144): every prior is kept, a raster
+        region is added unless more than half of it lies inside a region already kept or it sits right above a prior's
+        caption."""
         if n_labels < 0:
             raise RuntimeError(f"page has {-n_labels} components, more than max_labels={self.cfg.max_labels}")
         s = 72.0 / self.cfg.dpi
@@ -92,7 +99,8 @@ class RasterRegionDetector:
             elif a < page_area * G.DRAWING_MAX_PAGE_FRACTION:
                 small.append(rect)
         secondary = G.regions_from_rects(small, page_width_pt, page_height_pt, "raster_cluster", "raster components")
-        return G.merge_visual_regions(primary, secondary)
+        raster = G.merge_visual_regions(primary, secondary)
+        return G.merge_visual_regions(list(priors), raster) if priors else raster
 
     def _crop_px(self, bbox: BoundingBox, width: int, height: int):
         x, y, w, h = bbox.to_pixels(self.cfg.dpi)
@@ -102,7 +110,7 @@ class RasterRegionDetector:
 
     def detect_regions_batch(self, pages: torch.Tensor, page_nums: Optional[Sequence[int]] = None,
                              page_width_pt: Optional[float] = None, page_height_pt: Optional[float] = None,
-                             with_hash: bool = False) -> List[List[Dict]]:
+                             with_hash: bool = False, priors: Optional[Sequence[Optional[Sequence[Dict]]]] = None) -> List[List[Dict]]:
         """RGB pages (CUDA u8 [B,H,W,3]) -> per page a list of region dicts, sorted by (y0, x0).
 
         Region dict = the reference's schema (pdf_image_segmentation.py:3246-3252 / 3550-3555):
@@ -118,7 +126,9 @@ class RasterRegionDetector:
         n_h = n.cpu().numpy()
         nmax = int(np.abs(n_h).max()) if b else 0
         stats_h = stats[:, :max(nmax, 1)].cpu().numpy()
-        per_page = [self.candidate_regions(stats_h[i], int(n_h[i]), pw, ph) for i in range(b)]
+        if priors is not None and len(priors) != b:
+            raise ValueError(f"priors: expected one entry per page ({b}), got {len(priors)}")
+        per_page = [self.candidate_regions(stats_h[i], int(n_h[i]), pw, ph, priors[i] if priors is not None else None) for i in range(b)]
         rois, owners = [], []
         for i, regs in enumerate(per_page):
             for r in regs:
@@ -135,10 +145,16 @@ class RasterRegionDetector:
                 npx = cw * chh
                 s1, s2 = int(mom[j, 0]), int(mom[j, 1])
                 var = (npx * s2 - s1 * s1) / (npx * npx)
-                score, notes = G.validate_region(r["bbox"], cw, chh, var, ph)
                 r["variance"] = var
-                r["confidence"] = score
-                r["validation"] = notes
+                if r.get("detection_method") == "caption_based":
+                    # regions handed in from the PDF object model are not re-scored: the reference keeps every caption
+                    # region with confidence 0.9 (pdf_image_segmentation.py:2787-2799)
+                    r.setdefault("confidence", 0.9)
+                    r.setdefault("validation", "caption_based")
+                else:
+                    score, notes = G.validate_region(r["bbox"], cw, chh, var, ph)
+                    r["confidence"] = score
+                    r["validation"] = notes
                 if hashes is not None:
                     r["phash"] = int(hashes[j]) & 0xFFFFFFFFFFFFFFFF
         out = []
@@ -149,13 +165,13 @@ class RasterRegionDetector:
         return out
 
     def detect_regions(self, page_rgb, page_num: int = 0, dpi: Optional[int] = None, page_width_pt: Optional[float] = None,
-                       page_height_pt: Optional[float] = None) -> List[Dict]:
+                       page_height_pt: Optional[float] = None, priors: Optional[Sequence[Dict]] = None) -> List[Dict]:
         """Single-page form mirroring `_detect_visual_regions(page, page_num) -> List[Dict]` (:3105)."""
         if dpi is not None and dpi != self.cfg.dpi:
             raise ValueError(f"detector configured for {self.cfg.dpi} DPI, got a {dpi} DPI page")
         t = page_rgb if isinstance(page_rgb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(page_rgb))
         t = t.to(self.ctx.device, non_blocking=True)
-        return self.detect_regions_batch(t, [page_num], page_width_pt, page_height_pt)[0]
+        return self.detect_regions_batch(t, [page_num], page_width_pt, page_height_pt, priors=[priors] if priors is not None else None)[0]
 
     def extract_segments(self, page_rgb: np.ndarray, page_num: int, book_id: str = "textbook_001",
                          output_dir: Optional[str] = None) -> List[VisualSegment]:

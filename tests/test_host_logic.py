@@ -208,3 +208,31 @@ def test_writers_match_reference_bytes(tmp_path):
     assert list(image_seg["image_details"].keys()) == gold["a1_image_details_keys"]
     assert list(image_seg["image_data"].keys()) == gold["a1_image_data_keys"]
     assert w.summary_csv_text().splitlines()[0] == gold["a1_csv_header"]
+
+
+def test_candidate_regions_with_pdf_priors():
+    """Host stage of the detector (no GPU): component boxes -> region dicts, merged with caption-based priors exactly
+    like _detect_visual_regions merges drawing regions into caption regions (pdf_image_segmentation.py:3114-3144)."""
+    from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
+    det = RasterRegionDetector(DetectConfig(dpi=72), ctx=object())          # the host stage never touches the context
+    # stats rows: x, y, w, h, area (px = points at 72 DPI); row 0 = background
+    stats = np.array([[0, 0, 612, 792, 400000],
+                      [100, 100, 200, 150, 30000],       # a figure-sized component
+                      [100, 400, 220, 160, 35200],       # another one, 60 pt above a caption
+                      [400, 600, 8, 8, 64], [415, 600, 8, 8, 64], [430, 600, 8, 8, 64]], np.int32)   # three specks: one cluster, too small to keep
+    plain = det.candidate_regions(stats, len(stats), 612.0, 792.0)
+    assert [(r["detection_method"], r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1) for r in plain] == \
+        [("raster_cc", 100.0, 100.0, 300.0, 250.0), ("raster_cc", 100.0, 400.0, 320.0, 560.0)]
+    cap1 = {"bbox": BB(90, 90, 310, 260), "caption": "Figure 1.1 Something", "caption_bbox": (100, 265, 300, 278),
+            "detection_method": "caption_based", "notes": "Caption: Figure 1.1"}
+    cap2 = {"bbox": BB(400, 100, 560, 220), "caption": "Exhibit 2", "caption_bbox": (120, 570, 300, 583),
+            "detection_method": "caption_based", "notes": "Caption: Exhibit 2"}
+    merged = det.candidate_regions(stats, len(stats), 612.0, 792.0, priors=[cap1, cap2])
+    # both priors stay; component 1 duplicates cap1 (all of it lies inside); component 2 sits right above cap2's caption
+    assert [r["detection_method"] for r in merged] == ["caption_based", "caption_based"]
+    far = dict(cap2, caption_bbox=(120, 700, 300, 713))
+    merged = det.candidate_regions(stats, len(stats), 612.0, 792.0, priors=[cap1, far])
+    assert [r["detection_method"] for r in merged] == ["caption_based", "caption_based", "raster_cc"]
+    assert (merged[2]["bbox"].x0, merged[2]["bbox"].y0) == (100.0, 400.0)
+    with pytest.raises(RuntimeError):
+        det.candidate_regions(stats, -7, 612.0, 792.0)                      # label overflow is an error, not an empty page
