@@ -79,8 +79,8 @@ class RasterRegionDetector:
         priors: regions a PDF object model produced for this page (the reference's caption-based regions,
         `_detect_by_captions`, pdf_image_segmentation.py:3148-3254: dicts with 'bbox' and, when known, 'caption_bbox').
         They take the place `caption_regions` has in `_detect_visual_regions` (:3114-3144): every prior is kept, a raster
-        region is added unless more than half of it lies inside a region already kept or it sits right above a prior's
-        caption."""
+        region is added unless more than half of it lies inside a prior or it sits right above a prior's caption
+        (SURVEY.md 8f rank 4)."""
         if n_labels < 0:
             raise RuntimeError(f"page has {-n_labels} components, more than max_labels={self.cfg.max_labels}")
         s = 72.0 / self.cfg.dpi
@@ -100,7 +100,14 @@ class RasterRegionDetector:
                 small.append(rect)
         secondary = G.regions_from_rects(small, page_width_pt, page_height_pt, "raster_cluster", "raster components")
         raster = G.merge_visual_regions(primary, secondary)
-        return G.merge_visual_regions(list(priors), raster) if priors else raster
+        if not priors:
+            return raster
+        # every raster region is tested against the PRIORS only (among themselves the raster regions were merged above:
+        # with no priors the result must not change), by the two rules of _detect_visual_regions
+        priors = list(priors)
+        return priors + [r for r in raster
+                         if not G.overlaps_with_existing(r["bbox"], priors)
+                         and not any("caption_bbox" in p and G.caption_near_region(r["bbox"], p["caption_bbox"]) for p in priors)]
 
     def _crop_px(self, bbox: BoundingBox, width: int, height: int):
         x, y, w, h = bbox.to_pixels(self.cfg.dpi)

@@ -122,6 +122,20 @@ def test_detector_regions_cover_figures(ctx):
             assert any(r["bbox"].x0 <= x0 + 1 and r["bbox"].y0 <= y0 + 1 and r["bbox"].x1 >= x1 - 1 and r["bbox"].y1 >= y1 - 1 for r in regs)
     single = det.detect_regions(pages[0], 0)
     assert [r["bbox"] for r in single] == [r["bbox"] for r in regions[0]]
+    # a caption region handed in from a PDF object model: kept with the reference's 0.9, and the raster
+    # region it covers is dropped as its duplicate (_detect_visual_regions, pdf_image_segmentation.py:3122-3144)
+    from synapta_image_segmentation_b200.datamodel import BoundingBox
+    small = min(regions[0], key=lambda r: r["bbox"].area())
+    first = small["bbox"]
+    prior = {"bbox": BoundingBox(first.x0 - 5, first.y0 - 5, first.x1 + 5, first.y1 + 5, 612.0, 792.0), "caption": "Figure 1.1",
+             "detection_method": "caption_based", "notes": "Caption: Figure 1.1"}
+    with_prior = det.detect_regions(pages[0], 0, priors=[prior])
+    assert len(with_prior) == len(regions[0])
+    assert [r["detection_method"] for r in with_prior].count("caption_based") == 1
+    cap = [r for r in with_prior if r["detection_method"] == "caption_based"][0]
+    assert cap["confidence"] == 0.9 and cap["caption"] == "Figure 1.1" and "variance" in cap
+    assert sorted((r["bbox"].x0, r["bbox"].y0) for r in with_prior if r["detection_method"] != "caption_based") == \
+        sorted((r["bbox"].x0, r["bbox"].y0) for r in regions[0] if r is not small)
     segs = det.extract_segments(pages[0], 0, "textbook_001")
     assert all(s.segment_id.startswith("textbook_001_p000_") and s.page_no == 1 and s.notes.startswith("Validation: ") for s in segs)
     assert json.dumps(segs[0].to_dict())
