@@ -12,6 +12,9 @@
 // Canny hysteresis ORs its result into the same plane, the dilate (folded with the close's dilate into
 // one (2k-1) pass) and the erode run on bit planes, and the labelling reads bits.  The bit planes of a
 // 50-page batch (53 MB each) stay in the 126 MB L2; the grey plane (420 MB) is re-read from HBM by the two stencils.
+// Stream plan: a batch is cut into page chunks that run as independent chains on the caller's stream and on side streams
+// owned by the context (fork / join through events; SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams, default 2 on 2), so
+// the latency-bound union-find of one chunk overlaps the issue-bound stencils of another.
 //
 // synseg_grid_counts: per crop, grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2)
 //   -> non-zero counts, i.e. _detect_grid (pdf_image_segmentation.py:1546-1564) and the visual part of

@@ -120,6 +120,11 @@ def test_c_abi_exports_every_declared_symbol():
     exported = set(re.findall(r" T (synseg_\w+)", out))
     assert exported == declared, exported ^ declared
     assert lib.synseg_version() == 100
+    # the ctypes signatures carry as many arguments as the prototypes in the header
+    for m in re.finditer(r"\b(synseg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        n_params = 0 if params in ("", "void") else params.count(",") + 1
+        assert n_params == len(_lib.SIGNATURES[name][1]), (name, n_params, len(_lib.SIGNATURES[name][1]))
     import torch
     if not torch.cuda.is_available():      # fails loudly without a GPU: no CPU fallback
         import ctypes as C
