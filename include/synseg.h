@@ -221,21 +221,6 @@ typedef struct synseg_crop {
 int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int kw, int kh,
                        uint64_t *out, void *stream);
 
-/* One image of synseg_pack_rows: `rows` rows of `row_bytes` bytes, `src_row_stride` bytes apart at `src` (HOST memory),
- * go to dst_base + dst_offset, `dst_row_stride` bytes apart. */
-typedef struct synseg_pack_item {
-    const void *src;
-    uint64_t dst_offset;
-    int64_t src_row_stride, dst_row_stride, row_bytes;
-    int32_t rows;
-    int32_t _pad;
-} synseg_pack_item;
-
-/* Host-side helper of the crop hand-over (no device work, no context): copies the rows of n host images (the PIL images
- * _render_region returns, S:3638-3657) into one packed host buffer -- the layout synseg_hints_crops / synseg_colors_crops
- * read once it is on the device -- with `threads` threads, in pieces of about a megabyte.  Synchronous. */
-int synseg_pack_rows(void *dst_base, const synseg_pack_item *items, int32_t n, int32_t threads);
-
 /* Batched dominant colours of a ragged batch of crops (the batched form of OCRProcessor._extract_dominant_colors,
  * S:1566-1594; BASELINE.json configs[3]).  Exact: the HSV mask S > 30 & V > 40 & V < 240 (S:1571-1574), the masked
  * pixel count and the `fewer than min_pixels -> no colours` decision (S:1577, min_pixels = 100).  The clustering is a

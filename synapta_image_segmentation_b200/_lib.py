@@ -25,12 +25,6 @@ class Crop(C.Structure):
                 ("channels", C.c_int32), ("_pad", C.c_int32)]
 
 
-class PackItem(C.Structure):
-    """synseg_pack_item"""
-    _fields_ = [("src", C.c_void_p), ("dst_offset", C.c_uint64), ("src_row_stride", C.c_int64), ("dst_row_stride", C.c_int64),
-                ("row_bytes", C.c_int64), ("rows", C.c_int32), ("_pad", C.c_int32)]
-
-
 class DetectParams(C.Structure):
     """synseg_detect_params"""
     _fields_ = [("block_size", C.c_int32), ("C", C.c_int32), ("canny_lo", C.c_int32), ("canny_hi", C.c_int32),
@@ -67,7 +61,6 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_hints_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "synseg_colors_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "synseg_pack_rows": (C.c_int, [C.c_void_p, _P(PackItem), C.c_int32, C.c_int32]),
     "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),
 }
 

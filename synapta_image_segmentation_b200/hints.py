@@ -421,24 +421,16 @@ class FeatureHints:
 
 
 def _copy_views(hv: np.ndarray, views, descs, pool=None) -> None:
-    """Copies every crop view into its place of the packed buffer: one `synseg_pack_rows` call (plain memcpy per row,
-    spread over threads in megabyte pieces; the strided numpy assignment per crop it replaces was the slowest part of
-    `hints_batch`).  The GIL is released for the duration of the call."""
-    from . import _lib
-    n = len(descs)
-    if n == 0:
-        return
-    items = (_lib.PackItem * n)()
-    keep = []
-    for i in range(n):
+    """Copies every crop view into its place of the packed buffer (numpy releases the GIL for these copies)."""
+    def one(i):
         v = views[i][0]
         o, w, h, rs, ch = descs[i]
-        if v.strides[1] != 1 or v.strides[0] < w * ch:
-            v = np.ascontiguousarray(v)
-            keep.append(v)
-        items[i] = _lib.PackItem(v.ctypes.data, o, v.strides[0], rs, w * ch, h, 0)
-    threads = pool._max_workers + 1 if pool is not None else 1
-    _lib.check(_lib.load().synseg_pack_rows(hv.ctypes.data, items, n, threads), "synseg_pack_rows")
+        hv[o:o + rs * h].reshape(h, rs)[:, :w * ch] = v
+    if pool is None or len(descs) < 4:
+        for i in range(len(descs)):
+            one(i)
+    else:
+        list(pool.map(one, range(len(descs)), chunksize=max(1, len(descs) // (4 * pool._max_workers))))
 
 
 class _CropStager:

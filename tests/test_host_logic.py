@@ -241,34 +241,3 @@ def test_candidate_regions_with_pdf_priors():
     assert (merged[2]["bbox"].x0, merged[2]["bbox"].y0) == (100.0, 400.0)
     with pytest.raises(RuntimeError):
         det.candidate_regions(stats, -7, 612.0, 792.0)                      # label overflow is an error, not an empty page
-
-
-def test_pack_rows_host_helper():
-    """synseg_pack_rows (host-only C entry point): images of any row stride land in the packed, 16-byte padded layout the
-    crop entry points read; padding bytes are left alone; bad items are refused."""
-    import concurrent.futures as cf
-    from synapta_image_segmentation_b200 import _lib
-    from synapta_image_segmentation_b200.hints import FeatureHints, _copy_views
-    from PIL import Image
-    rng = np.random.default_rng(1)
-    crops = []
-    for i, (h, w) in enumerate([(1, 1), (5, 7), (33, 517), (64, 64), (457, 699), (20, 17)]):
-        a = rng.integers(0, 255, (h, w, 3) if i % 3 < 2 else (h, w), dtype=np.uint8)
-        crops.append(Image.fromarray(a) if i % 3 == 0 else a)
-    crops.append(np.asarray(crops[4])[10:200, 5:300])            # a strided view
-    views = [FeatureHints.crop_view(c) for c in crops]
-    descs, off = [], 0
-    for v, w, h, ch, _ in views:
-        rs = (w * ch + 15) // 16 * 16
-        descs.append((off, w, h, rs, ch))
-        off += rs * h
-    for pool in (None, cf.ThreadPoolExecutor(3)):
-        buf = np.full(off, 7, np.uint8)
-        _copy_views(buf, views, descs, pool)
-        for (v, w, h, ch, _), (o, _, _, rs, _) in zip(views, descs):
-            rows = buf[o:o + rs * h].reshape(h, rs)
-            assert np.array_equal(rows[:, :w * ch], v) and (rows[:, w * ch:] == 7).all()
-    lib = _lib.load()
-    bad = (_lib.PackItem * 1)(_lib.PackItem(buf.ctypes.data, 0, 4, 16, 8, 2, 0))     # source stride shorter than a row
-    assert lib.synseg_pack_rows(buf.ctypes.data, bad, 1, 2) == -1 and b"bad item" in lib.synseg_last_error()
-    assert lib.synseg_pack_rows(buf.ctypes.data, bad, 0, 2) == 0
