@@ -215,7 +215,7 @@ def run_reference(args):
             "dtype": "u8", "data": "synthetic",
             "config": dict(cfg, reference_sample=f"each step = {per_step} pages of the same generator through the cv2 4.13 chain "
                                                  f"(oracle/cv2_chain.py) on {cores} host cores"),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_baseline.cpu_model(),
                              "sample": f"{per_step} pages per step x {len(vals)} steps; best arrangement: {best['arrangement']}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -445,7 +445,7 @@ def main():
         if n_s > B:
             sample = np.concatenate([sample] * ((n_s + B - 1) // B))[:n_s]
         r = cpu_baseline.measure_pages(sample, args.dpi)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "cpu_model": cpu_baseline.cpu_model(),
                "sample": f"{r['pages']} pages of the same textbook through the cv2 4.13 chain (oracle/cv2_chain.py); {r['arrangement']}; "
                          f"other arrangement: {r['other']:.1f} pages/s"}
 

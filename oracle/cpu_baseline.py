@@ -40,6 +40,16 @@ def _chain_page_parallel(pages: np.ndarray, dpi: int, workers: int) -> float:
         cv2.setNumThreads(os.cpu_count() or 1)
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def measure_pages(pages: np.ndarray, dpi: int):
     """pages: u8 [n,H,W,3].  Returns dict(value pages/s, cores, arrangement, pages, other)."""
     cores = os.cpu_count() or 1
