@@ -278,6 +278,7 @@ extern "C" SYNSEG_EXPORT int synseg_colors_crops(synseg_ctx *ctx, const void *ba
     if (n <= 0) return SYNSEG_OK;
     if (!base || !crops_host || !out) { synseg_set_error("synseg_colors_crops: NULL argument"); return SYNSEG_E_INVALID; }
     if (n_colors < 1 || n_colors > CMAXK || iters < 0) { synseg_set_error("synseg_colors_crops: need 1 <= n_colors <= %d, iters >= 0", CMAXK); return SYNSEG_E_INVALID; }
+    if (min_pixels < 1) min_pixels = 1;                 // a crop without a masked pixel has no colour
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<CropTask> tasks(n);
     for (int i = 0; i < n; ++i) {
