@@ -14,7 +14,8 @@
  *    "Nothing found" (no components, empty mask) is a valid result, never an error.
  *  - all image/result pointers are DEVICE pointers owned by the caller; calls are asynchronous on
  *    `stream`.  The library owns only the opaque context (scratch arena, grown on demand or
- *    pre-sized with synseg_reserve); one context per (process, GPU), not thread-safe.
+ *    pre-sized with synseg_reserve); one context per (process, GPU), not thread-safe.  The scratch arena
+ *    is shared by all calls on a context: issue them to ONE stream, or order them yourself.
  *  - images are row-major, 8-bit unless stated, described by synseg_img: `batch` images of
  *    height x width, `row_stride` / `batch_stride` in BYTES.  RGB images are interleaved HWC
  *    (3 bytes per pixel; width counts pixels).  Any stride/alignment is accepted; rows whose base
