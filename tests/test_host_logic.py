@@ -241,3 +241,12 @@ def test_candidate_regions_with_pdf_priors():
     assert (merged[2]["bbox"].x0, merged[2]["bbox"].y0) == (100.0, 400.0)
     with pytest.raises(RuntimeError):
         det.candidate_regions(stats, -7, 612.0, 792.0)                      # label overflow is an error, not an empty page
+
+
+def test_decode_colors_row_layout():
+    """Host decoding of one synseg_colors_crops row: { mask_px, k, (cluster pixels << 24 | R << 16 | G << 8 | B) x k, 0 ... }."""
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    row = np.array([14900, 3, (6400 << 24) | 0x1EA03C, (4500 << 24) | 0x283CD2, (4000 << 24) | 0xC81E28, 0, 0], np.int64)
+    assert FeatureHints.decode_colors(row) == dict(mask_px=14900, dominant_colors=["#1ea03c", "#283cd2", "#c81e28"],
+                                                   color_weights=[6400, 4500, 4000])
+    assert FeatureHints.decode_colors(np.array([99, 0, 0, 0, 0, 0, 0], np.int64)) == dict(mask_px=99, dominant_colors=[], color_weights=[])
