@@ -15,7 +15,9 @@
  *  - all image/result pointers are DEVICE pointers owned by the caller; calls are asynchronous on
  *    `stream`.  The library owns only the opaque context (scratch arena, grown on demand or
  *    pre-sized with synseg_reserve); one context per (process, GPU), not thread-safe.  The scratch arena
- *    is shared by all calls on a context: issue them to ONE stream, or order them yourself.
+ *    is shared by all calls on a context: a call issued to a different stream than the previous one is made to wait
+ *    for it (an event per call), so calls on one context never overlap each other; use one context per concurrent
+ *    pipeline.  No call changes the caller's current CUDA device.
  *  - images are row-major, 8-bit unless stated, described by synseg_img: `batch` images of
  *    height x width, `row_stride` / `batch_stride` in BYTES.  RGB images are interleaved HWC
  *    (3 bytes per pixel; width counts pixels).  Any stride/alignment is accepted; rows whose base
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SYNSEG_VERSION 100
+#define SYNSEG_VERSION 200
 
 #define SYNSEG_OK 0
 #define SYNSEG_E_INVALID (-1)   /* bad argument */
@@ -156,15 +158,19 @@ typedef struct synseg_detect_params {
     int32_t canny_hi;     /* 150 (S:1324) */
     int32_t k;            /* dilate / close square size     : int(10*dpi/72)|1 -> 41 @300 DPI */
     int32_t max_labels;   /* capacity of stats / centroids per page */
+    int32_t channels;     /* 3 (or 0): interleaved RGB pages; 1: grey ('L') pages -- the handoff of S:3638-3657 may be RGB or L, and
+                             detection reads grey only (a renderer that produces 'L' saves two thirds of the PCIe bytes) */
+    int32_t _pad;
 } synseg_detect_params;
 
-/* rgb pages -> component boxes:  grey(cv2) -> adaptive(INV) | Canny -> dilate(k) -> close(k) -> CCL(8)+stats.
+/* pages -> component boxes:  grey(cv2) -> adaptive(INV) | Canny -> dilate(k) -> close(k) -> CCL(8)+stats.
  * Same outputs as synseg_ccl_stats (labels omitted).  Bit-exact with the cv2 chain of SURVEY.md 8(d).
- * gray_out may be NULL; if given it receives the cv2 grey pages (kept for downstream features). */
+ * `rgb` holds RGB pages (params->channels 3 or 0) or grey pages (params->channels 1: the chain starts at the threshold).
+ * gray_out may be NULL; if given (RGB pages only) it receives the cv2 grey pages (kept for downstream features). */
 int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *params,
                         const synseg_img *gray_out, int32_t *n_labels, int32_t *stats, double *centroids, void *stream);
 
-/* The same pipeline for pages in HOST memory (the rasterisation handoff of S:3638-3657: RGB u8, `row_stride` bytes per
+/* The same pipeline for pages in HOST memory (the rasterisation handoff of S:3638-3657: RGB or L u8 (params->channels), `row_stride` bytes per
  * row, `page_stride` bytes per page; pinned memory gives full PCIe speed and true copy/compute overlap, pageable
  * memory works but is staged by the driver).  The library copies `chunk_pages` pages at a time through three device
  * staging slots on its own copy stream, runs synseg_detect_pages on each chunk and copies the tables back to
@@ -179,8 +185,9 @@ int synseg_detect_pages_host(synseg_ctx *ctx, const void *host_rgb, int32_t widt
  * every component k >= 1 of `stats` (as written by synseg_detect_pages / synseg_ccl_stats) with
  * min_area <= w*h <= max_area, w >= min_w, h >= min_h is appended to rois[] (image, x, y, w, h) and
  * keys[] ((page_base + image) << 16 | k).  count: device int32 (must be zeroed by the caller before the
- * first call; appends are cumulative, capped at capacity).  Order inside rois[] is unspecified; keys
- * identify the entries. */
+ * first call; appends are cumulative).  Only the first `capacity` entries are stored; *count keeps counting, so
+ * *count > capacity afterwards signals the overflow (readers clamp it to capacity).  Order inside rois[] is
+ * unspecified; keys identify the entries. */
 int synseg_select_rois(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t batch, int32_t max_labels,
                        int64_t page_base, int32_t min_area, int32_t max_area, int32_t min_w, int32_t min_h,
                        synseg_roi *rois, uint64_t *keys, int32_t *count, int32_t capacity, void *stream);
@@ -188,6 +195,79 @@ int synseg_select_rois(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *
  * capacity): hashes[i] for i < *count. */
 int synseg_phash_indirect(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, const int32_t *count,
                           int32_t capacity, uint64_t *out, void *stream);
+
+/* ---- candidate regions (the box rules of the reference, on the device) ------------------------------------------------ */
+#define SYNSEG_REGION_CC 1          /* one large component: the analogue of an embedded-image rect (S:2876-2881)        */
+#define SYNSEG_REGION_CLUSTER 2     /* >= 3 small components clustered by the drawing rule (S:3559-3594), padded 10 pt  */
+#define SYNSEG_REGION_FLAG_LABELS 1     /* page has more components than max_labels: table truncated, no regions         */
+#define SYNSEG_REGION_FLAG_AMBIGUOUS 2  /* a rect pair lies within 1e-9 of the 100 pt cluster threshold: recompute on host */
+#define SYNSEG_REGION_FLAG_CAPACITY 4   /* more than max_regions regions: list truncated                                 */
+
+typedef struct synseg_region {
+    double x0, y0, x1, y1;        /* box in PDF points, top-left origin (BoundingBox, S:101-122)                        */
+    int32_t px, py, pw, ph;       /* the crop in page pixels: round(pt * dpi / 72) (S:3649), clamped to the page        */
+    int32_t kind;                 /* SYNSEG_REGION_CC | SYNSEG_REGION_CLUSTER                                           */
+    int32_t count;                /* CC: component area in pixels; CLUSTER: number of clustered components              */
+    uint64_t sum, sum_sq;         /* exact grey moments of the crop (PIL grey for RGB pages): np.var(L) of S:2988-2989  */
+} synseg_region;                  /* 72 bytes */
+
+typedef struct synseg_region_params {
+    double dpi;                   /* raster resolution: px = pt * dpi / 72                                              */
+    double page_width_pt, page_height_pt;
+    double min_extent_pt;         /* a CC region must exceed this in both directions (50 pt, S:3450)                    */
+    int32_t max_regions;          /* capacity of the region list per page (<= 1024)                                     */
+    int32_t _pad;
+} synseg_region_params;
+
+/* Component tables (as written by synseg_detect_pages / synseg_ccl_stats) -> candidate regions of every page + the grey
+ * moments of every region crop of `pages` (channels 3: RGB through PIL grey; 1: grey pages).  The device form of
+ * detector.py:candidate_regions: area / extent classes (S:3549, S:3450), greedy clustering of the small boxes
+ * (_cluster_drawings S:3559-3594, _drawing_distance S:3596-3618), padded cluster boxes (_detect_by_drawings S:3531-3555),
+ * duplicate rule (_overlaps_with_existing S:3620-3636).  Bit-identical with the host arithmetic; pages the device cannot
+ * decide exactly are flagged (SYNSEG_REGION_FLAG_*) and must be recomputed on the host from the table.
+ *   regions : synseg_region[batch][max_regions], n_regions / flags : int32[batch]  (all DEVICE). */
+int synseg_regions_from_stats(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t max_labels,
+                              const synseg_img *pages, int channels, const synseg_region_params *rparams,
+                              synseg_region *regions, int32_t *n_regions, int32_t *flags, void *stream);
+
+/* synseg_detect_pages + synseg_regions_from_stats in one call on one stream (device pages). centroids may be NULL. */
+int synseg_detect_regions(synseg_ctx *ctx, const synseg_img *pages, const synseg_detect_params *params,
+                          const synseg_region_params *rparams, int32_t *n_labels, int32_t *stats, double *centroids,
+                          synseg_region *regions, int32_t *n_regions, int32_t *flags, void *stream);
+
+/* The same for pages in HOST memory (see synseg_detect_pages_host): per page the library returns, in HOST memory,
+ *   n_regions_host int32[n_pages], flags_host int32[n_pages], regions_host synseg_region[n_pages][max_regions],
+ *   n_labels_host int32[n_pages] and stats_host int32[n_pages][max_labels][5] (both may be NULL: the table is only
+ *   needed to recompute flagged pages on the host). */
+int synseg_detect_regions_host(synseg_ctx *ctx, const void *host_pages, int32_t width, int32_t height, int64_t row_stride,
+                               int64_t page_stride, int32_t n_pages, const synseg_detect_params *params,
+                               const synseg_region_params *rparams, int32_t chunk_pages, int32_t *n_labels_host,
+                               int32_t *stats_host, synseg_region *regions_host, int32_t *n_regions_host, int32_t *flags_host,
+                               void *stream);
+
+/* ---- renderer-facing page slots (the rasterisation step before the path, S:3638-3657) ----------- */
+/* The reference renders a region with MuPDF, PNG-encodes it and decodes it again with PIL (S:3651-3655).  Here a
+ * rasteriser writes its pages (RGB or L, params->channels) STRAIGHT into pinned host memory owned by the library:
+ *   synseg_page_slots_init    allocates n_slots (2..4) pinned page buffers of pages_per_slot pages (rows padded to 16
+ *                             bytes) on the GPU's NUMA node, their device staging buffers and pinned result buffers;
+ *   synseg_page_slot_acquire  returns the next slot whose previous submission has been waited for: the pointer to write
+ *                             pages into and its strides;
+ *   synseg_page_slot_submit   queues H2D (own copy stream), detection, regions + moments and the D2H of the results for
+ *                             the first n_pages pages of the slot; returns at once;
+ *   synseg_page_slot_wait     blocks until that submission has finished and hands out the slot's result arrays (valid
+ *                             until the slot is acquired again): n_regions / flags / n_labels int32[n_pages],
+ *                             regions synseg_region[n_pages][max_regions], stats int32[n_pages][max_labels][5];
+ *   synseg_page_slots_release frees everything (also done by synseg_destroy). */
+int synseg_page_slots_init(synseg_ctx *ctx, int32_t width, int32_t height, int32_t channels, int32_t pages_per_slot,
+                           int32_t n_slots, int32_t max_labels, int32_t max_regions);
+int synseg_page_slot_acquire(synseg_ctx *ctx, int32_t *slot, void **host_pages, int64_t *row_stride, int64_t *page_stride);
+int synseg_page_slot_submit(synseg_ctx *ctx, int32_t slot, int32_t n_pages, const synseg_detect_params *params,
+                            const synseg_region_params *rparams, void *stream);
+int synseg_page_slot_wait(synseg_ctx *ctx, int32_t slot, const int32_t **n_regions, const int32_t **flags,
+                          const synseg_region **regions, const int32_t **n_labels, const int32_t **stats);
+int synseg_page_slots_release(synseg_ctx *ctx);
+/* NUMA node of the pinned slot memory (-1: unknown / single node) -- bench.py reports it. */
+int synseg_page_slots_numa_node(const synseg_ctx *ctx);
 
 /* Per-crop grid-line counts of _detect_grid (S:1546-1564) / _detect_chart_subtype (S:1365-1376):
  * grey (gray_mode) -> Canny(50,150) -> OPEN(kw x 1, it=2) and OPEN(1 x kh, it=2) -> non-zero counts.

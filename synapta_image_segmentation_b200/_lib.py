@@ -28,7 +28,25 @@ class Crop(C.Structure):
 class DetectParams(C.Structure):
     """synseg_detect_params"""
     _fields_ = [("block_size", C.c_int32), ("C", C.c_int32), ("canny_lo", C.c_int32), ("canny_hi", C.c_int32),
-                ("k", C.c_int32), ("max_labels", C.c_int32)]
+                ("k", C.c_int32), ("max_labels", C.c_int32), ("channels", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Region(C.Structure):
+    """synseg_region (72 bytes)"""
+    _fields_ = [("x0", C.c_double), ("y0", C.c_double), ("x1", C.c_double), ("y1", C.c_double),
+                ("px", C.c_int32), ("py", C.c_int32), ("pw", C.c_int32), ("ph", C.c_int32),
+                ("kind", C.c_int32), ("count", C.c_int32), ("sum", C.c_uint64), ("sum_sq", C.c_uint64)]
+
+
+class RegionParams(C.Structure):
+    """synseg_region_params"""
+    _fields_ = [("dpi", C.c_double), ("page_width_pt", C.c_double), ("page_height_pt", C.c_double), ("min_extent_pt", C.c_double),
+                ("max_regions", C.c_int32), ("_pad", C.c_int32)]
+
+
+REGION_BYTES = 72
+REGION_CC, REGION_CLUSTER = 1, 2
+FLAG_LABELS, FLAG_AMBIGUOUS, FLAG_CAPACITY = 1, 2, 4
 
 
 # name -> (restype, argtypes); mirrors include/synseg.h declaration by declaration
@@ -59,6 +77,18 @@ SIGNATURES = {
     "synseg_detect_pages": (C.c_int, [C.c_void_p, _P(Img), _P(DetectParams), _P(Img), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_detect_pages_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P(DetectParams), C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_regions_from_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _P(Img), C.c_int, _P(RegionParams), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
+    "synseg_detect_regions": (C.c_int, [C.c_void_p, _P(Img), _P(DetectParams), _P(RegionParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_detect_regions_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P(DetectParams),
+                                             _P(RegionParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_page_slots_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "synseg_page_slot_acquire": (C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_void_p), _P(C.c_int64), _P(C.c_int64)]),
+    "synseg_page_slot_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _P(DetectParams), _P(RegionParams), C.c_void_p]),
+    "synseg_page_slot_wait": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p)]),
+    "synseg_page_slots_release": (C.c_int, [C.c_void_p]),
+    "synseg_page_slots_numa_node": (C.c_int, [C.c_void_p]),
     "synseg_hints_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "synseg_colors_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),

@@ -343,6 +343,7 @@ int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u
 extern "C" SYNSEG_EXPORT int synseg_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges, int lo, int hi, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_canny: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(gray, "gray", 1));
     SS_TRY(validate_img(edges, "edges", 1));
     if (!same_shape(gray, edges)) { synseg_set_error("synseg_canny: shape mismatch"); return SYNSEG_E_INVALID; }

@@ -541,12 +541,16 @@ __global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int bat
     const int area = a.area[i];
     if (area > 0) {
         s[0] = a.minx[i]; s[1] = a.miny[i]; s[2] = a.maxx[i] - a.minx[i] + 1; s[3] = a.maxy[i] - a.miny[i] + 1; s[4] = area;
-        centroids[2 * i] = (double)a.sumx[i] / (double)area;
-        centroids[2 * i + 1] = (double)a.sumy[i] / (double)area;
+        if (centroids) {
+            centroids[2 * i] = (double)a.sumx[i] / (double)area;
+            centroids[2 * i + 1] = (double)a.sumy[i] / (double)area;
+        }
     } else {   // only possible for the background of an all-foreground image; cv2 4.13 reports exactly this row
         s[0] = -1; s[1] = 0x7fffffff; s[2] = 0; s[3] = 0; s[4] = 0;
-        centroids[2 * i] = __longlong_as_double(0x7ff8000000000000LL);
-        centroids[2 * i + 1] = __longlong_as_double(0x7ff8000000000000LL);
+        if (centroids) {
+            centroids[2 * i] = __longlong_as_double(0x7ff8000000000000LL);
+            centroids[2 * i + 1] = __longlong_as_double(0x7ff8000000000000LL);
+        }
     }
 }
 
@@ -766,6 +770,7 @@ extern "C" SYNSEG_EXPORT int synseg_ccl_stats(synseg_ctx *ctx, const synseg_img 
                                 int32_t *stats, double *centroids, int32_t max_labels, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_ccl_stats: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(mask, "mask", 1));
     if (labels) {
         SS_TRY(validate_img(labels, "labels", 4));

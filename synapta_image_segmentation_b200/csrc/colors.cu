@@ -275,6 +275,7 @@ extern "C" SYNSEG_EXPORT int synseg_colors_crops(synseg_ctx *ctx, const void *ba
                                                  int32_t iters, int32_t min_pixels, uint64_t *out, uint32_t *hist_out, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_colors_crops: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (n <= 0) return SYNSEG_OK;
     if (!base || !crops_host || !out) { synseg_set_error("synseg_colors_crops: NULL argument"); return SYNSEG_E_INVALID; }
     if (n_colors < 1 || n_colors > CMAXK || iters < 0) { synseg_set_error("synseg_colors_crops: need 1 <= n_colors <= %d, iters >= 0", CMAXK); return SYNSEG_E_INVALID; }

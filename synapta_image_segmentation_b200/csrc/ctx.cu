@@ -32,7 +32,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     int count = 0;
     SS_CUDA(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) { synseg_set_error("synseg_create: no CUDA device %d", device); return SYNSEG_E_INVALID; }
-    SS_CUDA(cudaSetDevice(device));
+    DeviceScope scope(device);          // the caller's current device is restored on return
     cudaDeviceProp prop;
     SS_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -44,6 +44,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->arena = nullptr; c->arena_bytes = 0; c->arena_top = 0; c->launches = 0; c->phash_basis = nullptr;
     c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
+    c->attr_done = 0; c->last_stream = nullptr; c->ev_last = nullptr; c->last_valid = false;
     memset(&c->hs, 0, sizeof(c->hs));
     const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
     c->tune_ad_band = e1 ? atoi(e1) : 0;
@@ -63,7 +64,8 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
         for (int x = 0; x < 32; ++x) basis[u * 32 + x] = (int32_t)lround(16384.0 * cos(M_PI * (2 * x + 1) * u / 64.0));
     int rc = synseg_check_cuda(cudaMalloc(&c->phash_basis, sizeof(basis)), "cudaMalloc(phash basis)");
     if (!rc) rc = synseg_check_cuda(cudaMemcpy(c->phash_basis, basis, sizeof(basis), cudaMemcpyHostToDevice), "cudaMemcpy(basis)");
-    if (rc) { delete c; return rc; }
+    if (!rc) rc = synseg_check_cuda(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming), "cudaEventCreate(ev_last)");
+    if (rc) { if (c->phash_basis) cudaFree(c->phash_basis); delete c; return rc; }
     *out = c;
     return SYNSEG_OK;
 }
@@ -71,8 +73,9 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
 extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
 {
     if (!ctx) return SYNSEG_OK;
-    cudaSetDevice(ctx->device);
+    DeviceScope scope(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->phash_basis) cudaFree(ctx->phash_basis);
     host_stream_release(ctx);
@@ -94,7 +97,7 @@ void arena_begin(synseg_ctx *ctx) { ctx->arena_top = 0; }
 int arena_ensure(synseg_ctx *ctx, size_t bytes)
 {
     if (bytes <= ctx->arena_bytes) return SYNSEG_OK;
-    SS_CUDA(cudaSetDevice(ctx->device));
+    DeviceScope scope(ctx->device);
     SS_CUDA(cudaDeviceSynchronize());
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
     size_t want = align_up(bytes, (size_t)1 << 20);
@@ -172,6 +175,7 @@ void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st)
 extern "C" SYNSEG_EXPORT int synseg_profile_begin(synseg_ctx *ctx, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_profile_begin: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (!ctx->prof_start) SS_CUDA(cudaEventCreate(&ctx->prof_start));
     ctx->prof_used = 0;
     ctx->prof_on = true;

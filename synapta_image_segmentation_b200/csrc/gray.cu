@@ -301,6 +301,7 @@ int launch_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gr
 extern "C" SYNSEG_EXPORT int synseg_rgb2gray(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, int mode, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_rgb2gray: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(rgb, "rgb", 3));
     SS_TRY(validate_img(gray, "gray", 1));
     if (!same_shape(rgb, gray)) { synseg_set_error("synseg_rgb2gray: shape mismatch"); return SYNSEG_E_INVALID; }

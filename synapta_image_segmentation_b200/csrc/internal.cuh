@@ -30,6 +30,12 @@ struct synseg_ctx {
     size_t arena_top;     // bump pointer, reset at the start of every public call
     int64_t launches;     // kernels launched through this context
     int32_t *phash_basis; // device int32[8*32]
+    uint32_t attr_done;   // ATTR_* bits: cudaFuncSetAttribute calls already made on THIS device (the attribute is per device)
+    // stream ordering of the shared scratch arena: every public call records `ev_last` on its stream when it returns; a
+    // call arriving on a different stream first waits for it (SS_ENTER)
+    cudaStream_t last_stream;
+    cudaEvent_t ev_last;
+    bool last_valid;
     int tune_ad_band;     // experiment knobs (env SYNSEG_TUNE_AD_BAND / SYNSEG_TUNE_CANNY_BAND), 0 = automatic
     int tune_canny_band;
     // Stage overlap inside synseg_detect_pages (pipeline.cu): side streams owned by the context, forked from and joined
@@ -38,16 +44,35 @@ struct synseg_ctx {
     int overlap_streams;                    // env SYNSEG_STREAMS: the caller's stream + up to 3 side streams (default 2)
     cudaStream_t aux[3];                    // side streams (created on first use)
     cudaEvent_t ev_split_fork, ev_split_join[3];
-    // host-buffer streaming (synseg_detect_pages_host): device staging ring + copy stream, created on first use
+    // host-buffer streaming (synseg_detect_pages_host / synseg_detect_regions_host / page slots): device staging ring +
+    // copy stream, created on first use.  Ring slots rotate ACROSS calls and carry their own `done` event, so the first
+    // copies of a call only wait for the work that last used the same slot (not for everything queued before).
     struct HostStream {
+        static constexpr int MAXS = 4;
         cudaStream_t copy;                 // H2D stream
-        uint8_t *pages[3];                 // staging slots for `slot_pages` pages each
-        int32_t *n_labels[3], *stats[3];
-        double *centroids[3];
-        cudaEvent_t copied[3], done[3];
+        uint8_t *pages[MAXS];              // staging slots for `slot_pages` pages each
+        int32_t *n_labels[MAXS], *stats[MAXS];
+        int32_t *n_regions[MAXS];          // n_regions[slot_pages] followed by flags[slot_pages]
+        double *centroids[MAXS];
+        synseg_region *regions[MAXS];
+        cudaEvent_t copied[MAXS], done[MAXS];
+        bool used[MAXS];                   // `done` has been recorded at least once
+        int next;                          // next ring slot
         size_t slot_bytes;                 // bytes per page slot buffer
-        int slot_pages, max_labels;
+        int slot_pages, max_labels, max_regions;
         bool ready;
+        // renderer-facing pinned page slots (synseg_page_slot_*)
+        struct PageSlot {
+            uint8_t *pages;                // pinned host pages
+            int32_t *ints;                 // pinned: n_labels | n_regions | flags, ps_pages each
+            int32_t *stats;                // pinned
+            synseg_region *regions;        // pinned
+            cudaEvent_t finished;
+            int state;                     // 0 free, 1 acquired, 2 submitted
+            int n_pages;
+        } ps[MAXS];
+        int ps_n, ps_next, ps_width, ps_height, ps_channels, ps_pages, ps_max_labels, ps_max_regions, ps_numa;
+        int64_t ps_row_stride, ps_page_stride;
     } hs;
     // optional per-kernel timing (synseg_profile_*): one event after every launch on the profiled stream
     bool prof_on;
@@ -55,6 +80,40 @@ struct synseg_ctx {
     std::vector<cudaEvent_t> prof_events;
     std::vector<const char *> prof_names;
     size_t prof_used;
+};
+
+enum : uint32_t { ATTR_BITMORPH_H = 1u, ATTR_BITMORPH_VH = 2u, ATTR_BITMORPH_V = 4u, ATTR_MORPH_U8_H = 8u, ATTR_MORPH_U8_V = 16u, ATTR_HSV_HIST = 32u,
+                  ATTR_FRONT = 64u, ATTR_MORPH2D = 128u };
+
+// Entry guard of every public call that queues work (SS_ENTER below):
+//  * makes the context's device current for the duration of the call and restores the caller's device afterwards
+//    (a context for GPU 1 used under current device 0 must neither change the caller's device nor mix devices);
+//  * orders the call behind the previous call on this context when that one was issued to a DIFFERENT stream -- all calls
+//    share one scratch arena, so two in-flight calls are only safe when the second waits for the first.
+struct CallGuard {
+    synseg_ctx *c;
+    cudaStream_t st;
+    int prev;
+    bool switched;
+    CallGuard(synseg_ctx *ctx, cudaStream_t stream) : c(ctx), st(stream), prev(-1), switched(false)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) { cudaSetDevice(c->device); switched = true; }
+        if (c->last_valid && c->last_stream != st && c->ev_last) cudaStreamWaitEvent(st, c->ev_last, 0);
+    }
+    ~CallGuard()
+    {
+        if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
+        else cudaGetLastError();
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define SS_ENTER(ctx, stream) CallGuard _ss_guard((ctx), (cudaStream_t)(stream))
+
+// Restores the caller's current device (for the few internal paths that must call cudaSetDevice outside SS_ENTER).
+struct DeviceScope {
+    int prev; bool switched;
+    explicit DeviceScope(int dev) : prev(-1), switched(false) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); switched = true; } }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
 };
 
 void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st);
@@ -188,6 +247,12 @@ struct CropTask {
 };
 int launch_crop_front(synseg_ctx *ctx, const void *base, const CropTask *tasks, int n, const synseg_img *gray_canvas, uint64_t *res,
                       cudaStream_t st);
+
+// regions.cu: component tables -> candidate regions + crop moments (the arena must hold regions_scratch_bytes from its top)
+size_t regions_scratch_bytes(int batch, int max_labels);
+int validate_region_params(const synseg_region_params *rp, const char *who);
+int run_regions(synseg_ctx *ctx, const int32_t *n_labels, const int32_t *stats, int32_t max_labels, const synseg_img *pages, int channels,
+                const synseg_region_params *rp, synseg_region *regions, int32_t *n_regions, int32_t *flags, cudaStream_t st);
 
 int launch_moments(synseg_ctx *ctx, const synseg_img *src, int src_kind, const synseg_roi *rois, int32_t n_rois,
                    uint64_t *out, cudaStream_t st);

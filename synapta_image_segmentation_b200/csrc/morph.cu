@@ -521,8 +521,9 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
     const int padw = cdiv(k, 32) + 1;
     const size_t smem = (size_t)8 * 2 * (nw + 2 * padw + 1) * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_h: row too wide for shared memory"); return SYNSEG_E_INVALID; }
-    static bool attr_set = false;
-    if (!attr_set) { SS_CUDA(cudaFuncSetAttribute(bitmorph_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (!(ctx->attr_done & ATTR_BITMORPH_H)) {     // the attribute is per device: remembered per context, not per process
+        SS_CUDA(cudaFuncSetAttribute(bitmorph_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); ctx->attr_done |= ATTR_BITMORPH_H;
+    }
     const int64_t rows = (int64_t)height * batch;
     int grid = (int)((rows + 7) / 8);
     const int maxg = ctx->sm_count * 8;
@@ -540,8 +541,9 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
         const int T = k <= 190 ? 256 : 128;
         const int nseg = cdiv(height, k);
         const int64_t total = (int64_t)nw * nseg * batch;
-        static bool vh_attr = false;
-        if (!vh_attr) { SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); vh_attr = true; }
+        if (!(ctx->attr_done & ATTR_BITMORPH_VH)) {
+            SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); ctx->attr_done |= ATTR_BITMORPH_VH;
+        }
         bitmorph_v_vh_kernel<<<(unsigned)cdiv(total, T), T, (size_t)k * T * sizeof(uint32_t), st>>>(src, dst, width, height, nw, nseg, total,
                                                                                                    op == SYNSEG_MORPH_ERODE, k, anchor);
         SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
@@ -550,8 +552,9 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
     if (src.dims) { synseg_set_error("bitmorph_v: ragged batches need k <= 384"); return SYNSEG_E_INVALID; }
     const size_t smem = (size_t)(BV_TH + k - 1) * 32 * sizeof(uint32_t);
     if (smem > 200 * 1024) { synseg_set_error("bitmorph_v: kernel height %d too large", k); return SYNSEG_E_INVALID; }
-    static bool attr_set = false;
-    if (!attr_set) { SS_CUDA(cudaFuncSetAttribute(bitmorph_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (!(ctx->attr_done & ATTR_BITMORPH_V)) {
+        SS_CUDA(cudaFuncSetAttribute(bitmorph_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); ctx->attr_done |= ATTR_BITMORPH_V;
+    }
     dim3 grid(cdiv(nw, 32), cdiv(height, BV_TH), batch);
     bitmorph_v_kernel<<<grid, 32, smem, st>>>(src, dst, width, height, nw, op == SYNSEG_MORPH_ERODE, k, anchor);
     SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
@@ -592,11 +595,10 @@ int launch_morph_u8_h(synseg_ctx *ctx, const synseg_img *src, const synseg_img *
     pitch_w |= 1;
     const size_t smem = (size_t)U8H_ROWS * pitch_w * 4;
     if (smem > 200 * 1024) { synseg_set_error("morph: kernel width %d too large", k); return SYNSEG_E_INVALID; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & ATTR_MORPH_U8_H)) {
         SS_CUDA(cudaFuncSetAttribute(morph_u8_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SS_CUDA(cudaFuncSetAttribute(morph_u8_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        ctx->attr_done |= ATTR_MORPH_U8_H;
     }
     for (int b = 0; b < src->batch; ++b) {
         Plane s = plane_of(src), d = plane_of(dst);
@@ -613,11 +615,10 @@ int launch_morph_u8_v(synseg_ctx *ctx, const synseg_img *src, const synseg_img *
 {
     const size_t smem = (size_t)(U8V_TH + k - 1) * 32 * 4;
     if (smem > 200 * 1024) { synseg_set_error("morph: kernel height %d too large", k); return SYNSEG_E_INVALID; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & ATTR_MORPH_U8_V)) {
         SS_CUDA(cudaFuncSetAttribute(morph_u8_v_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SS_CUDA(cudaFuncSetAttribute(morph_u8_v_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        ctx->attr_done |= ATTR_MORPH_U8_V;
     }
     dim3 grid(cdiv(src->width, 128), cdiv(src->height, U8V_TH), src->batch);
     if (op == SYNSEG_MORPH_DILATE) morph_u8_v_kernel<true><<<grid, 32, smem, st>>>(plane_of(src), plane_of(dst), src->width, src->height, k, anchor);
@@ -630,6 +631,7 @@ extern "C" SYNSEG_EXPORT int synseg_morph(synseg_ctx *ctx, const synseg_img *src
                             int iterations, int flags, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_morph: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(src, "src", 1));
     SS_TRY(validate_img(dst, "dst", 1));
     if (!same_shape(src, dst)) { synseg_set_error("synseg_morph: shape mismatch"); return SYNSEG_E_INVALID; }

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) select_rois_kernel(const int32_t *n_label
     const long long box = (long long)w * h;
     if (box < min_area || box > max_area || w < min_w || h < min_h) return;
     const int slot = atomicAdd(count, 1);
-    if (slot >= capacity) { atomicSub(count, 1); return; }
+    if (slot >= capacity) return;        // *count keeps counting: count > capacity tells the caller that entries were dropped
     synseg_roi r; r.image = img; r.x = s[0]; r.y = s[1]; r.width = w; r.height = h;
     rois[slot] = r;
     keys[slot] = ((unsigned long long)(page_base + img) << 16) | (unsigned long long)k;
@@ -210,6 +210,7 @@ extern "C" SYNSEG_EXPORT int synseg_select_rois(synseg_ctx *ctx, const int32_t *
                                                 void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_select_rois: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (!n_labels || !stats || !rois || !keys || !count || batch <= 0 || max_labels < 1 || capacity < 1 || max_labels > 65535) {
         synseg_set_error("synseg_select_rois: bad arguments"); return SYNSEG_E_INVALID;
     }
@@ -224,6 +225,7 @@ extern "C" SYNSEG_EXPORT int synseg_phash_indirect(synseg_ctx *ctx, const synseg
                                                    const int32_t *count, int32_t capacity, uint64_t *out, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_phash_indirect: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (src_kind < 0 || src_kind > 2) { synseg_set_error("synseg_phash_indirect: bad src_kind %d", src_kind); return SYNSEG_E_INVALID; }
     SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
     if (!rois || !count || !out || capacity < 1) { synseg_set_error("synseg_phash_indirect: bad arguments"); return SYNSEG_E_INVALID; }
@@ -236,6 +238,7 @@ extern "C" SYNSEG_EXPORT int synseg_phash(synseg_ctx *ctx, const synseg_img *src
                             void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_phash: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (src_kind < 0 || src_kind > 2) { synseg_set_error("synseg_phash: bad src_kind %d", src_kind); return SYNSEG_E_INVALID; }
     SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
     if (!out) { synseg_set_error("synseg_phash: out is NULL"); return SYNSEG_E_INVALID; }
@@ -255,6 +258,7 @@ extern "C" SYNSEG_EXPORT int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t 
                                   uint8_t *keep, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_phash_dedup: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (n <= 0) return SYNSEG_OK;
     if (!hashes || !keys || !keep) { synseg_set_error("synseg_phash_dedup: NULL buffer"); return SYNSEG_E_INVALID; }
     SS_CUDA(cudaMemsetAsync(keep, 1, (size_t)n, (cudaStream_t)stream));

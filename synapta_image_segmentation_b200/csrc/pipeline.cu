@@ -49,14 +49,17 @@ static int overlap_streams(synseg_ctx *ctx)
 }
 
 // One chain over the pages of `rgb` on stream `st`, scratch from the arena at `arena_base`.
+// channels 1: `rgb` holds grey pages and the chain starts at the threshold (nothing is converted or copied).
 static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
                         int32_t *n_labels, int32_t *stats, double *centroids, cudaStream_t st, size_t arena_base)
 {
     const int W = rgb->width, H = rgb->height, B = rgb->batch;
+    const bool grey_in = prm->channels == 1;
     ctx->arena_top = arena_base;
     void *p;
     synseg_img gray;
-    if (gray_out) gray = *gray_out;
+    if (grey_in) gray = *rgb;
+    else if (gray_out) gray = *gray_out;
     else {
         gray = *rgb;
         gray.row_stride = (int64_t)align_up((size_t)W, 16);
@@ -71,7 +74,7 @@ static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_det
     SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
     BitPlane other{(uint32_t *)p, wpr, (int64_t)wpr * H};
 
-    SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
+    if (!grey_in) SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
     SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
     const size_t mark = arena_mark(ctx);
     SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
@@ -84,25 +87,31 @@ static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_det
     return run_ccl_stats(ctx, m, nullptr, n_labels, stats, centroids, prm->max_labels, st);
 }
 
-extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
-                                   int32_t *n_labels, int32_t *stats, double *centroids, void *stream)
+static int check_detect_args(const char *who, const synseg_img *pages, const synseg_detect_params *prm, const synseg_img *gray_out)
 {
-    if (!ctx || !prm) { synseg_set_error("synseg_detect_pages: NULL ctx/params"); return SYNSEG_E_INVALID; }
-    SS_TRY(validate_img(rgb, "rgb", 3));
+    if (prm->channels != 0 && prm->channels != 1 && prm->channels != 3) { synseg_set_error("%s: channels must be 3 (RGB) or 1 (grey)", who); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(pages, "pages", prm->channels == 1 ? 1 : 3));
     if (gray_out) {
+        if (prm->channels == 1) { synseg_set_error("%s: gray_out is meaningless for grey pages", who); return SYNSEG_E_INVALID; }
         SS_TRY(validate_img(gray_out, "gray_out", 1));
-        if (!same_shape(rgb, gray_out)) { synseg_set_error("synseg_detect_pages: gray_out shape mismatch"); return SYNSEG_E_INVALID; }
+        if (!same_shape(pages, gray_out)) { synseg_set_error("%s: gray_out shape mismatch", who); return SYNSEG_E_INVALID; }
     }
-    if (!n_labels || !stats || !centroids) { synseg_set_error("synseg_detect_pages: NULL result buffer"); return SYNSEG_E_INVALID; }
     if (prm->block_size < 3 || prm->block_size > 255 || !(prm->block_size & 1) || prm->k < 1 || prm->max_labels < 1 || prm->canny_lo < 0 ||
         prm->canny_hi < prm->canny_lo) {
-        synseg_set_error("synseg_detect_pages: bad parameters"); return SYNSEG_E_INVALID;
+        synseg_set_error("%s: bad parameters", who); return SYNSEG_E_INVALID;
     }
+    if (pages->width > 32766 || pages->height > 32766 || pages->batch > 65535) { synseg_set_error("%s: image or batch too large", who); return SYNSEG_E_INVALID; }
+    return SYNSEG_OK;
+}
+
+// The chains of one call; on return every side stream has been joined into `st` -- also when a launch failed in between.
+static int detect_pages_impl(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
+                             int32_t *n_labels, int32_t *stats, double *centroids, cudaStream_t st, size_t extra_scratch)
+{
     const int W = rgb->width, H = rgb->height, B = rgb->batch;
-    if (W > 32766 || H > 32766 || B > 65535) { synseg_set_error("synseg_detect_pages: image or batch too large"); return SYNSEG_E_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
     const int chunks = ctx->prof_on ? 1 : ctx->overlap;      // per-kernel profiling needs every kernel alone on one stream
     const int ml = prm->max_labels;
+    const bool need_gray = gray_out == nullptr && prm->channels != 1;
     if (chunks >= 2 && B >= 2 * chunks) {
         // Page chunks as independent chains, dealt round-robin to the caller's stream and the context's side streams, each
         // stream with its own part of the arena: the latency-bound labelling of one chunk runs beside the issue- / HBM-bound
@@ -111,27 +120,64 @@ extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_i
         SS_TRY(overlap_streams(ctx));
         const int ns = chunks < ctx->overlap_streams ? chunks : ctx->overlap_streams;
         const int per = cdiv(B, chunks);
-        const size_t region = align_up(detect_scratch_bytes(W, H, per, ml, gray_out == nullptr), 256);
-        SS_TRY(arena_ensure(ctx, ns * region));
+        const size_t region = align_up(detect_scratch_bytes(W, H, per, ml, need_gray), 256);
+        const size_t total = ns * region;
+        SS_TRY(arena_ensure(ctx, total > extra_scratch ? total : extra_scratch));
         SS_CUDA(cudaEventRecord(ctx->ev_split_fork, st));
         for (int i = 1; i < ns; ++i) SS_CUDA(cudaStreamWaitEvent(ctx->aux[i - 1], ctx->ev_split_fork, 0));
-        for (int c = 0, p0 = 0; p0 < B; ++c, p0 += per) {
+        int rc = SYNSEG_OK;
+        for (int c = 0, p0 = 0; p0 < B && rc == SYNSEG_OK; ++c, p0 += per) {
             const int np = B - p0 < per ? B - p0 : per;
             const int lane = c % ns;
             synseg_img v = *rgb, g;
             v.data = (uint8_t *)rgb->data + (int64_t)p0 * rgb->batch_stride; v.batch = np;
             if (gray_out) { g = *gray_out; g.data = (uint8_t *)gray_out->data + (int64_t)p0 * gray_out->batch_stride; g.batch = np; }
-            SS_TRY(detect_chain(ctx, &v, prm, gray_out ? &g : nullptr, n_labels + p0, stats + (size_t)p0 * ml * 5, centroids + (size_t)p0 * ml * 2,
-                                lane ? ctx->aux[lane - 1] : st, lane * region));
+            rc = detect_chain(ctx, &v, prm, gray_out ? &g : nullptr, n_labels + p0, stats + (size_t)p0 * ml * 5,
+                              centroids ? centroids + (size_t)p0 * ml * 2 : nullptr, lane ? ctx->aux[lane - 1] : st, lane * region);
         }
-        for (int i = 1; i < ns; ++i) {
-            SS_CUDA(cudaEventRecord(ctx->ev_split_join[i - 1], ctx->aux[i - 1]));
-            SS_CUDA(cudaStreamWaitEvent(st, ctx->ev_split_join[i - 1], 0));
+        for (int i = 1; i < ns; ++i) {       // always join, so an error return never leaves a side stream running unordered
+            const int e1 = synseg_check_cuda(cudaEventRecord(ctx->ev_split_join[i - 1], ctx->aux[i - 1]), "join record");
+            const int e2 = e1 ? e1 : synseg_check_cuda(cudaStreamWaitEvent(st, ctx->ev_split_join[i - 1], 0), "join wait");
+            if (rc == SYNSEG_OK && e2) rc = e2;
         }
-        return SYNSEG_OK;
+        return rc;
     }
-    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(W, H, B, ml, gray_out == nullptr)));
+    const size_t need = detect_scratch_bytes(W, H, B, ml, need_gray);
+    SS_TRY(arena_ensure(ctx, need > extra_scratch ? need : extra_scratch));
     return detect_chain(ctx, rgb, prm, gray_out, n_labels, stats, centroids, st, 0);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_detect_pages(synseg_ctx *ctx, const synseg_img *rgb, const synseg_detect_params *prm, const synseg_img *gray_out,
+                                   int32_t *n_labels, int32_t *stats, double *centroids, void *stream)
+{
+    if (!ctx || !prm) { synseg_set_error("synseg_detect_pages: NULL ctx/params"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
+    SS_TRY(check_detect_args("synseg_detect_pages", rgb, prm, gray_out));
+    if (!n_labels || !stats || !centroids) { synseg_set_error("synseg_detect_pages: NULL result buffer"); return SYNSEG_E_INVALID; }
+    return detect_pages_impl(ctx, rgb, prm, gray_out, n_labels, stats, centroids, (cudaStream_t)stream, 0);
+}
+
+// pages -> component tables -> candidate regions with crop moments, one stream, no host round trip
+static int detect_regions_impl(synseg_ctx *ctx, const synseg_img *pages, const synseg_detect_params *prm, const synseg_region_params *rp,
+                               int32_t *n_labels, int32_t *stats, double *centroids, synseg_region *regions, int32_t *n_regions, int32_t *flags,
+                               cudaStream_t st)
+{
+    const int ch = prm->channels == 1 ? 1 : 3;
+    SS_TRY(detect_pages_impl(ctx, pages, prm, nullptr, n_labels, stats, centroids, st, regions_scratch_bytes(pages->batch, prm->max_labels)));
+    arena_begin(ctx);          // every chain has been joined into `st`: the region kernels follow them in stream order
+    return run_regions(ctx, n_labels, stats, prm->max_labels, pages, ch, rp, regions, n_regions, flags, st);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_detect_regions(synseg_ctx *ctx, const synseg_img *pages, const synseg_detect_params *prm,
+                                                   const synseg_region_params *rp, int32_t *n_labels, int32_t *stats, double *centroids,
+                                                   synseg_region *regions, int32_t *n_regions, int32_t *flags, void *stream)
+{
+    if (!ctx || !prm) { synseg_set_error("synseg_detect_regions: NULL ctx/params"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
+    SS_TRY(check_detect_args("synseg_detect_regions", pages, prm, nullptr));
+    SS_TRY(validate_region_params(rp, "synseg_detect_regions"));
+    if (!n_labels || !stats || !regions || !n_regions || !flags) { synseg_set_error("synseg_detect_regions: NULL result buffer"); return SYNSEG_E_INVALID; }
+    return detect_regions_impl(ctx, pages, prm, rp, n_labels, stats, centroids, regions, n_regions, flags, (cudaStream_t)stream);
 }
 
 // grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2) -> counts of ONE image (view->batch == 1).
@@ -187,6 +233,7 @@ extern "C" SYNSEG_EXPORT int synseg_grid_counts(synseg_ctx *ctx, const synseg_im
                                   int32_t n_rois, int kw, int kh, uint64_t *out, const synseg_img *edges_out, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_grid_counts: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (channels != 1 && channels != 3) { synseg_set_error("synseg_grid_counts: channels must be 1 or 3"); return SYNSEG_E_INVALID; }
     SS_TRY(validate_img(src, "src", channels));
     if (!out) { synseg_set_error("synseg_grid_counts: out is NULL"); return SYNSEG_E_INVALID; }
@@ -340,6 +387,7 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
                                   uint64_t *out, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_hints_crops: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (n <= 0) return SYNSEG_OK;
     if (!base || !crops_host || !out) { synseg_set_error("synseg_hints_crops: NULL argument"); return SYNSEG_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -378,16 +426,37 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
     return SYNSEG_OK;
 }
 
-// ---- host-buffer entry point ---------------------------------------------------------------------------------
+// ---- host-buffer entry points ---------------------------------------------------------------------------------
+#include <sys/syscall.h>
+#include <unistd.h>
+
+static void page_slots_free(synseg_ctx *ctx)
+{
+    synseg_ctx::HostStream &h = ctx->hs;
+    for (int i = 0; i < synseg_ctx::HostStream::MAXS; ++i) {
+        synseg_ctx::HostStream::PageSlot &q = h.ps[i];
+        if (q.pages) cudaFreeHost(q.pages);
+        if (q.ints) cudaFreeHost(q.ints);
+        if (q.stats) cudaFreeHost(q.stats);
+        if (q.regions) cudaFreeHost(q.regions);
+        if (q.finished) cudaEventDestroy(q.finished);
+        memset(&q, 0, sizeof(q));
+    }
+    h.ps_n = 0;
+}
+
 void host_stream_release(synseg_ctx *ctx)
 {
     synseg_ctx::HostStream &h = ctx->hs;
+    page_slots_free(ctx);
     if (!h.ready) return;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < synseg_ctx::HostStream::MAXS; ++i) {
         if (h.pages[i]) cudaFree(h.pages[i]);
         if (h.n_labels[i]) cudaFree(h.n_labels[i]);
         if (h.stats[i]) cudaFree(h.stats[i]);
+        if (h.n_regions[i]) cudaFree(h.n_regions[i]);
         if (h.centroids[i]) cudaFree(h.centroids[i]);
+        if (h.regions[i]) cudaFree(h.regions[i]);
         if (h.copied[i]) cudaEventDestroy(h.copied[i]);
         if (h.done[i]) cudaEventDestroy(h.done[i]);
     }
@@ -395,69 +464,285 @@ void host_stream_release(synseg_ctx *ctx)
     memset(&h, 0, sizeof(h));
 }
 
-static int host_stream_prepare(synseg_ctx *ctx, size_t slot_bytes, int slot_pages, int max_labels)
+constexpr int RING = 3;
+
+static int host_stream_prepare(synseg_ctx *ctx, size_t slot_bytes, int slot_pages, int max_labels, int max_regions)
 {
     synseg_ctx::HostStream &h = ctx->hs;
-    if (h.ready && h.slot_bytes >= slot_bytes && h.slot_pages >= slot_pages && h.max_labels == max_labels) return SYNSEG_OK;
-    SS_CUDA(cudaSetDevice(ctx->device));
+    if (h.ready && h.slot_bytes >= slot_bytes && h.slot_pages >= slot_pages && h.max_labels == max_labels && h.max_regions >= max_regions) return SYNSEG_OK;
+    if (h.ps_n) { synseg_set_error("host staging: the page slots are initialised with another geometry (release them first)"); return SYNSEG_E_INVALID; }
     SS_CUDA(cudaDeviceSynchronize());
+    if (h.ready) {
+        if (h.slot_bytes > slot_bytes) slot_bytes = h.slot_bytes;
+        if (h.slot_pages > slot_pages) slot_pages = h.slot_pages;
+        if (h.max_regions > max_regions) max_regions = h.max_regions;
+    }
     host_stream_release(ctx);
+    if (max_regions < 1) max_regions = 1;
     SS_CUDA(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < RING; ++i) {
         SS_CUDA(cudaMalloc(&h.pages[i], slot_bytes));
         SS_CUDA(cudaMalloc(&h.n_labels[i], sizeof(int32_t) * slot_pages));
         SS_CUDA(cudaMalloc(&h.stats[i], sizeof(int32_t) * 5 * (size_t)slot_pages * max_labels));
         SS_CUDA(cudaMalloc(&h.centroids[i], sizeof(double) * 2 * (size_t)slot_pages * max_labels));
+        SS_CUDA(cudaMalloc(&h.n_regions[i], sizeof(int32_t) * 2 * slot_pages));
+        SS_CUDA(cudaMalloc(&h.regions[i], sizeof(synseg_region) * (size_t)slot_pages * max_regions));
         SS_CUDA(cudaEventCreateWithFlags(&h.copied[i], cudaEventDisableTiming));
         SS_CUDA(cudaEventCreateWithFlags(&h.done[i], cudaEventDisableTiming));
     }
-    h.slot_bytes = slot_bytes; h.slot_pages = slot_pages; h.max_labels = max_labels; h.ready = true;
+    h.slot_bytes = slot_bytes; h.slot_pages = slot_pages; h.max_labels = max_labels; h.max_regions = max_regions; h.ready = true;
     return SYNSEG_OK;
 }
 
-// Pages in HOST memory (pinned for full PCIe speed and true overlap; pageable works, slower) -> component tables in
-// HOST memory.  The library stages the pages through three device slots of `chunk_pages` pages: a copy stream moves
-// chunk i+1, i+2 while the fused pipeline runs on chunk i and the tables of chunk i-1 travel back.  Returns after
-// everything is queued; `stream` is made to wait for the last chunk, so synchronising `stream` completes the call.
+// Row stride of staged pages on the device: RGB rows keep the host stride (rgb2gray takes any); grey rows are padded to
+// 16 bytes so that the stencils read them with 128-bit loads.
+static int64_t device_row_stride(int width, int channels, int64_t host_row_stride)
+{
+    return channels == 1 ? (int64_t)align_up((size_t)width, 16) : host_row_stride;
+}
+
+// np pages host -> device staging slot on the copy stream
+static int stage_pages(synseg_ctx *ctx, uint8_t *dst, const uint8_t *src, int width, int height, int channels, int64_t row_stride,
+                       int64_t page_stride, int np)
+{
+    cudaStream_t cs = ctx->hs.copy;
+    const int64_t dr = device_row_stride(width, channels, row_stride);
+    const size_t dpage = (size_t)dr * height;
+    if (row_stride == dr && page_stride == (int64_t)dpage) SS_CUDA(cudaMemcpyAsync(dst, src, dpage * np, cudaMemcpyHostToDevice, cs));
+    else if (row_stride == dr) SS_CUDA(cudaMemcpy2DAsync(dst, dpage, src, (size_t)page_stride, dpage, np, cudaMemcpyHostToDevice, cs));
+    else if (page_stride == row_stride * height)
+        SS_CUDA(cudaMemcpy2DAsync(dst, (size_t)dr, src, (size_t)row_stride, (size_t)width * channels, (size_t)height * np, cudaMemcpyHostToDevice, cs));
+    else
+        for (int i = 0; i < np; ++i)
+            SS_CUDA(cudaMemcpy2DAsync(dst + i * dpage, (size_t)dr, src + (int64_t)i * page_stride, (size_t)row_stride, (size_t)width * channels, height,
+                                      cudaMemcpyHostToDevice, cs));
+    return SYNSEG_OK;
+}
+
+struct HostOut {           // HOST result arrays of a job (any of them may be NULL), indexed from the job's first page
+    int32_t *n_labels, *stats;
+    double *centroids;
+    synseg_region *regions;
+    int32_t *n_regions, *flags;
+};
+
+// One chunk of pages already resident in ring slot s (its `copied` event recorded on the copy stream): pipeline + D2H on `st`.
+static int run_ring_slot(synseg_ctx *ctx, int s, int width, int height, int channels, int64_t host_row_stride, int np, const synseg_detect_params *prm,
+                         const synseg_region_params *rp, const HostOut &o, int p0, cudaStream_t st)
+{
+    synseg_ctx::HostStream &h = ctx->hs;
+    const int ml = prm->max_labels;
+    SS_CUDA(cudaStreamWaitEvent(st, h.copied[s], 0));
+    synseg_img img;
+    img.data = h.pages[s]; img.width = width; img.height = height; img.row_stride = device_row_stride(width, channels, host_row_stride);
+    img.batch = np; img._pad = 0; img.batch_stride = img.row_stride * height;
+    double *cen = o.centroids ? h.centroids[s] : nullptr;
+    if (rp) SS_TRY(detect_regions_impl(ctx, &img, prm, rp, h.n_labels[s], h.stats[s], cen, h.regions[s], h.n_regions[s], h.n_regions[s] + np, st));
+    else SS_TRY(detect_pages_impl(ctx, &img, prm, nullptr, h.n_labels[s], h.stats[s], cen, st, 0));
+    if (o.n_labels) SS_CUDA(cudaMemcpyAsync(o.n_labels + p0, h.n_labels[s], sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
+    if (o.stats) SS_CUDA(cudaMemcpyAsync(o.stats + (size_t)p0 * ml * 5, h.stats[s], sizeof(int32_t) * 5 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
+    if (o.centroids) SS_CUDA(cudaMemcpyAsync(o.centroids + (size_t)p0 * ml * 2, h.centroids[s], sizeof(double) * 2 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
+    if (rp) {
+        SS_CUDA(cudaMemcpyAsync(o.n_regions + p0, h.n_regions[s], sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
+        SS_CUDA(cudaMemcpyAsync(o.flags + p0, h.n_regions[s] + np, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
+        SS_CUDA(cudaMemcpyAsync(o.regions + (size_t)p0 * rp->max_regions, h.regions[s], sizeof(synseg_region) * (size_t)np * rp->max_regions,
+                                cudaMemcpyDeviceToHost, st));
+    }
+    SS_CUDA(cudaEventRecord(h.done[s], st));
+    h.used[s] = true;
+    return SYNSEG_OK;
+}
+
+// Pages in HOST memory (pinned for full PCIe speed and true overlap; pageable works, slower) -> results in HOST memory.
+// The library stages the pages through three device slots of `chunk_pages` pages: a copy stream moves chunk i+1, i+2
+// while the pipeline runs on chunk i and the results of chunk i-1 travel back.  Returns after everything is queued;
+// `stream` waits for the last chunk, so synchronising `stream` completes the call.
+static int host_pipeline(synseg_ctx *ctx, const char *who, const void *host_pages, int32_t width, int32_t height, int64_t row_stride, int64_t page_stride,
+                         int32_t n_pages, const synseg_detect_params *prm, const synseg_region_params *rp, int32_t chunk_pages, const HostOut &o,
+                         cudaStream_t st)
+{
+    const int ch = prm->channels == 1 ? 1 : 3;
+    if (prm->channels != 0 && prm->channels != 1 && prm->channels != 3) { synseg_set_error("%s: channels must be 3 (RGB) or 1 (grey)", who); return SYNSEG_E_INVALID; }
+    if (width <= 0 || height <= 0 || n_pages < 0 || chunk_pages <= 0 || row_stride < ch * (int64_t)width || page_stride < row_stride * height || prm->max_labels < 1) {
+        synseg_set_error("%s: bad shape / strides", who); return SYNSEG_E_INVALID;
+    }
+    if (n_pages == 0) return SYNSEG_OK;
+    if (chunk_pages > n_pages) chunk_pages = n_pages;
+    const size_t dpage = (size_t)device_row_stride(width, ch, row_stride) * height;
+    SS_TRY(host_stream_prepare(ctx, dpage * chunk_pages, chunk_pages, prm->max_labels, rp ? rp->max_regions : 1));
+    synseg_ctx::HostStream &h = ctx->hs;
+    // ring slots are private to the host entry points and every use ends with the slot's `done` event on the stream that
+    // computed on it; the copy stream waits for exactly that event before it overwrites the slot -- also across calls
+    const int n_chunks = cdiv(n_pages, chunk_pages);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s = h.next; h.next = (h.next + 1) % RING;
+        const int p0 = c * chunk_pages, np = (n_pages - p0 < chunk_pages) ? n_pages - p0 : chunk_pages;
+        if (h.used[s]) SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[s], 0));       // slot s free again (the chunk that used it last has finished)
+        SS_TRY(stage_pages(ctx, h.pages[s], (const uint8_t *)host_pages + (int64_t)p0 * page_stride, width, height, ch, row_stride, page_stride, np));
+        SS_CUDA(cudaEventRecord(h.copied[s], h.copy));
+        SS_TRY(run_ring_slot(ctx, s, width, height, ch, row_stride, np, prm, rp, o, p0, st));
+    }
+    return SYNSEG_OK;
+}
+
 extern "C" SYNSEG_EXPORT int synseg_detect_pages_host(synseg_ctx *ctx, const void *host_rgb, int32_t width, int32_t height,
                                         int64_t row_stride, int64_t page_stride, int32_t n_pages, const synseg_detect_params *prm,
                                         int32_t chunk_pages, int32_t *n_labels_host, int32_t *stats_host, double *centroids_host,
                                         void *stream)
 {
     if (!ctx || !prm || !host_rgb || !n_labels_host || !stats_host) { synseg_set_error("synseg_detect_pages_host: NULL argument"); return SYNSEG_E_INVALID; }
-    if (width <= 0 || height <= 0 || n_pages < 0 || chunk_pages <= 0 || row_stride < 3 * (int64_t)width || page_stride < row_stride * height || prm->max_labels < 1) {
-        synseg_set_error("synseg_detect_pages_host: bad shape / strides"); return SYNSEG_E_INVALID;
+    SS_ENTER(ctx, stream);
+    const HostOut o{n_labels_host, stats_host, centroids_host, nullptr, nullptr, nullptr};
+    return host_pipeline(ctx, "synseg_detect_pages_host", host_rgb, width, height, row_stride, page_stride, n_pages, prm, nullptr, chunk_pages, o,
+                         (cudaStream_t)stream);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_detect_regions_host(synseg_ctx *ctx, const void *host_pages, int32_t width, int32_t height, int64_t row_stride,
+                                                        int64_t page_stride, int32_t n_pages, const synseg_detect_params *prm,
+                                                        const synseg_region_params *rp, int32_t chunk_pages, int32_t *n_labels_host,
+                                                        int32_t *stats_host, synseg_region *regions_host, int32_t *n_regions_host,
+                                                        int32_t *flags_host, void *stream)
+{
+    if (!ctx || !prm || !host_pages || !regions_host || !n_regions_host || !flags_host) {
+        synseg_set_error("synseg_detect_regions_host: NULL argument"); return SYNSEG_E_INVALID;
     }
-    if (n_pages == 0) return SYNSEG_OK;
-    if (chunk_pages > n_pages) chunk_pages = n_pages;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ml = prm->max_labels;
-    const size_t page_bytes = (size_t)row_stride * height;            // pages are copied with their row stride, tightly per page
-    SS_TRY(host_stream_prepare(ctx, page_bytes * chunk_pages, chunk_pages, ml));
-    SS_TRY(arena_ensure(ctx, detect_scratch_bytes(width, height, chunk_pages, ml, true)));
+    SS_ENTER(ctx, stream);
+    SS_TRY(validate_region_params(rp, "synseg_detect_regions_host"));
+    const HostOut o{n_labels_host, stats_host, nullptr, regions_host, n_regions_host, flags_host};
+    return host_pipeline(ctx, "synseg_detect_regions_host", host_pages, width, height, row_stride, page_stride, n_pages, prm, rp, chunk_pages, o,
+                         (cudaStream_t)stream);
+}
+
+// ---- renderer-facing page slots ----------------------------------------------------------------------------------
+// NUMA node of the GPU (sysfs), -1 when unknown or the machine has a single node.
+static int gpu_numa_node(int device)
+{
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c += 'a' - 'A';
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0 || node >= 1024) return -1;
+    if (access("/sys/devices/system/node/node1", F_OK) != 0) return -1;     // single node: nothing to choose
+    return node;
+}
+
+// Pinned allocation whose pages are placed on `node` (set_mempolicy(MPOL_PREFERRED) around the allocation and the first
+// touch; cudaHostAlloc pins the pages where they are).  node < 0: plain cudaHostAlloc.
+static int pinned_alloc_on_node(void **out, size_t bytes, int node)
+{
+    unsigned long mask[16] = {0};
+    bool bound = false;
+    if (node >= 0) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8) == 0;
+    }
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    return synseg_check_cuda(e, "cudaHostAlloc(page slot)");
+}
+
+extern "C" SYNSEG_EXPORT int synseg_page_slots_release(synseg_ctx *ctx)
+{
+    if (!ctx) { synseg_set_error("synseg_page_slots_release: ctx is NULL"); return SYNSEG_E_INVALID; }
+    DeviceScope scope(ctx->device);
+    if (ctx->hs.ps_n) { cudaDeviceSynchronize(); page_slots_free(ctx); }
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_page_slots_numa_node(const synseg_ctx *ctx) { return ctx && ctx->hs.ps_n ? ctx->hs.ps_numa : -1; }
+
+extern "C" SYNSEG_EXPORT int synseg_page_slots_init(synseg_ctx *ctx, int32_t width, int32_t height, int32_t channels, int32_t pages_per_slot,
+                                                    int32_t n_slots, int32_t max_labels, int32_t max_regions)
+{
+    if (!ctx) { synseg_set_error("synseg_page_slots_init: ctx is NULL"); return SYNSEG_E_INVALID; }
+    if (width <= 0 || height <= 0 || (channels != 1 && channels != 3) || pages_per_slot < 1 || n_slots < 2 || n_slots > RING || max_labels < 1 ||
+        max_regions < 1 || max_regions > 1024) {
+        synseg_set_error("synseg_page_slots_init: bad arguments (channels 1 or 3, 2 <= n_slots <= %d)", RING); return SYNSEG_E_INVALID;
+    }
+    DeviceScope scope(ctx->device);
     synseg_ctx::HostStream &h = ctx->hs;
-    // the first copies must not overtake work the caller queued on `stream` that still reads the staging slots of a previous call
-    SS_CUDA(cudaEventRecord(h.done[0], st));
-    SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[0], 0));
-    const int n_chunks = cdiv(n_pages, chunk_pages);
-    for (int c = 0; c < n_chunks; ++c) {
-        const int s = c % 3;
-        const int p0 = c * chunk_pages, np = (n_pages - p0 < chunk_pages) ? n_pages - p0 : chunk_pages;
-        if (c >= 3) SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[s], 0));       // slot s free again (its chunk c-3 finished)
-        const uint8_t *src = (const uint8_t *)host_rgb + (int64_t)p0 * page_stride;
-        if (page_stride == (int64_t)page_bytes) SS_CUDA(cudaMemcpyAsync(h.pages[s], src, page_bytes * np, cudaMemcpyHostToDevice, h.copy));
-        else SS_CUDA(cudaMemcpy2DAsync(h.pages[s], page_bytes, src, (size_t)page_stride, page_bytes, np, cudaMemcpyHostToDevice, h.copy));
-        SS_CUDA(cudaEventRecord(h.copied[s], h.copy));
-        SS_CUDA(cudaStreamWaitEvent(st, h.copied[s], 0));
-        synseg_img img;
-        img.data = h.pages[s]; img.width = width; img.height = height; img.row_stride = row_stride; img.batch = np; img._pad = 0;
-        img.batch_stride = (int64_t)page_bytes;
-        SS_TRY(synseg_detect_pages(ctx, &img, prm, nullptr, h.n_labels[s], h.stats[s], h.centroids[s], stream));
-        SS_CUDA(cudaMemcpyAsync(n_labels_host + p0, h.n_labels[s], sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
-        SS_CUDA(cudaMemcpyAsync(stats_host + (size_t)p0 * ml * 5, h.stats[s], sizeof(int32_t) * 5 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
-        if (centroids_host)
-            SS_CUDA(cudaMemcpyAsync(centroids_host + (size_t)p0 * ml * 2, h.centroids[s], sizeof(double) * 2 * (size_t)np * ml, cudaMemcpyDeviceToHost, st));
-        SS_CUDA(cudaEventRecord(h.done[s], st));
+    if (h.ps_n) { cudaDeviceSynchronize(); page_slots_free(ctx); }
+    const int64_t rs = (int64_t)align_up((size_t)width * channels, 16);
+    const int64_t page = rs * height;
+    SS_TRY(host_stream_prepare(ctx, (size_t)device_row_stride(width, channels, rs) * height * pages_per_slot, pages_per_slot, max_labels, max_regions));
+    const int node = gpu_numa_node(ctx->device);
+    for (int i = 0; i < n_slots; ++i) {
+        synseg_ctx::HostStream::PageSlot &q = h.ps[i];
+        void *p;
+        SS_TRY(pinned_alloc_on_node(&p, (size_t)page * pages_per_slot, node)); q.pages = (uint8_t *)p;
+        SS_TRY(pinned_alloc_on_node(&p, sizeof(int32_t) * 3 * (size_t)pages_per_slot, node)); q.ints = (int32_t *)p;
+        SS_TRY(pinned_alloc_on_node(&p, sizeof(int32_t) * 5 * (size_t)pages_per_slot * max_labels, node)); q.stats = (int32_t *)p;
+        SS_TRY(pinned_alloc_on_node(&p, sizeof(synseg_region) * (size_t)pages_per_slot * max_regions, node)); q.regions = (synseg_region *)p;
+        SS_CUDA(cudaEventCreateWithFlags(&q.finished, cudaEventDisableTiming));
+        q.state = 0; q.n_pages = 0;
     }
+    h.ps_n = n_slots; h.ps_next = 0; h.ps_width = width; h.ps_height = height; h.ps_channels = channels; h.ps_pages = pages_per_slot;
+    h.ps_max_labels = max_labels; h.ps_max_regions = max_regions; h.ps_numa = node; h.ps_row_stride = rs; h.ps_page_stride = page;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_page_slot_acquire(synseg_ctx *ctx, int32_t *slot, void **host_pages, int64_t *row_stride, int64_t *page_stride)
+{
+    if (!ctx || !slot || !host_pages) { synseg_set_error("synseg_page_slot_acquire: NULL argument"); return SYNSEG_E_INVALID; }
+    synseg_ctx::HostStream &h = ctx->hs;
+    if (!h.ps_n) { synseg_set_error("synseg_page_slot_acquire: call synseg_page_slots_init first"); return SYNSEG_E_INVALID; }
+    synseg_ctx::HostStream::PageSlot &q = h.ps[h.ps_next];
+    if (q.state == 2) { synseg_set_error("synseg_page_slot_acquire: slot %d holds results nobody waited for (synseg_page_slot_wait)", h.ps_next); return SYNSEG_E_INVALID; }
+    q.state = 1;
+    *slot = h.ps_next; *host_pages = q.pages;
+    if (row_stride) *row_stride = h.ps_row_stride;
+    if (page_stride) *page_stride = h.ps_page_stride;
+    h.ps_next = (h.ps_next + 1) % h.ps_n;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_page_slot_submit(synseg_ctx *ctx, int32_t slot, int32_t n_pages, const synseg_detect_params *prm,
+                                                     const synseg_region_params *rp, void *stream)
+{
+    if (!ctx || !prm) { synseg_set_error("synseg_page_slot_submit: NULL argument"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
+    synseg_ctx::HostStream &h = ctx->hs;
+    if (slot < 0 || slot >= h.ps_n || h.ps[slot].state != 1) { synseg_set_error("synseg_page_slot_submit: slot %d was not acquired", slot); return SYNSEG_E_INVALID; }
+    if (n_pages < 1 || n_pages > h.ps_pages) { synseg_set_error("synseg_page_slot_submit: n_pages outside 1..%d", h.ps_pages); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_region_params(rp, "synseg_page_slot_submit"));
+    const int ch = prm->channels == 1 ? 1 : 3;
+    if (ch != h.ps_channels || prm->max_labels != h.ps_max_labels || rp->max_regions != h.ps_max_regions) {
+        synseg_set_error("synseg_page_slot_submit: channels / max_labels / max_regions differ from synseg_page_slots_init"); return SYNSEG_E_INVALID;
+    }
+    if (prm->block_size < 3 || prm->block_size > 255 || !(prm->block_size & 1) || prm->k < 1 || prm->canny_lo < 0 || prm->canny_hi < prm->canny_lo) {
+        synseg_set_error("synseg_page_slot_submit: bad parameters"); return SYNSEG_E_INVALID;
+    }
+    synseg_ctx::HostStream::PageSlot &q = h.ps[slot];
+    const int s = slot;                  // host slot i is staged through ring slot i (n_slots <= RING)
+    if (h.used[s]) SS_CUDA(cudaStreamWaitEvent(h.copy, h.done[s], 0));
+    SS_TRY(stage_pages(ctx, h.pages[s], q.pages, h.ps_width, h.ps_height, ch, h.ps_row_stride, h.ps_page_stride, n_pages));
+    SS_CUDA(cudaEventRecord(h.copied[s], h.copy));
+    const HostOut o{q.ints, q.stats, nullptr, q.regions, q.ints + h.ps_pages, q.ints + 2 * h.ps_pages};
+    SS_TRY(run_ring_slot(ctx, s, h.ps_width, h.ps_height, ch, h.ps_row_stride, n_pages, prm, rp, o, 0, (cudaStream_t)stream));
+    SS_CUDA(cudaEventRecord(q.finished, (cudaStream_t)stream));
+    q.state = 2; q.n_pages = n_pages;
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_page_slot_wait(synseg_ctx *ctx, int32_t slot, const int32_t **n_regions, const int32_t **flags,
+                                                   const synseg_region **regions, const int32_t **n_labels, const int32_t **stats)
+{
+    if (!ctx) { synseg_set_error("synseg_page_slot_wait: ctx is NULL"); return SYNSEG_E_INVALID; }
+    synseg_ctx::HostStream &h = ctx->hs;
+    if (slot < 0 || slot >= h.ps_n || h.ps[slot].state != 2) { synseg_set_error("synseg_page_slot_wait: slot %d was not submitted", slot); return SYNSEG_E_INVALID; }
+    synseg_ctx::HostStream::PageSlot &q = h.ps[slot];
+    SS_CUDA(cudaEventSynchronize(q.finished));
+    q.state = 0;
+    if (n_labels) *n_labels = q.ints;
+    if (n_regions) *n_regions = q.ints + h.ps_pages;
+    if (flags) *flags = q.ints + 2 * h.ps_pages;
+    if (regions) *regions = q.regions;
+    if (stats) *stats = q.stats;
     return SYNSEG_OK;
 }

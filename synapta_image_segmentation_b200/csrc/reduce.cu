@@ -186,6 +186,7 @@ extern "C" SYNSEG_EXPORT int synseg_moments(synseg_ctx *ctx, const synseg_img *s
                               uint64_t *out, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_moments: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     if (src_kind < 0 || src_kind > 2) { synseg_set_error("synseg_moments: bad src_kind %d", src_kind); return SYNSEG_E_INVALID; }
     SS_TRY(validate_img(src, "src", src_kind ? 3 : 1));
     if (!out) { synseg_set_error("synseg_moments: out is NULL"); return SYNSEG_E_INVALID; }
@@ -199,6 +200,7 @@ extern "C" SYNSEG_EXPORT int synseg_hsv_mask_hist(synseg_ctx *ctx, const synseg_
                                     uint32_t *hist, uint64_t *chan_sum, uint32_t *row_count, int32_t max_rows, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_hsv_mask_hist: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(rgb, "rgb", 3));
     if (!count) { synseg_set_error("synseg_hsv_mask_hist: count is NULL"); return SYNSEG_E_INVALID; }
     if (chan_sum && !hist) { synseg_set_error("synseg_hsv_mask_hist: chan_sum needs hist"); return SYNSEG_E_INVALID; }
@@ -212,10 +214,9 @@ extern "C" SYNSEG_EXPORT int synseg_hsv_mask_hist(synseg_ctx *ctx, const synseg_
     if (row_count) SS_CUDA(cudaMemsetAsync(row_count, 0, sizeof(uint32_t) * (size_t)max_rows * n_rois, st));
     const int gx = rois ? 8 : (rgb->height >= 1024 ? 32 : 8);
     const size_t smem = (256 + HBINS + (chan_sum ? 3 * HBINS : 0)) * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & ATTR_HSV_HIST)) {
         SS_CUDA(cudaFuncSetAttribute(hsv_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-        attr_set = true;
+        ctx->attr_done |= ATTR_HSV_HIST;
     }
     if (chan_sum)
         hsv_hist_kernel<true><<<dim3(gx, n_rois), 256, smem, st>>>(plane_of(rgb), rgb->width, rgb->height, rois, (unsigned long long *)count,
@@ -231,6 +232,7 @@ extern "C" SYNSEG_EXPORT int synseg_hsv_mask_gather(synseg_ctx *ctx, const synse
                                       const int64_t *ranks, int32_t n, uint8_t *out_rgb, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_hsv_mask_gather: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(rgb, "rgb", 3));
     if (!row_prefix || !ranks || !out_rgb) { synseg_set_error("synseg_hsv_mask_gather: NULL buffer"); return SYNSEG_E_INVALID; }
     if (n <= 0) return SYNSEG_OK;

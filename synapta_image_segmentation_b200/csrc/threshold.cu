@@ -292,6 +292,7 @@ extern "C" SYNSEG_EXPORT int synseg_adaptive_mean(synseg_ctx *ctx, const synseg_
                                     int invert, void *stream)
 {
     if (!ctx) { synseg_set_error("synseg_adaptive_mean: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
     SS_TRY(validate_img(gray, "gray", 1));
     SS_TRY(validate_img(out, "out", 1));
     if (!same_shape(gray, out)) { synseg_set_error("synseg_adaptive_mean: shape mismatch"); return SYNSEG_E_INVALID; }

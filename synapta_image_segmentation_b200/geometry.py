@@ -67,7 +67,46 @@ def cluster_rects(rects: Sequence[Sequence[float]], distance_threshold: float = 
                   min_members: int = CLUSTER_MIN_MEMBERS) -> List[List[int]]:
     """Greedy single-pass clustering (_cluster_drawings, :3559-3594): seed i absorbs every unused j closer
     than the threshold to the SEED (no transitive closure); clusters below `min_members` are dropped but
-    their members stay consumed.  Returns index lists in the reference's order."""
+    their members stay consumed.  Returns index lists in the reference's order.
+
+    The O(n) inner loop of a seed is vectorised (numpy f64, the reference's own operation order for the gaps);
+    `dx*dx + dy*dy < t*t` decides every pair except those within 1e-9 (relative) of the threshold, which go
+    through the scalar `drawing_distance` -- `(dx**2 + dy**2)**0.5 < t` as the reference writes it -- so the
+    result is the reference's for every input."""
+    n = len(rects)
+    if n == 0:
+        return []
+    if n < 16:
+        return _cluster_rects_scalar(rects, distance_threshold, min_members)
+    import numpy as np
+    r = np.asarray(rects, dtype=np.float64).reshape(n, 4)
+    x0, y0, x1, y1 = r[:, 0], r[:, 1], r[:, 2], r[:, 3]
+    used = np.zeros(n, dtype=bool)
+    t2 = float(distance_threshold) * float(distance_threshold)
+    clusters: List[List[int]] = []
+    for i in range(n):
+        if used[i]:
+            continue
+        used[i] = True
+        a0, b0, a1, b1 = x0[i], y0[i], x1[i], y1[i]
+        touch = (a0 <= x1) & (a1 >= x0) & (b0 <= y1) & (b1 >= y0)
+        dx = np.maximum(0.0, np.maximum(a0 - x1, x0 - a1))
+        dy = np.maximum(0.0, np.maximum(b0 - y1, y0 - b1))
+        v = dx * dx + dy * dy
+        near = (touch & (distance_threshold > 0)) | (~touch & (v < t2))
+        doubt = ~touch & (np.abs(v - t2) <= 1e-9 * t2)
+        for j in np.nonzero(doubt)[0]:
+            near[j] = drawing_distance(rects[i], rects[j]) < distance_threshold
+        near &= ~used
+        members = [i] + np.nonzero(near)[0].tolist()
+        used |= near
+        if len(members) >= min_members:
+            clusters.append(members)
+    return clusters
+
+
+def _cluster_rects_scalar(rects, distance_threshold, min_members) -> List[List[int]]:
+    """The reference's loops verbatim in structure (:3571-3592); also the checker of the vectorised form."""
     clusters: List[List[int]] = []
     used = set()
     for i, r1 in enumerate(rects):
@@ -194,3 +233,35 @@ def merge_visual_regions(primary: List[Dict], secondary: List[Dict]) -> List[Dic
             continue
         out.append(reg)
     return out
+
+
+def drawings_in_region(bbox: BoundingBox, drawing_rects: Optional[Sequence[Sequence[float]]]) -> int:
+    """Factor 4's count (:3080-3089): drawing rects whose TOP-LEFT corner lies inside the caption-based box."""
+    if not drawing_rects:
+        return 0
+    return sum(1 for d in drawing_rects if bbox.x0 <= d[0] <= bbox.x1 and bbox.y0 <= d[1] <= bbox.y1)
+
+
+def resolve_page_conflicts(caption_regions: Sequence[Dict], candidates: Sequence[Dict],
+                           drawing_rects: Optional[Sequence[Sequence[float]]] = None) -> List[Dict]:
+    """Pass 2 of _extract_images_from_page (:2822-2847) on region dicts.
+
+    caption_regions: the page's caption-based regions (pass 1; kept with confidence 0.9, :2787-2799).
+    candidates     : validated raster regions in detection order -- the role `_extract_embedded_images_validated`'s
+                     embedded images play (dicts with 'bbox', 'confidence', 'variance').
+    Every candidate is compared with the segments kept SO FAR (caption-based ones and candidates added before it):
+    the first one overlapping it by more than 0.4 of the smaller area is the conflict (`find_conflicting`); the
+    five-factor vote (`resolve_conflict`) then either replaces that segment by the candidate or discards the candidate.
+    Returns the final list in the reference's order (survivors of pass 1, then added candidates)."""
+    segments = list(caption_regions)
+    for cand in candidates:
+        conflict = find_conflicting(cand["bbox"], segments, key=lambda r: r["bbox"])
+        if conflict is None:
+            segments.append(cand)
+            continue
+        decision, reason = resolve_conflict(cand["bbox"], cand["confidence"], cand.get("variance"), conflict["bbox"], conflict.get("caption"),
+                                            drawings_in_region(conflict["bbox"], drawing_rects))
+        if decision == "keep_embedded":
+            segments.remove(conflict)
+            segments.append(dict(cand, conflict_resolution=reason))
+    return segments

@@ -276,7 +276,7 @@ class FeatureHints:
             best = max(scores, key=scores.get)
             if scores[best] >= 2.0:
                 return best
-        return None
+        return "unknown"          # pdf_image_segmentation.py:1461
 
     # ---- the old algorithm's per-type feature drivers (old_algo:887-1010), CV-derived fields only ----
     @staticmethod

@@ -13,7 +13,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Crop, DetectParams, Img, Roi, check
+from ._lib import Crop, DetectParams, Img, Region, RegionParams, Roi, check
+
+REGION_DTYPE = np.dtype([("x0", "<f8"), ("y0", "<f8"), ("x1", "<f8"), ("y1", "<f8"), ("px", "<i4"), ("py", "<i4"), ("pw", "<i4"), ("ph", "<i4"),
+                         ("kind", "<i4"), ("count", "<i4"), ("sum", "<u8"), ("sum_sq", "<u8")])     # synseg_region
+assert REGION_DTYPE.itemsize == _lib.REGION_BYTES == C.sizeof(Region)
 
 ERODE, DILATE, OPEN, CLOSE = 0, 1, 2, 3
 GRAY_CV, GRAY_PIL = 0, 1
@@ -83,6 +87,15 @@ class Context:
         check(self.lib.synseg_create(self.device.index, C.byref(h)), "synseg_create")
         self._h = h
 
+    def _s(self) -> C.c_void_p:
+        """The current torch stream of THIS context's device (not of torch's current device)."""
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _img(self, t: torch.Tensor, channels: int = 1, itemsize: int = 1) -> Img:
+        if t.is_cuda and t.device != self.device:
+            raise ValueError(f"tensor lives on {t.device}, this context on {self.device}")
+        return img_of(t, channels, itemsize)
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.synseg_destroy(self._h)
@@ -103,7 +116,7 @@ class Context:
 
     # ---- per-kernel timing ---------------------------------------------------------------------
     def profile_begin(self):
-        check(self.lib.synseg_profile_begin(self._h, _stream()), "synseg_profile_begin")
+        check(self.lib.synseg_profile_begin(self._h, self._s()), "synseg_profile_begin")
 
     def profile_end(self, cap: int = 4096):
         """[(kernel name, milliseconds), ...] in launch order since profile_begin()."""
@@ -119,7 +132,7 @@ class Context:
         r = _as3(rgb, 3)
         if out is None:
             out = empty_plane(r.shape[0], r.shape[1], r.shape[2], rgb.device)
-        check(self.lib.synseg_rgb2gray(self._h, C.byref(img_of(rgb, 3)), C.byref(img_of(out)), mode, _stream()), "synseg_rgb2gray")
+        check(self.lib.synseg_rgb2gray(self._h, C.byref(self._img(rgb, 3)), C.byref(self._img(out)), mode, self._s()), "synseg_rgb2gray")
         return out if rgb.dim() == 4 else out[0]
 
     # ---- threshold / edges ----------------------------------------------------------------------
@@ -128,7 +141,7 @@ class Context:
         g = _as3(gray, 1)
         if out is None:
             out = empty_plane(*g.shape, gray.device)
-        check(self.lib.synseg_adaptive_mean(self._h, C.byref(img_of(gray)), C.byref(img_of(out)), block_size, c, int(invert), _stream()),
+        check(self.lib.synseg_adaptive_mean(self._h, C.byref(self._img(gray)), C.byref(self._img(out)), block_size, c, int(invert), self._s()),
               "synseg_adaptive_mean")
         return out if gray.dim() == 3 else out[0]
 
@@ -136,7 +149,7 @@ class Context:
         g = _as3(gray, 1)
         if out is None:
             out = empty_plane(*g.shape, gray.device)
-        check(self.lib.synseg_canny(self._h, C.byref(img_of(gray)), C.byref(img_of(out)), lo, hi, _stream()), "synseg_canny")
+        check(self.lib.synseg_canny(self._h, C.byref(self._img(gray)), C.byref(self._img(out)), lo, hi, self._s()), "synseg_canny")
         return out if gray.dim() == 3 else out[0]
 
     # ---- morphology ---------------------------------------------------------------------------
@@ -145,8 +158,8 @@ class Context:
         s = _as3(src, 1)
         if out is None:
             out = empty_plane(*s.shape, src.device)
-        check(self.lib.synseg_morph(self._h, C.byref(img_of(src)), C.byref(img_of(out)), op, kw, kh, anchor[0], anchor[1], iterations,
-                                    1 if binary else 0, _stream()), "synseg_morph")
+        check(self.lib.synseg_morph(self._h, C.byref(self._img(src)), C.byref(self._img(out)), op, kw, kh, anchor[0], anchor[1], iterations,
+                                    1 if binary else 0, self._s()), "synseg_morph")
         return out if src.dim() == 3 else out[0]
 
     # ---- connected components -----------------------------------------------------------------
@@ -159,9 +172,9 @@ class Context:
         n = torch.empty(b, dtype=torch.int32, device=dev)
         stats = torch.empty((b, max_labels, 5), dtype=torch.int32, device=dev)
         cent = torch.empty((b, max_labels, 2), dtype=torch.float64, device=dev)
-        limg = C.byref(img_of(labels, 1, 4)) if want_labels else None
-        check(self.lib.synseg_ccl_stats(self._h, C.byref(img_of(mask)), limg, n.data_ptr(), stats.data_ptr(), cent.data_ptr(),
-                                        max_labels, _stream()), "synseg_ccl_stats")
+        limg = C.byref(self._img(labels, 1, 4)) if want_labels else None
+        check(self.lib.synseg_ccl_stats(self._h, C.byref(self._img(mask)), limg, n.data_ptr(), stats.data_ptr(), cent.data_ptr(),
+                                        max_labels, self._s()), "synseg_ccl_stats")
         return n, labels, stats, cent
 
     # ---- reductions ---------------------------------------------------------------------------
@@ -190,8 +203,8 @@ class Context:
             n = s.shape[0]
         out = torch.empty((n, 3), dtype=torch.int64, device=src.device)
         if n:
-            check(self.lib.synseg_moments(self._h, C.byref(img_of(src, ch)), src_kind, rt.data_ptr() if rt is not None else None, n,
-                                          out.data_ptr(), _stream()), "synseg_moments")
+            check(self.lib.synseg_moments(self._h, C.byref(self._img(src, ch)), src_kind, rt.data_ptr() if rt is not None else None, n,
+                                          out.data_ptr(), self._s()), "synseg_moments")
         return out
 
     def hsv_mask_hist(self, rgb: torch.Tensor, rois=None, want_hist: bool = True, want_sums: bool = False, want_rows: bool = False):
@@ -210,10 +223,10 @@ class Context:
         sums = torch.empty((n, HIST_BINS, 3), dtype=torch.int64, device=dev) if want_sums else None
         rows = torch.empty((n, max_rows), dtype=torch.int32, device=dev) if want_rows else None
         if n:
-            check(self.lib.synseg_hsv_mask_hist(self._h, C.byref(img_of(rgb, 3)), rt.data_ptr() if rt is not None else None, n,
+            check(self.lib.synseg_hsv_mask_hist(self._h, C.byref(self._img(rgb, 3)), rt.data_ptr() if rt is not None else None, n,
                                                 count.data_ptr(), hist.data_ptr() if hist is not None else None,
                                                 sums.data_ptr() if sums is not None else None,
-                                                rows.data_ptr() if rows is not None else None, max_rows, _stream()),
+                                                rows.data_ptr() if rows is not None else None, max_rows, self._s()),
                   "synseg_hsv_mask_hist")
         return dict(count=count, hist=hist, chan_sum=sums, row_count=rows)
 
@@ -223,8 +236,8 @@ class Context:
         out = torch.empty((n, 3), dtype=torch.uint8, device=rgb.device)
         r = Roi(*[int(v) for v in roi]) if roi is not None else None
         if n:
-            check(self.lib.synseg_hsv_mask_gather(self._h, C.byref(img_of(rgb, 3)), C.byref(r) if r is not None else None,
-                                                  row_prefix.data_ptr(), ranks.data_ptr(), n, out.data_ptr(), _stream()),
+            check(self.lib.synseg_hsv_mask_gather(self._h, C.byref(self._img(rgb, 3)), C.byref(r) if r is not None else None,
+                                                  row_prefix.data_ptr(), ranks.data_ptr(), n, out.data_ptr(), self._s()),
                   "synseg_hsv_mask_gather")
         return out
 
@@ -239,8 +252,8 @@ class Context:
             n = s.shape[0]
         out = torch.empty(n, dtype=torch.int64, device=src.device)
         if n:
-            check(self.lib.synseg_phash(self._h, C.byref(img_of(src, ch)), src_kind, rt.data_ptr() if rt is not None else None, n,
-                                        out.data_ptr(), _stream()), "synseg_phash")
+            check(self.lib.synseg_phash(self._h, C.byref(self._img(src, ch)), src_kind, rt.data_ptr() if rt is not None else None, n,
+                                        out.data_ptr(), self._s()), "synseg_phash")
         return out
 
     def select_rois(self, n_labels: torch.Tensor, stats: torch.Tensor, page_base: int, min_area: int, max_area: int, min_w: int,
@@ -248,27 +261,38 @@ class Context:
         """Device-side candidate selection: appends (image,x,y,w,h) rows to `rois` (int32 [cap,5]) and keys (int64 [cap])."""
         b, ml = stats.shape[0], stats.shape[1]
         check(self.lib.synseg_select_rois(self._h, n_labels.data_ptr(), stats.data_ptr(), b, ml, page_base, min_area, max_area, min_w, min_h,
-                                          rois.data_ptr(), keys.data_ptr(), count.data_ptr(), rois.shape[0], _stream()), "synseg_select_rois")
+                                          rois.data_ptr(), keys.data_ptr(), count.data_ptr(), rois.shape[0], self._s()), "synseg_select_rois")
 
     def phash_indirect(self, src: torch.Tensor, src_kind: int, rois: torch.Tensor, count: torch.Tensor, out: torch.Tensor):
         ch = 3 if src_kind else 1
-        check(self.lib.synseg_phash_indirect(self._h, C.byref(img_of(src, ch)), src_kind, rois.data_ptr(), count.data_ptr(), rois.shape[0],
-                                             out.data_ptr(), _stream()), "synseg_phash_indirect")
+        check(self.lib.synseg_phash_indirect(self._h, C.byref(self._img(src, ch)), src_kind, rois.data_ptr(), count.data_ptr(), rois.shape[0],
+                                             out.data_ptr(), self._s()), "synseg_phash_indirect")
 
     def phash_dedup(self, hashes: torch.Tensor, keys: torch.Tensor, max_hamming: int = 4) -> torch.Tensor:
         n = hashes.numel()
         keep = torch.empty(n, dtype=torch.uint8, device=hashes.device)
         if n:
-            check(self.lib.synseg_phash_dedup(self._h, hashes.data_ptr(), keys.data_ptr(), n, max_hamming, keep.data_ptr(), _stream()),
+            check(self.lib.synseg_phash_dedup(self._h, hashes.data_ptr(), keys.data_ptr(), n, max_hamming, keep.data_ptr(), self._s()),
                   "synseg_phash_dedup")
         return keep
 
     # ---- fused pipelines ------------------------------------------------------------------------
+    def _page_img(self, pages: torch.Tensor):
+        """(synseg_img, channels, batch) of RGB pages [B,H,W,3] / [H,W,3] or grey pages [B,H,W] (channels from the layout)."""
+        if pages.dim() == 4 or (pages.dim() == 3 and pages.shape[-1] == 3 and pages.stride(-1) == 1 and pages.stride(-2) == 3):
+            r = _as3(pages, 3)
+            return self._img(pages, 3), 3, r.shape[0]
+        r = _as3(pages, 1)
+        return self._img(pages, 1), 1, r.shape[0]
+
     def detect_pages(self, rgb: torch.Tensor, block_size: int, c: int, k: int, canny_lo: int = 50, canny_hi: int = 150,
-                     max_labels: int = 1024, gray_out: Optional[torch.Tensor] = None, out=None):
-        """RGB pages [B,H,W,3] -> (n_labels int32 [B], stats int32 [B,max,5], centroids f64 [B,max,2])."""
-        r = _as3(rgb, 3)
-        b = r.shape[0]
+                     max_labels: int = 1024, gray_out: Optional[torch.Tensor] = None, out=None, channels: Optional[int] = None):
+        """Pages -> (n_labels int32 [B], stats int32 [B,max,5], centroids f64 [B,max,2]).
+        RGB pages [B,H,W,3] (channels 3) or grey 'L' pages [B,H,W] (channels 1; guessed from the layout when None)."""
+        if channels is None:
+            img, channels, b = self._page_img(rgb)
+        else:
+            img, b = self._img(rgb, channels), _as3(rgb, channels).shape[0]
         dev = rgb.device
         if out is None:
             n = torch.empty(b, dtype=torch.int32, device=dev)
@@ -276,31 +300,107 @@ class Context:
             cent = torch.empty((b, max_labels, 2), dtype=torch.float64, device=dev)
         else:
             n, stats, cent = out
-        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels)
-        gimg = C.byref(img_of(gray_out)) if gray_out is not None else None
-        check(self.lib.synseg_detect_pages(self._h, C.byref(img_of(rgb, 3)), C.byref(prm), gimg, n.data_ptr(), stats.data_ptr(),
-                                           cent.data_ptr(), _stream()), "synseg_detect_pages")
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels, channels, 0)
+        gimg = C.byref(self._img(gray_out)) if gray_out is not None else None
+        check(self.lib.synseg_detect_pages(self._h, C.byref(img), C.byref(prm), gimg, n.data_ptr(), stats.data_ptr(),
+                                           cent.data_ptr(), self._s()), "synseg_detect_pages")
         return n, stats, cent
+
+    @staticmethod
+    def region_buffers(batch: int, max_labels: int, max_regions: int, device=None, pinned: bool = False):
+        """Result tensors of detect_regions / detect_regions_host: dict(n_labels, stats, regions (uint8 [B,R,72]), n_regions, flags)."""
+        kw = dict(pin_memory=True) if pinned else dict(device=device)
+        return dict(n_labels=torch.empty(batch, dtype=torch.int32, **kw), stats=torch.empty((batch, max_labels, 5), dtype=torch.int32, **kw),
+                    regions=torch.empty((batch, max_regions, _lib.REGION_BYTES), dtype=torch.uint8, **kw),
+                    n_regions=torch.empty(batch, dtype=torch.int32, **kw), flags=torch.empty(batch, dtype=torch.int32, **kw))
+
+    @staticmethod
+    def regions_view(regions: torch.Tensor) -> np.ndarray:
+        """Host uint8 [B,R,72] tensor -> structured numpy view [B,R] (REGION_DTYPE), no copy."""
+        a = regions.numpy()
+        return a.view(REGION_DTYPE).reshape(a.shape[0], a.shape[1])
+
+    def detect_regions(self, pages: torch.Tensor, block_size: int, c: int, k: int, dpi: float, page_width_pt: float, page_height_pt: float,
+                       canny_lo: int = 50, canny_hi: int = 150, max_labels: int = 1024, max_regions: int = 64, min_extent_pt: float = 50.0,
+                       out=None, channels: Optional[int] = None):
+        """Device pages -> component tables + candidate regions with crop moments, one call on the current stream
+        (synseg_detect_regions).  Returns the dict of `region_buffers` (device tensors)."""
+        if channels is None:
+            img, channels, b = self._page_img(pages)
+        else:
+            img, b = self._img(pages, channels), _as3(pages, channels).shape[0]
+        o = out or self.region_buffers(b, max_labels, max_regions, pages.device)
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels, channels, 0)
+        rp = RegionParams(float(dpi), float(page_width_pt), float(page_height_pt), float(min_extent_pt), max_regions, 0)
+        check(self.lib.synseg_detect_regions(self._h, C.byref(img), C.byref(prm), C.byref(rp), o["n_labels"].data_ptr(), o["stats"].data_ptr(), None,
+                                             o["regions"].data_ptr(), o["n_regions"].data_ptr(), o["flags"].data_ptr(), self._s()),
+              "synseg_detect_regions")
+        return o
+
+    def regions_from_stats(self, n_labels: torch.Tensor, stats: torch.Tensor, pages: torch.Tensor, dpi: float, page_width_pt: float,
+                           page_height_pt: float, max_regions: int = 64, min_extent_pt: float = 50.0, channels: Optional[int] = None):
+        """Component tables -> (regions uint8 [B,R,72], n_regions, flags) on the device (synseg_regions_from_stats)."""
+        if channels is None:
+            img, channels, b = self._page_img(pages)
+        else:
+            img, b = self._img(pages, channels), _as3(pages, channels).shape[0]
+        dev = pages.device
+        regions = torch.empty((b, max_regions, _lib.REGION_BYTES), dtype=torch.uint8, device=dev)
+        n_regions = torch.empty(b, dtype=torch.int32, device=dev)
+        flags = torch.empty(b, dtype=torch.int32, device=dev)
+        rp = RegionParams(float(dpi), float(page_width_pt), float(page_height_pt), float(min_extent_pt), max_regions, 0)
+        check(self.lib.synseg_regions_from_stats(self._h, n_labels.data_ptr(), stats.data_ptr(), stats.shape[1], C.byref(img), channels, C.byref(rp),
+                                                 regions.data_ptr(), n_regions.data_ptr(), flags.data_ptr(), self._s()), "synseg_regions_from_stats")
+        return regions, n_regions, flags
+
+    @staticmethod
+    def _host_pages_layout(pages: torch.Tensor):
+        if pages.is_cuda or pages.dtype != torch.uint8 or pages.stride(-1) != 1:
+            raise ValueError("pages must be a CPU uint8 tensor [N,H,W,3] (RGB) or [N,H,W] (grey) with contiguous pixels")
+        if pages.dim() == 4:
+            if pages.shape[-1] != 3 or pages.stride(-2) != 3:
+                raise ValueError("RGB pages must be interleaved [N,H,W,3]")
+            ch = 3
+        elif pages.dim() == 3:
+            ch = 1
+        else:
+            raise ValueError("pages must be [N,H,W,3] or [N,H,W]")
+        n, h, w = pages.shape[0], pages.shape[1], pages.shape[2]
+        return ch, n, h, w, pages.stride(1), (pages.stride(0) if n > 1 else pages.stride(1) * h)
 
     def detect_pages_host(self, pages: torch.Tensor, block_size: int, c: int, k: int, canny_lo: int = 50, canny_hi: int = 150,
                           max_labels: int = 1024, chunk_pages: int = 16, want_centroids: bool = True, out=None):
-        """HOST pages (CPU u8 tensor [N,H,W,3], ideally pinned) -> HOST tables (pinned): (n_labels [N], stats [N,max,5],
+        """HOST pages (CPU u8 tensor [N,H,W,3] RGB or [N,H,W] grey, ideally pinned) -> HOST tables (pinned): (n_labels [N], stats [N,max,5],
         centroids [N,max,2] | None).  Staging, H2D/compute/D2H overlap and chunking happen inside the library
         (synseg_detect_pages_host); the call is asynchronous on the current stream -- synchronise before reading."""
-        if pages.is_cuda or pages.dtype != torch.uint8 or pages.dim() != 4 or pages.shape[-1] != 3 or pages.stride(-1) != 1 or pages.stride(-2) != 3:
-            raise ValueError("pages must be a CPU uint8 tensor [N,H,W,3] with interleaved pixels")
-        n, h, w, _ = pages.shape
+        ch, n, h, w, rs, ps = self._host_pages_layout(pages)
         if out is not None:                       # caller-provided (pinned) result tensors, reused across calls
             n_labels, stats, cent = out
         else:
             n_labels = torch.empty(n, dtype=torch.int32).pin_memory()
             stats = torch.empty((n, max_labels, 5), dtype=torch.int32).pin_memory()
             cent = torch.empty((n, max_labels, 2), dtype=torch.float64).pin_memory() if want_centroids else None
-        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels)
-        check(self.lib.synseg_detect_pages_host(self._h, C.c_void_p(pages.data_ptr()), w, h, pages.stride(1), pages.stride(0) if n > 1 else pages.stride(1) * h,
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels, ch, 0)
+        check(self.lib.synseg_detect_pages_host(self._h, C.c_void_p(pages.data_ptr()), w, h, rs, ps,
                                                 n, C.byref(prm), chunk_pages, C.c_void_p(n_labels.data_ptr()), C.c_void_p(stats.data_ptr()),
-                                                C.c_void_p(cent.data_ptr()) if cent is not None else None, _stream()), "synseg_detect_pages_host")
+                                                C.c_void_p(cent.data_ptr()) if cent is not None else None, self._s()), "synseg_detect_pages_host")
         return n_labels, stats, cent
+
+    def detect_regions_host(self, pages: torch.Tensor, block_size: int, c: int, k: int, dpi: float, page_width_pt: float, page_height_pt: float,
+                            canny_lo: int = 50, canny_hi: int = 150, max_labels: int = 1024, max_regions: int = 64, min_extent_pt: float = 50.0,
+                            chunk_pages: int = 10, out=None, want_stats: bool = True):
+        """HOST pages (pinned u8 [N,H,W,3] RGB or [N,H,W] grey) -> HOST result tensors (dict of `region_buffers(pinned=True)`):
+        staging ring, copy stream, detection, region rules and crop moments all inside the library (synseg_detect_regions_host).
+        Asynchronous on the current stream -- synchronise (or record / wait an event) before reading."""
+        ch, n, h, w, rs, ps = self._host_pages_layout(pages)
+        o = out or self.region_buffers(n, max_labels, max_regions, pinned=True)
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, max_labels, ch, 0)
+        rp = RegionParams(float(dpi), float(page_width_pt), float(page_height_pt), float(min_extent_pt), max_regions, 0)
+        check(self.lib.synseg_detect_regions_host(self._h, C.c_void_p(pages.data_ptr()), w, h, rs, ps, n, C.byref(prm), C.byref(rp), chunk_pages,
+                                                  C.c_void_p(o["n_labels"].data_ptr()), C.c_void_p(o["stats"].data_ptr()) if want_stats else None,
+                                                  C.c_void_p(o["regions"].data_ptr()), C.c_void_p(o["n_regions"].data_ptr()),
+                                                  C.c_void_p(o["flags"].data_ptr()), self._s()), "synseg_detect_regions_host")
+        return o
 
     def hints_crops(self, packed: torch.Tensor, crops, kw: int = 25, kh: int = 25) -> torch.Tensor:
         """Ragged batch of crops packed in one CUDA u8 buffer.  crops = [(offset, width, height, row_stride, channels), ...].
@@ -317,7 +417,7 @@ class Context:
             if off < 0 or w <= 0 or h <= 0 or rs < w * ch or off + rs * (h - 1) + w * ch > total:
                 raise ValueError(f"crop {i} lies outside the packed buffer")
             arr[i] = Crop(int(off), int(w), int(h), int(rs), int(ch), 0)
-        check(self.lib.synseg_hints_crops(self._h, C.c_void_p(packed.data_ptr()), arr, n, kw, kh, C.c_void_p(out.data_ptr()), _stream()),
+        check(self.lib.synseg_hints_crops(self._h, C.c_void_p(packed.data_ptr()), arr, n, kw, kh, C.c_void_p(out.data_ptr()), self._s()),
               "synseg_hints_crops")
         return out
 
@@ -344,7 +444,7 @@ class Context:
             return out, hist
         arr = self._crop_array(packed, crops)
         check(self.lib.synseg_colors_crops(self._h, C.c_void_p(packed.data_ptr()), arr, n, n_colors, iters, min_pixels,
-                                           C.c_void_p(out.data_ptr()), C.c_void_p(hist.data_ptr()) if hist is not None else None, _stream()),
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(hist.data_ptr()) if hist is not None else None, self._s()),
               "synseg_colors_crops")
         return out, hist
 
@@ -366,7 +466,61 @@ class Context:
         if want_edges:
             edges = empty_plane(n, int(a[:, 4].max()), int(a[:, 3].max()), src.device)
             edges.zero_()
-            eimg = C.byref(img_of(edges))
-        check(self.lib.synseg_grid_counts(self._h, C.byref(img_of(src, ch)), ch, gray_mode, a.ctypes.data_as(C.POINTER(Roi)), n, kw, kh,
-                                          out.data_ptr(), eimg, _stream()), "synseg_grid_counts")
+            eimg = C.byref(self._img(edges))
+        check(self.lib.synseg_grid_counts(self._h, C.byref(self._img(src, ch)), ch, gray_mode, a.ctypes.data_as(C.POINTER(Roi)), n, kw, kh,
+                                          out.data_ptr(), eimg, self._s()), "synseg_grid_counts")
         return out, edges
+
+
+class PageSlots:
+    """Renderer-facing pinned page slots (synseg_page_slot_*): a rasteriser writes pages straight into pinned memory owned
+    by the library -- the handoff of pdf_image_segmentation.py:3638-3657 without the PNG round trip.
+
+        slots = PageSlots(ctx, width, height, channels=1, pages_per_slot=16)
+        s, pages = slots.acquire()            # numpy uint8 view [pages_per_slot, H, W(, 3)] of the pinned slot
+        pages[:n] = ...                       # the renderer fills it
+        slots.submit(s, n, block_size, C, k, dpi, page_w_pt, page_h_pt)
+        res = slots.wait(s)                   # dict of numpy views: n_labels, stats, regions (REGION_DTYPE), n_regions, flags
+    """
+
+    def __init__(self, ctx: Context, width: int, height: int, channels: int = 3, pages_per_slot: int = 16, n_slots: int = 3,
+                 max_labels: int = 1024, max_regions: int = 64):
+        self.ctx, self.w, self.h, self.ch, self.pages, self.n_slots = ctx, width, height, channels, pages_per_slot, n_slots
+        self.max_labels, self.max_regions = max_labels, max_regions
+        check(ctx.lib.synseg_page_slots_init(ctx._h, width, height, channels, pages_per_slot, n_slots, max_labels, max_regions), "synseg_page_slots_init")
+        self._n = {}
+
+    @property
+    def numa_node(self) -> int:
+        return int(self.ctx.lib.synseg_page_slots_numa_node(self.ctx._h))
+
+    def acquire(self):
+        slot, ptr, rs, ps = C.c_int32(), C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self.ctx.lib.synseg_page_slot_acquire(self.ctx._h, C.byref(slot), C.byref(ptr), C.byref(rs), C.byref(ps)), "synseg_page_slot_acquire")
+        buf = (C.c_uint8 * (ps.value * self.pages)).from_address(ptr.value)
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(self.pages, self.h, rs.value)[:, :, :self.w * self.ch]
+        return slot.value, (a.reshape(self.pages, self.h, self.w, 3) if self.ch == 3 else a)
+
+    def submit(self, slot: int, n_pages: int, block_size: int, c: int, k: int, dpi: float, page_width_pt: float, page_height_pt: float,
+               canny_lo: int = 50, canny_hi: int = 150, min_extent_pt: float = 50.0):
+        prm = DetectParams(block_size, c, canny_lo, canny_hi, k, self.max_labels, self.ch, 0)
+        rp = RegionParams(float(dpi), float(page_width_pt), float(page_height_pt), float(min_extent_pt), self.max_regions, 0)
+        check(self.ctx.lib.synseg_page_slot_submit(self.ctx._h, slot, n_pages, C.byref(prm), C.byref(rp), self.ctx._s()), "synseg_page_slot_submit")
+        self._n[slot] = n_pages
+
+    def wait(self, slot: int):
+        p = [C.c_void_p() for _ in range(5)]
+        check(self.ctx.lib.synseg_page_slot_wait(self.ctx._h, slot, *[C.byref(q) for q in p]), "synseg_page_slot_wait")
+        n = self._n.pop(slot)
+
+        def view(ptr, dtype, shape):
+            count = int(np.prod(shape))
+            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        return dict(n_regions=view(p[0], np.int32, (n,)), flags=view(p[1], np.int32, (n,)), regions=view(p[2], REGION_DTYPE, (n, self.max_regions)),
+                    n_labels=view(p[3], np.int32, (n,)), stats=view(p[4], np.int32, (n, self.max_labels, 5)))
+
+    def close(self):
+        if self.ctx is not None and getattr(self.ctx, "_h", None):
+            self.ctx.lib.synseg_page_slots_release(self.ctx._h)
+        self.ctx = None

@@ -56,7 +56,12 @@ class RasterSegmentationPipeline:
         page_num = first_page
         try:
             for page in pages:
-                buf.append(np.ascontiguousarray(page))
+                page = np.ascontiguousarray(page)
+                if buf and page.shape != buf[0].shape:      # a batch holds pages of ONE size (PDFs mix page sizes)
+                    self._process_batch(buf, page_num)
+                    page_num += len(buf)
+                    buf = []
+                buf.append(page)
                 if len(buf) == self.batch:
                     self._process_batch(buf, page_num)
                     page_num += len(buf)
@@ -69,8 +74,12 @@ class RasterSegmentationPipeline:
 
     def _process_batch(self, pages: List[np.ndarray], first_page: int) -> None:
         det = self.detector
-        batch = torch.from_numpy(np.stack(pages)).to(det.ctx.device, non_blocking=True)
-        regions = det.detect_regions_batch(batch, page_nums=list(range(first_page, first_page + len(pages))))
+        try:
+            batch = torch.from_numpy(np.stack(pages)).to(det.ctx.device, non_blocking=True)
+            regions = det.detect_regions_batch(batch, page_nums=list(range(first_page, first_page + len(pages))))
+        except Exception as e:                      # a failing batch is reported and skipped like a failing segment (:2749-2754)
+            print(f"    ERROR detecting regions on pages {first_page + 1}..{first_page + len(pages)}: {e}")
+            return
         for i, regs in enumerate(regions):
             page_num = first_page + i
             for r in regs:

@@ -2,15 +2,21 @@
 
     python tests/golden/make_golden.py
 
-* copies a handful of small real crops from /root/reference/investments_segmented (inputs only, data
-  not source) plus synthetic crops, and records what the reference's own functions return on them:
-  OCRProcessor._detect_grid / _count_arrows / _detect_shapes / _estimate_data_points / np.var /
-  mask counts (pdf_image_segmentation.py:1320-1341, 1546-1617, 1753-1810);
+* copies 64 real crops from /root/reference/investments_segmented (inputs only, data not source; among them
+  the 1191x1500 Appendix-D crop and 40+ crops wider than one 480-column strip) plus synthetic crops, and records
+  what the reference's own functions return on them: OCRProcessor._detect_grid / _count_arrows / _detect_shapes /
+  _estimate_data_points / _detect_chart_subtype (no OCR and four OCR texts) / np.var / mask counts
+  (pdf_image_segmentation.py:1320-1461, 1546-1617, 1753-1810);
+* records the same deterministic quantities for ALL 591 crops of the shipped run in reference_corpus.json and copies
+  the crops to tests/golden/_a2/ (git-ignored: 38 MB; they travel to the GPU box with the tree, the JSON is committed);
 * records the pure-geometry known answers of SURVEY.md Appendix D by calling
   _calculate_overlap_ratio, _overlaps_with_existing, _drawing_distance, _cluster_drawings,
   _detect_by_drawings and _validate_embedded_image on an uninitialised pipeline instance.
 """
+import contextlib
+import io
 import json
+import multiprocessing as mp
 import os
 import shutil
 import sys
@@ -27,17 +33,40 @@ from synapta_image_segmentation_b200.synth import render_figure  # noqa: E402
 
 ref = ref_import.load()
 A2 = os.path.join(ref_import.REFERENCE_DIR, "investments_segmented")
-REAL = ["textbook_001_p020_2b1be7d6.png", "textbook_001_p022_3c6ac748.png", "textbook_001_p022_f96abaf9.png",
+BASE = ["textbook_001_p020_2b1be7d6.png", "textbook_001_p022_3c6ac748.png", "textbook_001_p022_f96abaf9.png",
         "textbook_001_p023_e2cf5878.png",
         # a spread over the book (RGB and grey, 245..548 rows), each < 40 KB
         "textbook_001_p169_513ec97a.png", "textbook_001_p183_af3dbb7a.png", "textbook_001_p207_364b0248.png",
         "textbook_001_p269_7d5d6fda.png", "textbook_001_p405_1ee5f3bc.png", "textbook_001_p457_ee651881.png",
         "textbook_001_p510_5645a3d3.png", "textbook_001_p553_a84c5fb1.png", "textbook_001_p712_8719d410.png",
         "textbook_001_p826_62601fad.png", "textbook_001_p971_84e35f5e.png", "textbook_001_p973_d3eae19d.png",
-        "textbook_001_p988_5b5815f5.png"]
+        "textbook_001_p988_5b5815f5.png",
+        # SURVEY.md Appendix D known-answer crop (1191 x 1500: arrows 20, rectangles 89) and the next largest ones
+        "textbook_001_p000_ab84f0ff.png", "textbook_001_p948_749fb1c3.png", "textbook_001_p179_aa2281bf.png"]
+OCR_TEXTS = ["Figure 3.2 Bar chart of annual returns by asset class", "A line graph of the yield curve: rates (%) against maturity",
+             "Pie chart: portfolio weights", "Open High Low Close prices; scatter of risk and return"]
 
 
-def helper_record(path):
+def real_selection():
+    """BASE + every 13th file of the sorted corpus below 160 KB (deterministic): 64 crops."""
+    names = sorted(f for f in os.listdir(A2) if f.endswith(".png"))
+    out = list(BASE)
+    for f in names[::13]:
+        if f not in out and os.path.getsize(os.path.join(A2, f)) < 160_000 and len(out) < 64:
+            out.append(f)
+    for f in names[5::29]:
+        if f not in out and os.path.getsize(os.path.join(A2, f)) < 160_000 and len(out) < 64:
+            out.append(f)
+    return out
+
+
+def quiet(fn, *a):
+    """The reference's _detect_chart_subtype prints DEBUG lines (pdf_image_segmentation.py:1379-1451)."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a)
+
+
+def helper_record(path, colours=True):
     img = Image.open(path)
     g = np.array(img.convert("L"))
     edges = cv2.Canny(g, 50, 150)
@@ -51,8 +80,17 @@ def helper_record(path):
                estimate_data_points=int(ref.OCRProcessor._estimate_data_points(img)),
                connections=len(ref.OCRProcessor._extract_connections(img)),
                image_subtype=ref.OCRProcessor._detect_image_subtype(img, None),
+               chart_subtype=quiet(ref.OCRProcessor._detect_chart_subtype, img, None),
                h_count=h_count, v_count=v_count, edge_px=int(np.sum(edges > 0)), variance=float(np.var(g)))
     assert rec["detect_grid"] == (h_count > 300 and v_count > 300)
+    if not colours:
+        if img.mode == "RGB":
+            hsv = cv2.cvtColor(np.array(img), cv2.COLOR_RGB2HSV)
+            rec["mask_px"] = int(((hsv[:, :, 1] > 30) & (hsv[:, :, 2] > 40) & (hsv[:, :, 2] < 240)).sum())
+        else:
+            rec["mask_px"] = 0
+        return rec
+    rec["chart_subtype_texts"] = [quiet(ref.OCRProcessor._detect_chart_subtype, img, ref.OCRResult(raw_text=t)) for t in OCR_TEXTS]
     if img.mode == "RGB":
         a = np.array(img)
         hsv = cv2.cvtColor(a, cv2.COLOR_RGB2HSV)
@@ -65,11 +103,25 @@ def helper_record(path):
     return rec
 
 
+def corpus_record(name):
+    return name, helper_record(os.path.join(A2, name), colours=False)
+
+
 def main():
     crops = {}
-    for name in REAL:
+    for name in real_selection():
         shutil.copy(os.path.join(A2, name), os.path.join(HERE, name))
         crops[name] = helper_record(os.path.join(HERE, name))
+    # the whole shipped run ("parity on the 591 real crops")
+    names = sorted(f for f in os.listdir(A2) if f.endswith(".png"))
+    os.makedirs(os.path.join(HERE, "_a2"), exist_ok=True)
+    for f in names:
+        if not os.path.exists(os.path.join(HERE, "_a2", f)):
+            shutil.copy(os.path.join(A2, f), os.path.join(HERE, "_a2", f))
+    with mp.Pool(os.cpu_count()) as pool:
+        corpus = dict(pool.map(corpus_record, names, chunksize=8))
+    json.dump(dict(crops=corpus, ocr_texts=OCR_TEXTS, grid_true=sum(r["detect_grid"] for r in corpus.values())),
+              open(os.path.join(HERE, "reference_corpus.json"), "w"), indent=0)
     for i in range(4):       # synthetic crops at 150 DPI
         fig = render_figure([99, i], 150, 500, 700)
         name = f"synth_fig_{i}.png"
@@ -137,9 +189,50 @@ def main():
                                       Seg(BB(*cap_bb, 612, 792), caption_text=cap_text, extraction_method="rendered_region"), FakePage([]))
         rc.append(dict(emb=list(emb_bb), cap=list(cap_bb), caption=cap_text, confidence=conf, image=os.path.basename(path)[5:-4], decision=d, reasons=why))
     geo["resolve_conflict"] = rc
+
+    # Pass 2 of _extract_images_from_page (pdf_image_segmentation.py:2822-2847): every validated candidate is tested against the
+    # segments kept so far with the reference's own _find_conflicting_segment / _resolve_conflict (the loop statements
+    # around those two calls are restated here; `page.get_drawings()` feeds factor 4).
+    def pass2(captions, candidates, drawings):
+        segments = [Seg(BB(*c["bbox"], 612, 792), caption_text=c["caption"], extraction_method="caption_based", confidence=0.9) for c in captions]
+        for c in candidates:
+            cand = Seg(BB(*c["bbox"], 612, 792), confidence=c["confidence"], image_path=npath if c["image"] == "noise" else fpath)
+            conflict = pl._find_conflicting_segment(cand, segments)
+            if conflict:
+                decision, _ = pl._resolve_conflict(cand, conflict, FakePage([{"rect": FakeDrawRect(*d)} for d in drawings]))
+                if decision == "keep_embedded":
+                    segments.remove(conflict)
+                    segments.append(cand)
+            else:
+                segments.append(cand)
+        return [dict(method=s_.extraction_method, bbox=[s_.bbox.x0, s_.bbox.y0, s_.bbox.x1, s_.bbox.y1]) for s_ in segments]
+
+    class FakeDrawRect:
+        def __init__(self, x0, y0, x1, y1):
+            self.x0, self.y0, self.x1, self.y1 = x0, y0, x1, y1
+
+    ref.fitz.Rect = FakeDrawRect          # `drawing.get('rect', fitz.Rect(0, 0, 0, 0))` builds the default eagerly (:3083)
+    scenarios = [
+        dict(captions=[dict(bbox=[50, 100, 300, 330], caption="Figure 2.1 Returns")],
+             candidates=[dict(bbox=[60, 110, 290, 300], confidence=0.9, image="noise"),      # photo inside a captioned region: caption wins 5:3
+                         dict(bbox=[320, 400, 560, 600], confidence=0.8, image="flat")],     # no conflict: added
+             drawings=[]),
+        dict(captions=[dict(bbox=[50, 100, 300, 300], caption=None)],
+             candidates=[dict(bbox=[40, 90, 320, 330], confidence=0.9, image="noise")],      # no caption text, photo-like: embedded replaces it
+             drawings=[]),
+        dict(captions=[dict(bbox=[50, 100, 300, 300], caption=None), dict(bbox=[50, 400, 300, 600], caption="Fig. 3 Flow")],
+             candidates=[dict(bbox=[60, 110, 290, 290], confidence=0.6, image="flat"),       # 0:0 -> keep_embedded (ties go to the embedded image)
+                         dict(bbox=[70, 120, 280, 280], confidence=0.9, image="noise"),      # now conflicts with the candidate kept before it
+                         dict(bbox=[60, 410, 290, 590], confidence=0.95, image="noise")],    # caption 3 vs embedded 2+1: tie -> keep_embedded
+             drawings=[]),
+        dict(captions=[dict(bbox=[50, 100, 300, 300], caption=None)],
+             candidates=[dict(bbox=[60, 110, 290, 290], confidence=0.75, image="flat")],     # 12 drawings inside the caption region: caption 2 vs 1
+             drawings=[[60 + 5 * i, 120, 70 + 5 * i, 130] for i in range(12)]),
+    ]
+    geo["pass2"] = [dict(s_, result=pass2(s_["captions"], s_["candidates"], s_["drawings"])) for s_ in scenarios]
     os.remove(npath); os.remove(fpath)
 
-    json.dump(dict(crops=crops, versions=dict(cv2=cv2.__version__, numpy=np.__version__)), open(os.path.join(HERE, "reference_helpers.json"), "w"), indent=1)
+    json.dump(dict(crops=crops, ocr_texts=OCR_TEXTS, versions=dict(cv2=cv2.__version__, numpy=np.__version__)), open(os.path.join(HERE, "reference_helpers.json"), "w"), indent=1)
     json.dump(geo, open(os.path.join(HERE, "reference_geometry.json"), "w"), indent=1)
     print("wrote", len(crops), "crop records and geometry vectors")
 

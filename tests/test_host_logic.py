@@ -77,6 +77,34 @@ def test_resolve_conflict(geo):
         assert (d, why) == (v["decision"], v["reasons"])
 
 
+def test_pass2_conflict_resolution_matches_reference(geo):
+    """`_extract_images_from_page` pass 2 (pdf_image_segmentation.py:2822-2847): which segments survive when validated candidates
+    meet caption-based ones -- decisions recorded from the reference's own _find_conflicting_segment / _resolve_conflict."""
+    var = {"noise": float(np.var(_gray("noise"))), "flat": 0.0}
+    for sc in geo["pass2"]:
+        caps = [dict(bbox=BB(*c["bbox"]), caption=c["caption"], detection_method="caption_based", confidence=0.9) for c in sc["captions"]]
+        cands = [dict(bbox=BB(*c["bbox"]), confidence=c["confidence"], variance=var[c["image"]], detection_method="raster_cc") for c in sc["candidates"]]
+        out = G.resolve_page_conflicts(caps, cands, sc["drawings"])
+        got = [dict(method="caption_based" if r["detection_method"] == "caption_based" else "embedded_image",
+                    bbox=[r["bbox"].x0, r["bbox"].y0, r["bbox"].x1, r["bbox"].y1]) for r in out]
+        assert got == sc["result"], sc
+
+
+def test_vectorised_clustering_equals_the_reference_loops():
+    """cluster_rects (numpy inner loop) == the reference's two nested loops, also on grids full of pairs at exactly 100 pt."""
+    rng = np.random.default_rng(3)
+    for trial in range(60):
+        n = int(rng.integers(16, 220))
+        if trial % 3 == 0:
+            xy = rng.uniform(0, 700, (n, 2)); wh = rng.uniform(1, 60, (n, 2))
+        elif trial % 3 == 1:
+            xy = 0.24 * rng.integers(0, 3000, (n, 2)); wh = 0.24 * rng.integers(1, 200, (n, 2))
+        else:
+            xy = 20.0 * rng.integers(0, 40, (n, 2)); wh = 20.0 * rng.integers(1, 3, (n, 2))      # (60, 80) gaps: distance exactly 100
+        rects = np.concatenate([xy, xy + wh], 1).tolist()
+        assert G.cluster_rects(rects) == G._cluster_rects_scalar(rects, G.CLUSTER_GAP, G.CLUSTER_MIN_MEMBERS)
+
+
 def test_merge_visual_regions():
     a = {"bbox": BB(0, 0, 100, 100), "caption_bbox": [10, 120, 90, 130]}
     dup = {"bbox": BB(10, 10, 90, 90)}                  # 100 % of its area inside a -> dropped
@@ -119,7 +147,7 @@ def test_c_abi_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (synseg_\w+)", out))
     assert exported == declared, exported ^ declared
-    assert lib.synseg_version() == 100
+    assert lib.synseg_version() == 200
     # the ctypes signatures carry as many arguments as the prototypes in the header
     for m in re.finditer(r"\b(synseg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
         name, params = m.group(1), m.group(2).strip()
@@ -240,7 +268,12 @@ def test_candidate_regions_with_pdf_priors():
     assert [r["detection_method"] for r in merged] == ["caption_based", "caption_based", "raster_cc"]
     assert (merged[2]["bbox"].x0, merged[2]["bbox"].y0) == (100.0, 400.0)
     with pytest.raises(RuntimeError):
-        det.candidate_regions(stats, -7, 612.0, 792.0)                      # label overflow is an error, not an empty page
+        det.candidate_regions(stats, -7, 612.0, 792.0)                      # label overflow is an error on the host rules (the detector retries)
+    # the live flow of the reference (pass 2 of _extract_images_from_page): a validated raster candidate against the caption-based segments
+    cands = [dict(r, confidence=0.8, variance=50.0) for r in plain]
+    out = G.resolve_page_conflicts([dict(cap1, confidence=0.9)], cands)
+    # candidate 1 overlaps cap1 (ratio 1.0 > 0.4): caption 3 + 2 (larger) vs embedded 1 (confidence) -> caption stays; candidate 2 is added
+    assert [r["detection_method"] for r in out] == ["caption_based", "raster_cc"] and out[1]["bbox"].y0 == 400.0
 
 
 def test_decode_colors_row_layout():
