@@ -129,7 +129,7 @@ def test_detector_regions_cover_figures(ctx):
     first = small["bbox"]
     prior = {"bbox": BoundingBox(first.x0 - 5, first.y0 - 5, first.x1 + 5, first.y1 + 5, 612.0, 792.0), "caption": "Figure 1.1",
              "detection_method": "caption_based", "notes": "Caption: Figure 1.1"}
-    with_prior = det.detect_regions(pages[0], 0, priors=[prior])
+    with_prior = det.detect_regions(pages[0], 0, priors=[prior], prior_rule="visual_regions")
     assert len(with_prior) == len(regions[0])
     assert [r["detection_method"] for r in with_prior].count("caption_based") == 1
     cap = [r for r in with_prior if r["detection_method"] == "caption_based"][0]

@@ -315,31 +315,46 @@ def test_two_contexts_on_two_devices(ctx):
 
 
 def test_two_pass_priors_on_the_gpu(ctx):
-    """Pass 2 of _extract_images_from_page through the detector: a caption-based prior covering a detected figure wins the
-    vote (caption text + larger box) and replaces the raster region; an unrelated prior just adds a segment."""
+    """Pass 2 of _extract_images_from_page through the detector: validated raster regions are candidates resolved, in detection
+    order, against the caption-based priors by find_conflicting / resolve_conflict (golden-tested in test_host_logic.py)."""
+    from synapta_image_segmentation_b200 import geometry as G
     from synapta_image_segmentation_b200.datamodel import BoundingBox
     dpi = 150
     det = RasterRegionDetector(DetectConfig(dpi=dpi), ctx=ctx)
     page = synth_page(0, dpi, n_figures=2)[0]
+    h, w = page.shape[:2]
     base = det.detect_regions(page, 0)
     assert len(base) >= 2
-    tgt = base[0]["bbox"]
-    prior = {"bbox": BoundingBox(tgt.x0 - 5, tgt.y0 - 5, tgt.x1 + 5, tgt.y1 + 40, 612.0, 792.0), "caption": "Figure 1.1 Returns",
-             "notes": "Caption: Figure 1.1"}
-    out = det.detect_regions(page, 0, priors=[prior])
-    methods = [r["detection_method"] for r in out]
-    assert methods.count("caption_based") == 1 and len(out) == len(base)
-    assert not any(r["bbox"] == tgt for r in out)                       # the raster region lost the vote
-    cap = [r for r in out if r["detection_method"] == "caption_based"][0]
-    assert cap["confidence"] == 0.9 and cap["caption"] == "Figure 1.1 Returns" and "variance" in cap
-    # without caption text and with a box no larger than the raster region, a photo-like / well-validated raster region replaces the prior
-    weak = {"bbox": BoundingBox(tgt.x0, tgt.y0, tgt.x1, tgt.y1, 612.0, 792.0), "caption": None}
-    out2 = det.detect_regions(page, 0, priors=[weak])
-    assert [r["detection_method"] for r in out2].count("caption_based") == 0 and len(out2) == len(base)
-    assert any("conflict_resolution" in r for r in out2)
+    # the validated raster candidates in DETECTION order (the order pass 2 walks them in)
+    t = det.detect_tables(torch.from_numpy(page).cuda()[None], 612.0, 792.0)
+    cands = det.regions_from_table(Context.regions_view(t["regions"].cpu())[0], int(t["n_regions"][0]), 612.0, 792.0)
+    det._score(cands, 792.0)
+    cands = [r for r in cands if r["confidence"] >= 0.5]
+    assert sorted(_key(r) for r in cands) == sorted(_key(r) for r in base)
+    tgt = min(base, key=lambda r: r["bbox"].area())["bbox"]
+    priors = {
+        "captioned, larger": {"bbox": BoundingBox(tgt.x0 - 5, tgt.y0 - 5, tgt.x1 + 5, tgt.y1 + 40, 612.0, 792.0), "caption": "Figure 1.1 Returns",
+                              "notes": "Caption: Figure 1.1"},
+        "no caption, same box": {"bbox": BoundingBox(tgt.x0, tgt.y0, tgt.x1, tgt.y1, 612.0, 792.0), "caption": None},
+        "far away": {"bbox": BoundingBox(2, 2, 40, 40, 612.0, 792.0), "caption": "Exhibit 9"},
+    }
+    seen = set()
+    for name, prior in priors.items():
+        out = det.detect_regions(page, 0, priors=[prior])
+        scored = dict(prior, detection_method="caption_based", confidence=0.9, caption=prior.get("caption"))
+        want = G.resolve_page_conflicts([scored], [dict(c) for c in cands])
+        want.sort(key=lambda r: (r["bbox"].y0, r["bbox"].x0))
+        assert [(r["detection_method"], r["bbox"]) for r in out] == [(r["detection_method"], r["bbox"]) for r in want], name
+        for r in out:
+            if r["detection_method"] == "caption_based":
+                assert r["confidence"] == 0.9 and r["caption"] == prior["caption"] and "variance" in r and "crop_px" in r
+        seen.add(("caption_based" in [r["detection_method"] for r in out], any("conflict_resolution" in r for r in out)))
+    assert (True, False) in seen and any(replaced for _, replaced in seen)      # a prior that stays, and one a raster region replaced
+    far = det.detect_regions(page, 0, priors=[priors["far away"]])
+    assert len(far) == len(base) + 1
     # the other rule (dead code in the reference, kept selectable): _detect_visual_regions' duplicate test
-    out3 = det.detect_regions(page, 0, priors=[prior], prior_rule="visual_regions")
-    assert [r["detection_method"] for r in out3].count("caption_based") == 1 and len(out3) == len(base)
-    segs = det.extract_segments(page, 0, "textbook_001", priors=[prior])
+    out3 = det.detect_regions(page, 0, priors=[priors["captioned, larger"]], prior_rule="visual_regions")
+    assert [r["detection_method"] for r in out3].count("caption_based") == 1
+    segs = det.extract_segments(page, 0, "textbook_001", priors=[priors["far away"]])
     capseg = [s for s in segs if s.extraction_method == "caption_based"][0]
-    assert capseg.caption_text == "Figure 1.1 Returns" and capseg.notes == "Caption: Figure 1.1" and capseg.confidence == 0.9
+    assert capseg.caption_text == "Exhibit 9" and capseg.notes == "" and capseg.confidence == 0.9 and capseg.page_no == 1
