@@ -7,11 +7,16 @@ One "step" = one pass of the detection hot path over one batch of synthetic page
 BASELINE.json configs[2]: a 1,000-page synthetic textbook at 300 DPI on one B200 (20 steps x 50 pages).
 
   value : whole-job pages/s with the batch already resident in HBM (device pipeline only), CUDA events.
-  e2e   : pages/s through the public API from PINNED HOST pages: H2D of every page, fused pipeline, D2H of the
-          component tables, host-side box filter/merge into region boxes -- all inside the timed region.
+  e2e   : pages/s through the public API from PINNED HOST pages (PageStreamer -> synseg_detect_regions_host): H2D of every
+          page, fused pipeline, region rules + crop moments on the device, D2H of the region / component tables, host-side
+          validation score + keep filter -> the validated regions detect_regions_batch returns -- all inside the timed region.
+          e2e.grey_pages: the same with 'L' pages (a third of the PCIe bytes); bare_h2d: the box's concurrent copy bound.
   roofline : the dominant kernel of a step (per-kernel CUDA-event timing of profiled steps in this same run),
           algorithmic bytes / its time / measured HBM peak (MEASURED_PEAKS.json).
   cpu_baseline : the cv2 chain (oracle/cv2_chain.py) on the box's host cores, bounded sample, rank 0, N=1.
+  crops    : BASELINE.json configs[3] (10k figure crops: hints + dominant colours), resident and from PIL images, rank 0, N=1.
+  dense_pages : the same step on pages without blank paper (content-dependent worst case of the stencils), rank 0, N=1.
+  dedup.fixed_corpus : a fixed 400-page corpus sharded over the N ranks; its survivor digest is the same at every N.
 
 Every step also selects the candidate component boxes on the device; after the K steps their perceptual hashes are
 computed and the replicated Hamming dedup runs, inside the timed region.  N>1 (torchrun, one rank per GPU): pages
@@ -58,6 +63,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pages in the CPU baseline sample (0 = 8 x cores, capped)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-corpus", action="store_true")
+    ap.add_argument("--crops", type=int, default=10000, help="crops of the config-4 line (0 = skip)")
     return ap.parse_args()
 
 
@@ -155,6 +163,27 @@ class gpu_numa_affinity:
         return False
 
 
+def numa_info(index: int):
+    """NUMA facts of this box for the record: node of GPU `index` (sysfs), number of nodes, CPUs NVML calls local to the GPU."""
+    import glob
+    out = {"nodes": len(glob.glob("/sys/devices/system/node/node[0-9]*")), "gpu_numa_node": None, "gpu_local_cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(hdl).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        out["gpu_numa_node"] = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        out["gpu_local_cpus"] = sum(bin(int(wd)).count("1") for wd in words)
+    except Exception:
+        pass
+    return out
+
+
 def build_textbook(dpi: int, batch: int, unique: int, start_page: int, pin: bool):
     """[batch,H,W,3] u8 host tensor: `unique` distinct seeded pages tiled to `batch` pages."""
     import numpy as np
@@ -222,19 +251,75 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def crop_sizes(n, seed=4):
+    """(h, w) pairs: log-normal around the reference's median crop 457 x 699, clipped to [60, 1500] x [70, 1191]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    h = np.clip(np.exp(rng.normal(np.log(457), 0.45, n)), 60, 1500).astype(int)
+    w = np.clip(np.exp(rng.normal(np.log(699), 0.35, n)), 70, 1191).astype(int)
+    return list(zip(h.tolist(), w.tolist()))
+
+
+def crops_line(ctx, n_crops: int, n_objects: int = 2000):
+    """BASELINE.json configs[3]: 10k cropped figure regions -> grid-line / variance / mask hints + dominant colours.
+    resident: the two C-ABI calls on the packed batch already in HBM (CUDA events); from_pil: FeatureHints.hints_batch from
+    PIL images (host copy into pinned slots + H2D + both calls + D2H, wall clock).  `n_objects` distinct PIL images with the
+    size distribution of the shipped run are cycled to n_crops (every one is packed and uploaded again)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    from synapta_image_segmentation_b200.synth import render_figure
+    n_objects = min(n_objects, n_crops)
+    sizes = crop_sizes(n_objects)
+    uniq = [render_figure([11, i], 150, *sizes[i]) for i in range(min(n_objects, 48))]
+    objs = []
+    for i, (h, w) in enumerate(sizes):
+        u = uniq[i % len(uniq)]
+        if u.shape[:2] != (h, w):
+            u = np.tile(u, (-(-h // u.shape[0]), -(-w // u.shape[1]), 1))[:h, :w]
+        objs.append(Image.fromarray(np.ascontiguousarray(u)))
+    crops = [objs[i % n_objects] for i in range(n_crops)]
+    mpx = sum(c.size[0] * c.size[1] for c in crops) / 1e6
+    FeatureHints.hints_batch(crops[:64])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    FeatureHints.hints_batch(crops)
+    torch.cuda.synchronize()
+    t_api = time.perf_counter() - t0
+    # resident: pack a quarter of the batch once (keeps the pinned + device buffers below 4 GB), time the two calls on it
+    part = crops[:max(1, n_crops // 4)]
+    host, descs = FeatureHints.pack_crops(part)
+    dev = host.to(ctx.device)
+    ctx.hints_crops(dev, descs); ctx.colors_crops(dev, descs)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    e[0].record(); ctx.hints_crops(dev, descs); e[1].record(); ctx.colors_crops(dev, descs); e[2].record()
+    torch.cuda.synchronize()
+    ms_h, ms_c = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+    return {"workload": f"{n_crops} crops, size distribution of the reference's shipped run (median 699x457), {mpx:.0f} Mpx; {n_objects} distinct images cycled",
+            "from_pil": {"value": n_crops / t_api, "unit": "crops/s", "seconds": t_api,
+                         "includes": "PIL -> pinned slots (threaded copy), H2D, synseg_hints_crops + synseg_colors_crops, D2H"},
+            "resident": {"value": len(part) / ((ms_h + ms_c) / 1e3), "unit": "crops/s", "crops": len(part), "hints_ms": ms_h, "colors_ms": ms_c,
+                         "gpu_launches": int(ctx.launches - l0), "bytes_read_gb": host.numel() / 1e9,
+                         "GBps": host.numel() * 2 / ((ms_h + ms_c) / 1e3) / 1e9}}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    import hashlib
     import numpy as np
     import torch
     import torch.distributed as dist
-    from synapta_image_segmentation_b200.dedup import cross_page_dedup
+    from synapta_image_segmentation_b200 import dedup
     from synapta_image_segmentation_b200.detector import DetectConfig, RasterRegionDetector
     from synapta_image_segmentation_b200.ops import Context
     from synapta_image_segmentation_b200.streaming import PageStreamer
-    from synapta_image_segmentation_b200.synth import page_shape
+    from synapta_image_segmentation_b200.synth import dense_page, page_shape, synth_pages
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,11 +328,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION and =WARN; stdout must carry the one JSON line only
-        os.environ["NCCL_DEBUG"] = os.environ.get("SYNSEG_NCCL_DEBUG", "NONE")
+        # NCCL prints its INFO lines (communicator, nranks, transport) to STDOUT by default; stdout must carry the one JSON
+        # line only, so they are routed to stderr -- visible to whoever runs the bench, never silenced
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = Context(local)
+    comm_world = dedup.init_comm(ctx)                      # the library's own communicator for the exchange step (ncclAllGather)
     det = RasterRegionDetector(DetectConfig(dpi=args.dpi, max_labels=1024), ctx=ctx)
     h, w = page_shape(args.dpi)
     B, K, W_ = args.batch, args.steps, args.warmup
@@ -264,34 +353,25 @@ def main():
            torch.empty((B, ml, 2), dtype=torch.float64, device=dev))
     # device-side candidate selection + hashing for the cross-page duplicate removal (every N; the gather is a
     # real NCCL collective at N>1 and local at N=1, so per-GPU work is identical for every N)
-    cap = 16 * B * max(K, W_, 1)
+    cap = 8 * B * max(K, W_, 1)
     rois = torch.empty((cap, 5), dtype=torch.int32, device=dev)
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
     hashes = torch.empty(cap, dtype=torch.int64, device=dev)
     count = torch.zeros(1, dtype=torch.int32, device=dev)
+    exch = dedup.DedupExchange(ctx, cap, comm_world, max_hamming=4)
     s = args.dpi / 72.0
     min_area, max_area = int(5000 * s * s), int(0.8 * npx)
     min_ext = int(50 * s)
 
-    def step(i):
-        det.detect_components(pages, out=out)
+    def step(i, src=pages):
+        det.detect_components(src, out=out)
         ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
 
-    phases = os.environ.get("SYNSEG_BENCH_PHASES") == "1"       # diagnostic: wall-clock of the exchange phases on stderr
-
-    def dedup_exchange():
-        t = [time.perf_counter()]
-        n_valid = int(count.item())                            # one host sync; also sizes the hashing grid exactly
-        t.append(time.perf_counter())
-        ctx.phash_indirect(pages, 1, rois[:max(n_valid, 1)], count, hashes)      # all candidate boxes of the K steps share `pages`
-        if phases:
-            torch.cuda.synchronize(); t.append(time.perf_counter())
-        k_all, keep = cross_page_dedup(ctx, hashes[:n_valid], keys[:n_valid], capacity=cap, max_hamming=4, phases=t if phases else None)
-        n_keep = int(keep.sum().item())
-        if phases:
-            t.append(time.perf_counter())
-            print(f"[rank {rank}] exchange phases ms: " + " ".join(f"{1000 * (b - a):.2f}" for a, b in zip(t, t[1:])), file=sys.stderr)
-        return k_all, n_keep
+    def dedup_exchange(src=pages):
+        # all candidate boxes of the K steps share `src`; hashing, ONE ncclAllGather and the replicated dedup are queued on the
+        # stream by two library calls -- no host synchronisation, no torch kernel
+        ctx.phash_indirect(src, 1, rois, count, hashes)
+        exch.run(hashes, keys, count)
 
     def barrier():
         if world > 1:
@@ -300,8 +380,8 @@ def main():
 
     for i in range(W_):
         step(i)
-    for _ in range(3):          # warm-up of the exchange too: the first collective creates the NCCL communicator and
-        dedup_exchange()        # the next ones still finish lazy connection set-up (20 ms per call at 8 ranks otherwise)
+    for _ in range(3):          # warm-up of the exchange too: the first collective finishes NCCL's lazy connection set-up
+        dedup_exchange()
     barrier()
     count.zero_()
     # rank 0 samples its GPU's clocks (one NVML client per box is enough and keeps the other ranks' driver calls quiet)
@@ -314,7 +394,7 @@ def main():
     e0.record()
     for i in range(K):
         step(i)
-    k_all, n_survivors = dedup_exchange()
+    dedup_exchange()
     e1.record()
     barrier()
     launches = ctx.launches - launches0
@@ -324,116 +404,182 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * K * B / (ms_total / 1000.0)
+    k_all, keep = exch.result()
+    n_hashed, n_survivors = int(k_all.numel()), int(keep.sum())
+    overflow = int(count.item()) > cap
 
-    # ---- end to end: pinned host pages -> H2D -> pipeline -> D2H -> host box filter/merge ---------------------
-    e2e = None
-    if not args.no_e2e:
-        streamer = PageStreamer(det, B, h, w, slots=3)
-        pw, ph = w * 72.0 / args.dpi, h * 72.0 / args.dpi
-        n_regions = [0]
-
-        def on_result(i, n_h, stats_h):
-            n_np, st_np = n_h.numpy(), stats_h.numpy()
-            for j in range(n_np.shape[0]):
-                n_regions[0] += len(det.candidate_regions(st_np[j], int(n_np[j]), pw, ph))
-
-        streamer.run((host_pages for _ in range(max(1, W_ // 2))), on_result)
-        barrier()
-        streamer.h2d_bytes = streamer.d2h_bytes = 0
-        t0 = time.perf_counter()
-        streamer.run((host_pages for _ in range(K)), on_result)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        td = torch.tensor([dt], dtype=torch.float64, device=dev)
+    def max_over_ranks(x):
+        td = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dt = float(td.item())
-        # the same end-to-end step through the C ABI's HOST-buffer entry point (synseg_detect_pages_host: staging ring,
-        # copy stream and chunking inside the library; no torch copies): results of call i-2 are consumed after call i is queued
-        bs_, c_, k_ = det.cfg.resolved()
-        outs = [(torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty((B, ml, 5), dtype=torch.int32).pin_memory(), None) for _ in range(3)]
-        evs = [torch.cuda.Event() for _ in range(3)]
+        return float(td.item())
 
-        def host_entry_run(steps):
-            for i in range(steps + 2):
-                if i < steps:
-                    ctx.detect_pages_host(host_pages, bs_, c_, k_, det.cfg.canny_lo, det.cfg.canny_hi, ml, chunk_pages=10,
-                                          want_centroids=False, out=outs[i % 3])
-                    evs[i % 3].record()
-                if i >= 2:
-                    evs[(i - 2) % 3].synchronize()
-                    on_result(i - 2, outs[(i - 2) % 3][0], outs[(i - 2) % 3][1])
+    # ---- end to end through the public API: pinned host pages -> validated regions --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def run_e2e(host, channels):
+            streamer = PageStreamer(det, B, h, w, slots=3, chunk_pages=10, channels=channels)
+            n_regions = [0]
 
-        host_entry_run(max(1, W_ // 2))
-        barrier()
-        t0 = time.perf_counter()
-        host_entry_run(K)
-        torch.cuda.synchronize()
-        dt_c = time.perf_counter() - t0
-        tdc = torch.tensor([dt_c], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tdc, op=dist.ReduceOp.MAX)
-        dt_c = float(tdc.item())
-        # the PCIe bound of this step: the same pinned batch copied alone (no compute), CUDA events
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        streamer.dev_pages[0].copy_(host_pages, non_blocking=True)
-        torch.cuda.synchronize()
-        c0.record()
-        for _ in range(3):
-            streamer.dev_pages[0].copy_(host_pages, non_blocking=True)
-        c1.record()
-        torch.cuda.synchronize()
-        h2d_ms = c0.elapsed_time(c1) / 3
-        e2e = {"value": world * K * B / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // K,
-               "d2h_bytes_per_step": streamer.d2h_bytes // K, "ms_per_step": 1000.0 * dt / K,
-               "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": host_pages.numel() / h2d_ms / 1e6,
-               "frac_of_pcie_bound": h2d_ms / (1000.0 * dt / K),
-               "c_abi_host_entry": {"value": world * K * B / dt_c, "unit": UNIT, "ms_per_step": 1000.0 * dt_c / K,
-                                    "call": "synseg_detect_pages_host, 10-page chunks through 3 staging slots inside the library"},
-               "host_pages_numa_bound_cpus": numa.applied,
-               "includes": "pinned H2D (3 slots, copy stream), fused pipeline, D2H of component tables, host box filter/merge (geometry.py)"}
-        del streamer
+            def on_regions(i, regs):
+                n_regions[0] += sum(len(r) for r in regs)
+
+            streamer.run((host for _ in range(max(2, W_ // 2))), on_regions=on_regions)
+            barrier()
+            streamer.h2d_bytes = streamer.d2h_bytes = 0
+            n_regions[0] = 0
+            t0 = time.perf_counter()
+            streamer.run((host for _ in range(K)), on_regions=on_regions)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            # the bound of this stage on this box: the same pinned batch copied by EVERY rank at the same time, nothing else running
+            buf = torch.empty_like(host, device=dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            buf.copy_(host, non_blocking=True)
+            barrier()
+            c0.record()
+            for _ in range(3):
+                buf.copy_(host, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            h2d_ms = max_over_ranks(c0.elapsed_time(c1) / 3)
+            del buf
+            return {"value": world * K * B / dt, "unit": UNIT, "h2d_bytes_per_step": streamer.h2d_bytes // K,
+                    "d2h_bytes_per_step": streamer.d2h_bytes // K, "ms_per_step": 1000.0 * dt / K,
+                    "validated_regions_per_step": n_regions[0] / K,
+                    "bare_h2d": {"ms_per_step": h2d_ms, "GBps_per_gpu": host.numel() / h2d_ms / 1e6, "pages_per_s_bound": world * B / (h2d_ms / 1e3),
+                                 "what": f"the same pinned batch copied alone by all {world} rank(s) concurrently (barrier, CUDA events, max over ranks)"},
+                    "frac_of_bare_h2d_bound": h2d_ms / (1000.0 * dt / K)}
+
+        e2e = run_e2e(host_pages, 3)
+        e2e["call"] = ("PageStreamer.run(on_regions=...) -> synseg_detect_regions_host: pinned H2D in 10-page chunks through a 3-slot device ring on "
+                       "the library's copy stream, fused pipeline, region rules + crop moments on the device, D2H of the region and component "
+                       "tables, host: _validate_embedded_image score, keep >= 0.5, sort (what detect_regions_batch returns)")
+        # the same pages handed over as 'L' (the handoff allows RGB or L, pdf_image_segmentation.py:3638-3657): one third of the PCIe bytes
+        import cv2
+        with gpu_numa_affinity(local):
+            host_grey = torch.empty((B, h, w), dtype=torch.uint8).pin_memory()
+            hp = host_pages.numpy()
+            for i in range(B):
+                cv2.cvtColor(hp[i], cv2.COLOR_RGB2GRAY, dst=host_grey.numpy()[i])
+        e2e["grey_pages"] = run_e2e(host_grey, 1)
+        e2e["host_pages_numa_bound_cpus"] = numa.applied
+        e2e["numa"] = numa_info(local)
+        del host_grey
     clocks = sampler.stop() if sampler is not None else None     # sampled over both timed regions (resident steps and end-to-end streaming)
 
     # ---- per-kernel timing of profiled steps (same run, same stream) -> roofline of the dominant kernel -------
     peak, peak_src = load_peak()
     PROF_STEPS = 3
-    agg = {}
-    for _ in range(PROF_STEPS):
-        torch.cuda.synchronize()
-        ctx.profile_begin()
-        det.detect_components(pages, out=out)
-        for name, ms in ctx.profile_end():
-            a = agg.setdefault(name, [0.0, 0])
-            a[0] += ms
-            a[1] += 1
-    step_ms = sum(a[0] for a in agg.values()) / PROF_STEPS
-    kernels = {name: {"ms_per_step": a[0] / PROF_STEPS, "launches_per_step": a[1] // PROF_STEPS,
-                      "share": (a[0] / PROF_STEPS) / step_ms} for name, a in agg.items()}
+
+    def profile(src):
+        agg = {}
+        for _ in range(PROF_STEPS):
+            torch.cuda.synchronize()
+            ctx.profile_begin()
+            det.detect_components(src, out=out)
+            for name, ms in ctx.profile_end():
+                a = agg.setdefault(name, [0.0, 0])
+                a[0] += ms
+                a[1] += 1
+        step_ms = sum(a[0] for a in agg.values()) / PROF_STEPS
+        return step_ms, {name: {"ms_per_step": a[0] / PROF_STEPS, "launches_per_step": a[1] // PROF_STEPS,
+                                "share": (a[0] / PROF_STEPS) / step_ms} for name, a in agg.items()}
+
+    step_ms, kernels = profile(pages)
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
     launch_ms = dk["ms_per_step"] / max(1, dk["launches_per_step"])
     alg_bytes = ALG_BYTES_PER_PX.get(dom, 1.0) * npx * B
     achieved = alg_bytes / (launch_ms / 1000.0) / 1e9
     traffic = None                      # DRAM bytes per launch of that kernel from the committed ncu capture
+    binding = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tj.get("pages_per_launch") == B and dom in tj["kernels"]:
             traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
+            binding = tj["kernels"][dom].get("binding")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "share_of_step": dk["share"],
                 "serial_step_ms": step_ms,
-                "note": "per-kernel times from profiled steps that run every kernel alone on one stream; the timed region runs "
-                        "the page chunks of a step on two streams (SYNSEG_OVERLAP, default 2), so ms_per_step < serial_step_ms",
+                "binding_resource": binding,
+                "note": "frac is the HBM fraction the contract asks for; the kernel's BINDING resource (from the committed ncu capture, "
+                        "profiles/traffic.json) is reported in binding_resource. Per-kernel times come from profiled steps that run every "
+                        "kernel alone on one stream; the timed region runs the page chunks of a step on two streams (SYNSEG_OVERLAP)",
                 "page_level": {"algorithmic_bytes_per_page": 19.0 * npx, "achieved": 19.0 * npx * B / (step_ms / 1000.0) / 1e9,
                                "frac": 19.0 * npx * B / (step_ms / 1000.0) / 1e9 / peak},
                 "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "share": round(v["share"], 4),
                                 "launches": v["launches_per_step"],
                                 "GBps": round(ALG_BYTES_PER_PX.get(k, 0.0) * npx * B / max(v["ms_per_step"] / max(1, v["launches_per_step"]), 1e-9) / 1e6, 1)}
                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+
+    # ---- dense pages: the content-dependent worst case (no blank paper anywhere), rank 0 at N=1 ----------------------
+    dense = None
+    if rank == 0 and world == 1 and not args.no_dense:
+        nd = min(args.unique, B)
+        hd = torch.empty((B, h, w, 3), dtype=torch.uint8)
+        for i in range(nd):
+            hd.numpy()[i] = dense_page(i, args.dpi)
+        for i in range(nd, B):
+            hd.numpy()[i] = hd.numpy()[i % nd]
+        dpages = hd.to(dev)
+        for i in range(W_):
+            det.detect_components(dpages, out=out)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        d0.record()
+        for i in range(K):
+            det.detect_components(dpages, out=out)
+        d1.record()
+        torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1) / K
+        dstep, dk_ = profile(dpages)
+        dense = {"value": B / (dms / 1e3), "unit": UNIT, "ms_per_step": dms, "ratio_to_text_pages": (B / (dms / 1e3)) / (value / world),
+                 "workload": f"{B} resident pages per step from {nd} unique dense pages (synth.dense_page: full-bleed scan texture with sensor noise, "
+                             "edge-to-edge text, two figures; no blank row, no constant 16-pixel group)",
+                 "components_per_page": float(out[0].float().abs().mean()),
+                 "kernels_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(dk_.items(), key=lambda kv: -kv[1]["ms_per_step"])[:8]}}
+        del dpages, hd
+
+    # ---- fixed global corpus sharded over the ranks: the survivor set must not depend on N ---------------------------
+    corpus = None
+    if not args.no_corpus:
+        CN, CDPI = 400, 150
+        ch_, cw_ = page_shape(CDPI)
+        cdet = RasterRegionDetector(DetectConfig(dpi=CDPI, max_labels=1024), ctx=ctx)
+        mine = dedup.shard_pages(CN, rank, world)
+        ccap = 16 * CN
+        crois = torch.empty((ccap, 5), dtype=torch.int32, device=dev)
+        ckeys = torch.empty(ccap, dtype=torch.int64, device=dev)
+        chash = torch.empty(ccap, dtype=torch.int64, device=dev)
+        ccount = torch.zeros(1, dtype=torch.int32, device=dev)
+        cex = dedup.DedupExchange(ctx, ccap, comm_world, max_hamming=4)
+        cs_ = CDPI / 72.0
+        for p0 in range(mine.start, mine.stop, 50):
+            nb = min(50, mine.stop - p0)
+            cp = torch.from_numpy(synth_pages(nb, CDPI, base_seed=4321, start=p0)).to(dev)
+            n_, st_, _ = cdet.detect_components(cp)
+            c_before = int(ccount.item())
+            ctx.select_rois(n_, st_, p0, int(5000 * cs_ * cs_), int(0.8 * ch_ * cw_), int(50 * cs_), int(50 * cs_), crois, ckeys, ccount)
+            c_after = min(int(ccount.item()), ccap)
+            if c_after > c_before:                 # hash this batch's boxes while its pages are resident (roi.image indexes the batch)
+                chash[c_before:c_after] = ctx.phash(cp, 1, crois[c_before:c_after].cpu().numpy().tolist())
+        cex.run(chash, ckeys, ccount)
+        ck, ckeep = cex.result()
+        corpus = {"pages": CN, "dpi": CDPI, "regions_hashed": int(ck.numel()), "survivors": int(ckeep.sum()),
+                  "survivors_digest": dedup.survivors_digest(ck, ckeep),
+                  "what": f"{CN} fixed seeded pages sharded over {world} rank(s) (contiguous blocks), candidate boxes hashed per rank, one "
+                          "synseg_dedup_exchange; the digest (sha1 of the surviving keys) is the same at every N"}
+
+    # ---- config 4: 10k crops, rank 0 at N=1 -----------------------------------------------------------------------
+    crops = None
+    if rank == 0 and world == 1 and args.crops > 0:
+        del pages
+        torch.cuda.empty_cache()
+        crops = crops_line(ctx, args.crops)
 
     # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------------------
     cpu = None
@@ -455,11 +601,17 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": workload_config(args, world, h, w),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        line["dedup"] = {"regions_hashed": int(k_all.numel()), "survivors": n_survivors,
-                         "collective": "nccl all_gather_into_tensor" if world > 1 else "none (single GPU)"}
+        info = dedup.comm_info(ctx)
+        line["dedup"] = {"regions_hashed": n_hashed, "survivors": n_survivors, "capacity_overflow": overflow,
+                         "collective": (f"ncclAllGather inside synseg_dedup_exchange (library communicator, {info['world']} ranks, NCCL {info['nccl_version']})"
+                                        if world > 1 else "none (single GPU)"),
+                         "fixed_corpus": corpus}
+        line["crops"] = crops
+        line["dense_pages"] = dense
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        ctx.lib.synseg_comm_destroy(ctx._h)
         dist.destroy_process_group()
     ctx.close()
 

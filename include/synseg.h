@@ -150,6 +150,24 @@ int synseg_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const syn
 int synseg_phash_dedup(synseg_ctx *ctx, const uint64_t *hashes, const uint64_t *keys, int32_t n, int32_t max_hamming,
                        uint8_t *keep, void *stream);
 
+/* ---- the exchange step over all GPUs ------------------------------------------------------------- */
+/* One process per GPU.  Bootstrap: rank 0 calls synseg_comm_unique_id and hands the 128 bytes to the other ranks by any
+ * means (the host code uses torch.distributed's store); every rank then calls synseg_comm_init(ctx, id, rank, world).
+ * NCCL is bound at run time (the libnccl.so.2 already in the process, else the system one); world == 1 needs none. */
+int synseg_comm_unique_id(uint8_t *id128);
+int synseg_comm_init(synseg_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world);
+int synseg_comm_destroy(synseg_ctx *ctx);
+int synseg_comm_info(const synseg_ctx *ctx, int32_t *rank, int32_t *world, int32_t *nccl_version);
+/* Cross-page duplicate removal in one call, everything queued on `stream`, no host synchronisation: this rank's
+ * (hashes[i], keys[i]) for i < *count (count: DEVICE int32, clamped to capacity) travel in ONE ncclAllGather of
+ * fixed-capacity blocks; then every rank computes, identically,
+ *   all_keys  uint64[world * capacity]  the keys of all ranks in ascending order (all_hashes alongside, may be NULL),
+ *   keep      uint8 [world * capacity]  0 iff an entry with a smaller key lies within max_hamming bits,
+ *   n_total   DEVICE int32              number of valid entries.
+ * Keys must be unique over all ranks (page index << 16 | region index). */
+int synseg_dedup_exchange(synseg_ctx *ctx, const uint64_t *hashes, const uint64_t *keys, const int32_t *count, int32_t capacity,
+                          int32_t max_hamming, uint64_t *all_keys, uint64_t *all_hashes, uint8_t *keep, int32_t *n_total, void *stream);
+
 /* ---- fused page pipeline ------------------------------------------------------------------- */
 typedef struct synseg_detect_params {
     int32_t block_size;   /* adaptive threshold window (odd) : (dpi/6)|1      -> 51 @300 DPI */
@@ -314,6 +332,16 @@ int synseg_hints_crops(synseg_ctx *ctx, const void *base, const synseg_crop *cro
  * crops_host is a HOST array; everything is queued on `stream` without synchronising. */
 int synseg_colors_crops(synseg_ctx *ctx, const void *base, const synseg_crop *crops_host, int32_t n, int32_t n_colors,
                         int32_t iters, int32_t min_pixels, uint64_t *out, uint32_t *hist_out, void *stream);
+
+/* The two batched hint calls on regions of pages that are ALREADY in device memory (rois_host: HOST array of (page, x, y, w, h),
+ * e.g. the px/py/pw/ph of synseg_region): the kernels read the regions in place, nothing is packed or uploaded again.
+ * out as synseg_hints_crops / synseg_colors_crops.  channels 3: RGB pages; 1: grey pages (hints only).  The page allocation must be
+ * readable 16 bytes past its last pixel (the 128-bit loads of a region touching the last row may look that far; any
+ * cudaMalloc / torch allocation that is not an exact multiple of 512 bytes is). */
+int synseg_hints_rois(synseg_ctx *ctx, const synseg_img *pages, int channels, const synseg_roi *rois_host, int32_t n, int kw, int kh,
+                      uint64_t *out, void *stream);
+int synseg_colors_rois(synseg_ctx *ctx, const synseg_img *pages, const synseg_roi *rois_host, int32_t n, int32_t n_colors,
+                       int32_t iters, int32_t min_pixels, uint64_t *out, uint32_t *hist_out, void *stream);
 
 #ifdef __cplusplus
 }

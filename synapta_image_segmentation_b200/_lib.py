@@ -91,6 +91,14 @@ SIGNATURES = {
     "synseg_page_slots_numa_node": (C.c_int, [C.c_void_p]),
     "synseg_hints_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "synseg_colors_crops": (C.c_int, [C.c_void_p, C.c_void_p, _P(Crop), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "synseg_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "synseg_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "synseg_comm_destroy": (C.c_int, [C.c_void_p]),
+    "synseg_comm_info": (C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
+    "synseg_dedup_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
+    "synseg_hints_rois": (C.c_int, [C.c_void_p, _P(Img), C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "synseg_colors_rois": (C.c_int, [C.c_void_p, _P(Img), _P(Roi), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "synseg_grid_counts": (C.c_int, [C.c_void_p, _P(Img), C.c_int, C.c_int, _P(Roi), C.c_int32, C.c_int, C.c_int, C.c_void_p, _P(Img), C.c_void_p]),
 }
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsynseg.so")
-SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "ccl.cu", "reduce.cu", "phash.cu", "colors.cu", "regions.cu", "pipeline.cu"]
+SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "ccl.cu", "reduce.cu", "phash.cu", "colors.cu", "regions.cu", "exchange.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("SYNSEG_NVCC_EXTRA", "").split()
 
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-Xlinker", "--exclude-libs,ALL"]
+               "-Xlinker", "--exclude-libs,ALL", "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), res.stderr))

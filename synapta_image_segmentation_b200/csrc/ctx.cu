@@ -44,6 +44,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->arena = nullptr; c->arena_bytes = 0; c->arena_top = 0; c->launches = 0; c->phash_basis = nullptr;
     c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
+    c->comm = nullptr; c->comm_world = 1; c->comm_rank = 0;
     c->attr_done = 0; c->last_stream = nullptr; c->ev_last = nullptr; c->last_valid = false;
     memset(&c->hs, 0, sizeof(c->hs));
     const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
@@ -79,6 +80,7 @@ extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->phash_basis) cudaFree(ctx->phash_basis);
     host_stream_release(ctx);
+    comm_release(ctx);
     if (ctx->ev_split_fork) cudaEventDestroy(ctx->ev_split_fork);
     for (int i = 0; i < 3; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);

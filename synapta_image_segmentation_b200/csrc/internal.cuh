@@ -30,6 +30,8 @@ struct synseg_ctx {
     size_t arena_top;     // bump pointer, reset at the start of every public call
     int64_t launches;     // kernels launched through this context
     int32_t *phash_basis; // device int32[8*32]
+    void *comm;           // ncclComm_t of the dedup exchange (exchange.cu), NULL on a single GPU
+    int comm_world, comm_rank;
     uint32_t attr_done;   // ATTR_* bits: cudaFuncSetAttribute calls already made on THIS device (the attribute is per device)
     // stream ordering of the shared scratch arena: every public call records `ev_last` on its stream when it returns; a
     // call arriving on a different stream first waits for it (SS_ENTER)
@@ -118,6 +120,7 @@ struct DeviceScope {
 
 void prof_mark(synseg_ctx *ctx, const char *name, cudaStream_t st);
 void host_stream_release(synseg_ctx *ctx);
+void comm_release(synseg_ctx *ctx);
 
 void synseg_set_error(const char *fmt, ...);
 int synseg_check_cuda(cudaError_t e, const char *what);

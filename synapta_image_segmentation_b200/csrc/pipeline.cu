@@ -426,6 +426,52 @@ extern "C" SYNSEG_EXPORT int synseg_hints_crops(synseg_ctx *ctx, const void *bas
     return SYNSEG_OK;
 }
 
+// ---- hints on regions of pages that are already in HBM ----------------------------------------------------------
+// The detector knows every region's crop rectangle (synseg_region px/py/pw/ph) and the pages are still resident: the hint
+// kernels read the regions in place (a crop descriptor = byte offset + the page's row stride) instead of taking re-uploaded crops.
+static int rois_to_crops(const char *who, const synseg_img *pages, int channels, const synseg_roi *rois, int32_t n, std::vector<synseg_crop> &crops)
+{
+    crops.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const synseg_roi &r = rois[i];
+        if (r.image < 0 || r.image >= pages->batch || r.x < 0 || r.y < 0 || r.width <= 0 || r.height <= 0 || r.x + r.width > pages->width ||
+            r.y + r.height > pages->height) {
+            synseg_set_error("%s: region %d outside the pages", who, i); return SYNSEG_E_INVALID;
+        }
+        synseg_crop &c = crops[i];
+        c.offset = (uint64_t)((int64_t)r.image * pages->batch_stride + (int64_t)r.y * pages->row_stride + (int64_t)r.x * channels);
+        c.width = r.width; c.height = r.height; c.row_stride = pages->row_stride; c.channels = channels; c._pad = 0;
+    }
+    return SYNSEG_OK;
+}
+
+extern "C" SYNSEG_EXPORT int synseg_hints_rois(synseg_ctx *ctx, const synseg_img *pages, int channels, const synseg_roi *rois_host, int32_t n, int kw, int kh,
+                                               uint64_t *out, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_hints_rois: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
+    if (channels != 1 && channels != 3) { synseg_set_error("synseg_hints_rois: channels must be 1 or 3"); return SYNSEG_E_INVALID; }
+    SS_TRY(validate_img(pages, "pages", channels));
+    if (n <= 0) return SYNSEG_OK;
+    if (!rois_host || !out) { synseg_set_error("synseg_hints_rois: NULL argument"); return SYNSEG_E_INVALID; }
+    std::vector<synseg_crop> crops;
+    SS_TRY(rois_to_crops("synseg_hints_rois", pages, channels, rois_host, n, crops));
+    return synseg_hints_crops(ctx, pages->data, crops.data(), n, kw, kh, out, stream);
+}
+
+extern "C" SYNSEG_EXPORT int synseg_colors_rois(synseg_ctx *ctx, const synseg_img *pages, const synseg_roi *rois_host, int32_t n, int32_t n_colors,
+                                                int32_t iters, int32_t min_pixels, uint64_t *out, uint32_t *hist_out, void *stream)
+{
+    if (!ctx) { synseg_set_error("synseg_colors_rois: ctx is NULL"); return SYNSEG_E_INVALID; }
+    SS_ENTER(ctx, stream);
+    SS_TRY(validate_img(pages, "pages", 3));
+    if (n <= 0) return SYNSEG_OK;
+    if (!rois_host || !out) { synseg_set_error("synseg_colors_rois: NULL argument"); return SYNSEG_E_INVALID; }
+    std::vector<synseg_crop> crops;
+    SS_TRY(rois_to_crops("synseg_colors_rois", pages, 3, rois_host, n, crops));
+    return synseg_colors_crops(ctx, pages->data, crops.data(), n, n_colors, iters, min_pixels, out, hist_out, stream);
+}
+
 // ---- host-buffer entry points ---------------------------------------------------------------------------------
 #include <sys/syscall.h>
 #include <unistd.h>

@@ -58,14 +58,78 @@ def gather_hashes(hashes: torch.Tensor, keys: torch.Tensor, capacity: int, group
     return h_sorted[:n_valid], k_sorted[:n_valid]
 
 
+def init_comm(ctx, group=None) -> int:
+    """Creates the library's own NCCL communicator over the ranks of the (already initialised) torch.distributed group:
+    rank 0 draws the unique id (synseg_comm_unique_id), torch.distributed's store carries its 128 bytes to the other ranks,
+    every rank calls synseg_comm_init.  Returns the world size (1: nothing to do)."""
+    import ctypes as C
+    from ._lib import check
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(ctx.lib.synseg_comm_unique_id(buf), "synseg_comm_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    check(ctx.lib.synseg_comm_init(ctx._h, ident, rank, world), "synseg_comm_init")
+    return world
+
+
+def comm_info(ctx):
+    import ctypes as C
+    r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+    ctx.lib.synseg_comm_info(ctx._h, C.byref(r), C.byref(w), C.byref(v))
+    return dict(rank=r.value, world=w.value, nccl_version=v.value)
+
+
+class DedupExchange:
+    """Device buffers + the one call of the exchange step (synseg_dedup_exchange: pack, ONE ncclAllGather, replicated
+    rank-and-dedup kernels).  `run` queues everything on the current stream and returns device tensors; nothing in it
+    synchronises the host or launches a torch kernel."""
+
+    def __init__(self, ctx, capacity: int, world: int = 1, max_hamming: int = 4):
+        dev = ctx.device
+        self.ctx, self.capacity, self.world, self.max_hamming = ctx, capacity, world, max_hamming
+        total = capacity * world
+        self.all_keys = torch.empty(total, dtype=torch.int64, device=dev)
+        self.all_hashes = torch.empty(total, dtype=torch.int64, device=dev)
+        self.keep = torch.empty(total, dtype=torch.uint8, device=dev)
+        self.n_total = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def run(self, hashes: torch.Tensor, keys: torch.Tensor, count: torch.Tensor):
+        from ._lib import check
+        c = self.ctx
+        check(c.lib.synseg_dedup_exchange(c._h, hashes.data_ptr(), keys.data_ptr(), count.data_ptr(), self.capacity, self.max_hamming,
+                                          self.all_keys.data_ptr(), self.all_hashes.data_ptr(), self.keep.data_ptr(), self.n_total.data_ptr(), c._s()),
+              "synseg_dedup_exchange")
+        return self.all_keys, self.keep, self.n_total
+
+    def result(self):
+        """(keys int64 [n] ascending, keep uint8 [n]) on the host -- the one synchronisation of the step."""
+        n = int(self.n_total.item())
+        return self.all_keys[:n].cpu(), self.keep[:n].cpu()
+
+
+def survivors_digest(keys: torch.Tensor, keep: torch.Tensor) -> str:
+    """sha1 over the surviving keys in ascending order: equal on every rank and for every world size over the same corpus."""
+    import hashlib
+    k = keys[keep.bool()].cpu().numpy().astype("<i8")
+    return hashlib.sha1(k.tobytes()).hexdigest()[:16]
+
+
 def cross_page_dedup(ctx, hashes: torch.Tensor, keys: torch.Tensor, capacity: int, max_hamming: int = 4, group=None, phases=None):
-    """Returns (all_keys int64 [N] sorted, keep uint8 [N]) -- identical on every rank.
-    phases: optional list that receives wall-clock stamps after the gather and after the dedup kernel (diagnostics)."""
+    """Returns (all_keys int64 [N] sorted, keep uint8 [N]) -- identical on every rank.  CUDA tensors go through the
+    library's exchange (the communicator of `init_comm` when the job has several ranks); CPU tensors (the gloo host-logic
+    tests) through `gather_hashes`."""
+    if hashes.is_cuda:
+        world = comm_info(ctx)["world"]
+        ex = DedupExchange(ctx, capacity, world, max_hamming)
+        count = torch.tensor([hashes.numel()], dtype=torch.int32, device=hashes.device)
+        ex.run(hashes.contiguous(), keys.contiguous(), count)
+        k, keep = ex.result()
+        return k.to(hashes.device), keep.to(hashes.device)
     h, k = gather_hashes(hashes, keys, capacity, group)
-    if phases is not None:
-        import time
-        torch.cuda.synchronize(); phases.append(time.perf_counter())
     keep = ctx.phash_dedup(h, k, max_hamming)
-    if phases is not None:
-        torch.cuda.synchronize(); phases.append(time.perf_counter())
     return k, keep

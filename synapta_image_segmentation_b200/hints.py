@@ -407,17 +407,43 @@ class FeatureHints:
             first += len(descs)
         res = torch.cat(results).cpu().numpy()
         col = torch.cat(colours).cpu().numpy()
-        out = []
-        for (v, w, h, ch, _), r, cr in zip(views, res, col):
-            n = w * h
-            s1, s2 = int(r[3]), int(r[4])
-            var = (n * s2 - s1 * s1) / (n * n)
-            out.append(dict(h_count=int(r[0]), v_count=int(r[1]), edge_px=int(r[2]), grid_detected=bool(r[0] > 300 and r[1] > 300),
-                            variance=var, mask_px=int(r[6]), data_points_fallback=min(int(r[2]) // 150, 500),
-                            image_subtype_visual="photo" if var > 1500 else "illustration"))
-            c = FeatureHints.decode_colors(cr)
-            out[-1].update(dominant_colors=c["dominant_colors"], color_weights=c["color_weights"])
+        return [FeatureHints._hint_dict(r, w * h, cr) for (v, w, h, ch, _), r, cr in zip(views, res, col)]
+
+
+    @staticmethod
+    def hints_regions(pages: torch.Tensor, regions_per_page, with_colors: bool = True) -> List[List[Dict[str, Any]]]:
+        """`hints_batch` for regions of pages that are still on the device (the normal case right after detection): per page,
+        per region dict (as `RasterRegionDetector.detect_regions_batch` returns them: 'crop_px' = x, y, w, h) the same hint
+        dict as `hints_batch` gives for the cropped PIL image -- read in place by `synseg_hints_rois` / `synseg_colors_rois`,
+        no crop is cut, packed or uploaded.  pages: CUDA u8 [B,H,W,3] (or grey [B,H,W]: no colours)."""
+        ctx = get_context(pages.device.index)
+        rois = [(i,) + tuple(r["crop_px"]) for i, regs in enumerate(regions_per_page) for r in regs]
+        if not rois:
+            return [[] for _ in regions_per_page]
+        grey = pages.dim() == 3 and not (pages.shape[-1] == 3 and pages.stride(-2) == 3)
+        res = ctx.hints_rois(pages, rois).cpu().numpy()
+        col = ctx.colors_rois(pages, rois).cpu().numpy() if (with_colors and not grey) else None
+        out, j = [], 0
+        for regs in regions_per_page:
+            cur = []
+            for r in regs:
+                _, _, w, h = r["crop_px"]
+                cur.append(FeatureHints._hint_dict(res[j], w * h, col[j] if col is not None else None))
+                j += 1
+            out.append(cur)
         return out
+
+    @staticmethod
+    def _hint_dict(r, n: int, cr) -> Dict[str, Any]:
+        s1, s2 = int(r[3]), int(r[4])
+        var = (n * s2 - s1 * s1) / (n * n)
+        d = dict(h_count=int(r[0]), v_count=int(r[1]), edge_px=int(r[2]), grid_detected=bool(r[0] > 300 and r[1] > 300),
+                 variance=var, mask_px=int(r[6]), data_points_fallback=min(int(r[2]) // 150, 500),
+                 image_subtype_visual="photo" if var > 1500 else "illustration")
+        if cr is not None:
+            c = FeatureHints.decode_colors(cr)
+            d.update(dominant_colors=c["dominant_colors"], color_weights=c["color_weights"])
+        return d
 
 
 def _copy_views(hv: np.ndarray, views, descs, pool=None) -> None:

@@ -448,6 +448,34 @@ class Context:
               "synseg_colors_crops")
         return out, hist
 
+    def hints_rois(self, pages: torch.Tensor, rois, kw: int = 25, kh: int = 25, channels: Optional[int] = None) -> torch.Tensor:
+        """`hints_crops` on regions [(page, x, y, w, h), ...] of pages already on the device (read in place).  int64 [n, 8]."""
+        if channels is None:
+            img, channels, b = self._page_img(pages)
+        else:
+            img, b = self._img(pages, channels), _as3(pages, channels).shape[0]
+        a = rois_array(rois)
+        n = a.shape[0]
+        out = torch.empty((n, 8), dtype=torch.int64, device=pages.device)
+        if n:
+            p = _as3(pages, channels)
+            self._check_rois(a, p.shape[0], p.shape[1], p.shape[2])
+            check(self.lib.synseg_hints_rois(self._h, C.byref(img), channels, a.ctypes.data_as(C.POINTER(Roi)), n, kw, kh, C.c_void_p(out.data_ptr()),
+                                             self._s()), "synseg_hints_rois")
+        return out
+
+    def colors_rois(self, pages: torch.Tensor, rois, n_colors: int = 5, iters: int = 20, min_pixels: int = 100) -> torch.Tensor:
+        """`colors_crops` on regions of RGB pages already on the device.  int64 [n, 2 + n_colors]."""
+        a = rois_array(rois)
+        n = a.shape[0]
+        out = torch.empty((n, 2 + n_colors), dtype=torch.int64, device=pages.device)
+        if n:
+            p = _as3(pages, 3)
+            self._check_rois(a, p.shape[0], p.shape[1], p.shape[2])
+            check(self.lib.synseg_colors_rois(self._h, C.byref(self._img(pages, 3)), a.ctypes.data_as(C.POINTER(Roi)), n, n_colors, iters, min_pixels,
+                                              C.c_void_p(out.data_ptr()), None, self._s()), "synseg_colors_rois")
+        return out
+
     def grid_counts(self, src: torch.Tensor, rois=None, gray_mode: int = GRAY_PIL, kw: int = 25, kh: int = 25,
                     want_edges: bool = False, channels: Optional[int] = None):
         """Per region (h_count, v_count, edge_px) int64 [n,3] (+ edges u8 [n,maxH,maxW] when want_edges)."""

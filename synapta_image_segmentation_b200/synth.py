@@ -125,6 +125,38 @@ def synth_page(page_idx: int, dpi: int = 300, base_seed: int = 1234, n_figures: 
     return page, truth
 
 
+def dense_page(page_idx: int, dpi: int = 300, base_seed: int = 1234) -> np.ndarray:
+    """A page without any blank paper: full-bleed low-pass "scan" background with per-pixel sensor noise, text boxes from edge
+    to edge and two photo blocks.  It bounds the content-dependent cost of the stencils from above (their blank-row and
+    constant-group shortcuts never fire); bench.py times it beside the text pages.  Pure function of (base_seed, page_idx, dpi)."""
+    h, w = page_shape(dpi)
+    s = dpi / 72.0
+    rng = np.random.default_rng([base_seed, 900_000 + page_idx])
+    low = rng.normal(0, 1, (max(4, h // 96), max(4, w // 96)))
+    f = _upsample(low, h, w)
+    f = (f - f.mean()) / (f.std() + 1e-9)
+    page = np.empty((h, w, 3), np.uint8)
+    for c in range(3):
+        noise = rng.integers(-8, 9, (h, w))
+        page[:, :, c] = np.clip(205 + 22 * f + noise, 0, 255).astype(np.uint8)
+    pitch = int(np.ceil(12 * s)); wh = int(7 * s); gap = int(4 * s)
+    for ry in range(gap, h - wh, pitch):
+        widths = (rng.uniform(5, 30, 96) * s).astype(int)
+        shades = rng.integers(0, 61, 96)
+        x = gap
+        for wd, sh in zip(widths, shades):
+            if x + wd > w - gap:
+                break
+            page[ry:ry + wh, x:x + wd] = sh
+            x += wd + gap
+    for k in range(2):
+        fig = render_figure([base_seed, 800_000 + page_idx, k], dpi, h // 3, w // 2)
+        fh, fw = fig.shape[:2]
+        y0 = int(rng.integers(0, h - fh)); x0 = int(rng.integers(0, w - fw))
+        page[y0:y0 + fh, x0:x0 + fw] = fig
+    return page
+
+
 def synth_pages(n: int, dpi: int = 300, base_seed: int = 1234, start: int = 0, n_figures: int | None = None,
                 out: np.ndarray | None = None) -> np.ndarray:
     """[n, H, W, 3] u8 batch (optionally into a caller-provided, e.g. pinned, array)."""

@@ -358,3 +358,63 @@ def test_two_pass_priors_on_the_gpu(ctx):
     segs = det.extract_segments(page, 0, "textbook_001", priors=[priors["far away"]])
     capseg = [s for s in segs if s.extraction_method == "caption_based"][0]
     assert capseg.caption_text == "Exhibit 9" and capseg.notes == "" and capseg.confidence == 0.9 and capseg.page_no == 1
+
+
+def test_hints_on_resident_regions_equal_hints_on_crops(ctx):
+    """synseg_hints_rois / synseg_colors_rois read the detector's regions in place on the pages in HBM; same numbers as the crops
+    cut out, packed and uploaded (hints_batch), which the goldens pin to the reference."""
+    from synapta_image_segmentation_b200.hints import FeatureHints
+    dpi = 150
+    det = RasterRegionDetector(DetectConfig(dpi=dpi), ctx=ctx)
+    pages = synth_pages(6, dpi, base_seed=17)
+    t = torch.from_numpy(pages).cuda()
+    regions = det.detect_regions_batch(t)
+    got = FeatureHints.hints_regions(t, regions)
+    crops = [Image.fromarray(np.ascontiguousarray(pages[i][y:y + h, x:x + w])) for i, regs in enumerate(regions) for (x, y, w, h) in [r["crop_px"] for r in regs]]
+    want = FeatureHints.hints_batch(crops)
+    flat = [hd for page in got for hd in page]
+    assert len(flat) == len(want) >= 6
+    assert flat == want
+    # a region that ends on the very last pixel of the last page, and grey pages (no colours)
+    h, w = pages.shape[1], pages.shape[2]
+    edge = [[] for _ in range(5)] + [[{"crop_px": (w - 333, h - 200, 333, 200)}]]
+    e = FeatureHints.hints_regions(t, edge)[5][0]
+    assert e == FeatureHints.hints_batch([Image.fromarray(np.ascontiguousarray(pages[5][h - 200:, w - 333:]))])[0]
+    import cv2
+    grey = np.stack([cv2.cvtColor(p, cv2.COLOR_RGB2GRAY) for p in pages])
+    g = FeatureHints.hints_regions(torch.from_numpy(grey).cuda(), regions)
+    gw = FeatureHints.hints_batch([Image.fromarray(np.ascontiguousarray(grey[i][y:y + hh, x:x + ww])) for i, regs in enumerate(regions)
+                                   for (x, y, ww, hh) in [r["crop_px"] for r in regs]])
+    assert [{k: v for k, v in d.items()} for page in g for d in page] == [{k: v for k, v in d.items() if k not in ("dominant_colors", "color_weights")} for d in gw]
+
+
+def test_dedup_exchange_equals_sorted_all_pairs(ctx):
+    """synseg_dedup_exchange at world = 1 (pack -> compact -> rank + all-pairs -> scatter): keys ascending, keep flags equal to the
+    plain all-pairs rule on the sorted list; entries past *count are ignored; order of the input does not matter."""
+    from synapta_image_segmentation_b200.dedup import DedupExchange, survivors_digest
+    rng = np.random.default_rng(8)
+    n, cap = 3000, 4096
+    base = rng.integers(0, 2 ** 63 - 1, 600, dtype=np.int64)
+    hashes = base[rng.integers(0, 600, n)] ^ (np.int64(1) << rng.integers(0, 63, n)) * (rng.random(n) < 0.5)      # near-duplicates (1 bit apart)
+    keys = rng.permutation(n * 7)[:n].astype(np.int64) << 16
+    ks = np.argsort(keys)
+    hk, kk = hashes[ks], keys[ks]
+    x = (hk[:, None] ^ hk[None, :]).view(np.uint64)
+    pop = np.zeros(x.shape, np.int32)
+    for b in range(64):
+        pop += ((x >> np.uint64(b)) & np.uint64(1)).astype(np.int32)
+    want_keep = ~((pop <= 4) & (np.arange(n)[None, :] < np.arange(n)[:, None])).any(1)
+    for trial in range(2):
+        perm = rng.permutation(n)
+        hb = torch.zeros(cap, dtype=torch.int64); kb = torch.zeros(cap, dtype=torch.int64)
+        hb[:n] = torch.from_numpy(hashes[perm]); kb[:n] = torch.from_numpy(keys[perm])
+        hb[n:] = 12345; kb[n:] = 1                                      # garbage past count must be ignored
+        ex = DedupExchange(ctx, cap, 1, 4)
+        ex.run(hb.cuda(), kb.cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
+        k, keep = ex.result()
+        assert k.numpy().tolist() == kk.tolist()
+        assert keep.numpy().astype(bool).tolist() == want_keep.tolist()
+        assert len(survivors_digest(k, keep)) == 16
+    ex.run(hb.cuda(), kb.cuda(), torch.zeros(1, dtype=torch.int32, device="cuda"))
+    k, keep = ex.result()
+    assert k.numel() == 0
