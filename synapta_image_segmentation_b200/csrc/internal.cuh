@@ -53,6 +53,8 @@ struct synseg_ctx {
         static constexpr int MAXS = 4;
         cudaStream_t copy;                 // H2D stream
         uint8_t *pages[MAXS];              // staging slots for `slot_pages` pages each
+        uint8_t *raw[MAXS];                // grey pages whose host rows are not 16-byte multiples land here first (1-D copy at full
+        size_t raw_bytes;                  // PCIe speed) and are re-pitched on the device; a strided 2-D H2D copy runs at a third of it
         int32_t *n_labels[MAXS], *stats[MAXS];
         int32_t *n_regions[MAXS];          // n_regions[slot_pages] followed by flags[slot_pages]
         double *centroids[MAXS];

@@ -207,6 +207,8 @@ class RasterRegionDetector:
             else:
                 raster = self.regions_from_table(tables["regions"][i], int(tables["n_regions"][i]), pw, ph)
             pr = priors[i] if priors is not None else None
+            if pr is not None:
+                pr = [dict(p, detection_method=p.get("detection_method", "caption_based"), caption=p.get("caption")) for p in pr]
             if pr and prior_rule == "visual_regions":
                 regs = self.apply_priors_visual_regions(raster, pr)
             else:
@@ -217,9 +219,10 @@ class RasterRegionDetector:
             for r in regs:
                 r["page_num"] = int(page_nums[i]) if page_nums is not None else i
             kept = [r for r in regs if r["confidence"] >= self.cfg.keep_score]
-            if pr and prior_rule == "two_pass":
-                # _extract_images_from_page (:2763-2849): caption-based regions are pass 1; every validated raster region is a
-                # pass-2 candidate resolved against the segments kept so far (find_conflicting > 0.4, five-factor vote)
+            if pr is not None and prior_rule == "two_pass":
+                # _extract_images_from_page (:2763-2849): caption-based regions are pass 1 (possibly none); every validated raster
+                # region is a pass-2 candidate resolved against the segments kept so far (find_conflicting > 0.4, five-factor
+                # vote) -- also against candidates added before it, exactly like overlapping embedded images in the reference
                 caps = [r for r in kept if r.get("detection_method") == "caption_based"]
                 cands = [r for r in kept if r.get("detection_method") != "caption_based"]
                 kept = G.resolve_page_conflicts(caps, cands, drawings[i] if drawings is not None else None)
@@ -245,7 +248,9 @@ class RasterRegionDetector:
         'crop_px' (x, y, w, h) and, with_hash, 'phash'.
 
         priors: per page the regions a PDF object model produced (caption-based regions with 'bbox', 'caption', optional
-        'caption_bbox'; detection_method 'caption_based').  prior_rule "two_pass" (default) follows the live flow of the
+        'caption_bbox'; detection_method 'caption_based'); an EMPTY list for a page still runs pass 2 among the raster
+        candidates of that page, None (or priors=None) returns the validated regions as detected.
+        prior_rule "two_pass" (default) follows the live flow of the
         reference, `_extract_images_from_page` pass 2 (:2822-2847): validated raster regions are candidates resolved against
         the caption-based segments by `_find_conflicting_segment` / `_resolve_conflict` (`drawings`: per page the drawing
         rects for factor 4).  "visual_regions" applies `_detect_visual_regions`' duplicate / caption rule (:3122-3144) instead."""
@@ -260,7 +265,7 @@ class RasterRegionDetector:
         if priors is not None and len(priors) != b:
             raise ValueError(f"priors: expected one entry per page ({b}), got {len(priors)}")
         if priors is not None:
-            priors = [[dict(p, detection_method=p.get("detection_method", "caption_based"), caption=p.get("caption")) for p in (pp or [])] for pp in priors]
+            priors = [list(pp) if pp is not None else None for pp in priors]
         t = self.detect_tables(pages, pw, ph)
         n_h = t["n_labels"].cpu().numpy()
         tables = dict(n_labels=n_h, n_regions=t["n_regions"].cpu().numpy(), flags=t["flags"].cpu().numpy(),
@@ -289,7 +294,7 @@ class RasterRegionDetector:
         `{book}_p{page:03d}_{md5(png)[:8]}` (:3777-3783), page_no = page_num + 1, extraction_method =
         the region's detection method, confidence / notes from the validation score (:2915-2927)."""
         from PIL import Image
-        regions = self.detect_regions(page_rgb, page_num, priors=priors, prior_rule="two_pass", drawings=drawings)
+        regions = self.detect_regions(page_rgb, page_num, priors=priors if priors is not None else [], prior_rule="two_pass", drawings=drawings)
         segs = []
         for r in regions:
             x, y, w, h = r["crop_px"]

@@ -76,7 +76,8 @@ class RasterSegmentationPipeline:
         det = self.detector
         try:
             batch = torch.from_numpy(np.stack(pages)).to(det.ctx.device, non_blocking=True)
-            regions = det.detect_regions_batch(batch, page_nums=list(range(first_page, first_page + len(pages))))
+            # pass 2 of _extract_images_from_page runs on every page (no caption-based priors without a PDF object model)
+            regions = det.detect_regions_batch(batch, page_nums=list(range(first_page, first_page + len(pages))), priors=[[]] * len(pages))
         except Exception as e:                      # a failing batch is reported and skipped like a failing segment (:2749-2754)
             print(f"    ERROR detecting regions on pages {first_page + 1}..{first_page + len(pages)}: {e}")
             return

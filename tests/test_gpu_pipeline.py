@@ -540,7 +540,7 @@ def test_raster_segmentation_pipeline_writes_reference_artefacts(ctx, tmp_path):
     pages = [synth_page(i, 150, n_figures=2)[0] for i in range(5)]
     pl = RasterSegmentationPipeline("textbook_001", tmp_path, dpi=150, pdf_path="book.pdf", detector=det, batch=2)
     segs = pl.process(iter(pages))
-    expected = det.detect_regions_batch(torch.from_numpy(np.stack(pages)).cuda(), page_nums=list(range(5)))
+    expected = det.detect_regions_batch(torch.from_numpy(np.stack(pages)).cuda(), page_nums=list(range(5)), priors=[[]] * 5)
     assert len(segs) == sum(len(r) for r in expected) >= 5
     doc = load_segments_json(tmp_path / "textbook_001_visual_segments.json")
     assert doc["book_id"] == "textbook_001" and doc["pdf_path"] == "book.pdf" and doc["total_segments"] == len(segs)

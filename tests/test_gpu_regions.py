@@ -349,9 +349,11 @@ def test_two_pass_priors_on_the_gpu(ctx):
             if r["detection_method"] == "caption_based":
                 assert r["confidence"] == 0.9 and r["caption"] == prior["caption"] and "variance" in r and "crop_px" in r
         seen.add(("caption_based" in [r["detection_method"] for r in out], any("conflict_resolution" in r for r in out)))
-    assert (True, False) in seen and any(replaced for _, replaced in seen)      # a prior that stays, and one a raster region replaced
+    assert any(stays for stays, _ in seen) and any(not stays for stays, _ in seen)      # a prior that stays, and one a raster region replaced
     far = det.detect_regions(page, 0, priors=[priors["far away"]])
-    assert len(far) == len(base) + 1
+    alone = det.detect_regions(page, 0, priors=[])                      # pass 2 among the raster candidates only
+    assert len(far) == len(alone) + 1 and len(alone) <= len(base)
+    assert [r["bbox"] for r in alone] == [r["bbox"] for r in sorted(G.resolve_page_conflicts([], [dict(c) for c in cands]), key=lambda r: (r["bbox"].y0, r["bbox"].x0))]
     # the other rule (dead code in the reference, kept selectable): _detect_visual_regions' duplicate test
     out3 = det.detect_regions(page, 0, priors=[priors["captioned, larger"]], prior_rule="visual_regions")
     assert [r["detection_method"] for r in out3].count("caption_based") == 1
