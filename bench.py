@@ -327,12 +327,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    json_fd = None
     if world > 1:
-        # NCCL prints its INFO lines (communicator, nranks, transport) to STDOUT by default; stdout must carry the one JSON
-        # line only, so they are routed to stderr -- visible to whoever runs the bench, never silenced
+        # NCCL writes its version banner and INFO lines (communicator, nranks, transport) to STDOUT; stdout must carry the one
+        # JSON line only.  They are not silenced: file descriptor 1 is pointed at stderr for the whole run (the JSON line goes
+        # to the saved descriptor at the end), and NCCL_DEBUG defaults to INFO / INIT so the ranks of every communicator are on record.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = Context(local)
@@ -608,7 +612,11 @@ def main():
                          "fixed_corpus": corpus}
         line["crops"] = crops
         line["dense_pages"] = dense
-        print(json.dumps(line))
+        if json_fd is None:
+            print(json.dumps(line))
+        else:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         ctx.lib.synseg_comm_destroy(ctx._h)

@@ -20,6 +20,9 @@
 //   pixel" flag; no host round trip, no iteration count that depends on the image.
 //
 // Roofline: HBM-bound, 1.25 algorithmic bytes per pixel (1 read + two bit planes written) for stage 1.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "internal.cuh"
 #include "pixel.cuh"
 
@@ -294,7 +297,341 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused front end: RGB pages -> cv2 grey plane + Canny classes in ONE pass over the RGB bytes, fed by TMA.
+//
+// The RGB rows of a strip are fetched by the tensor memory accelerator: one elected lane issues
+// cp.async.bulk.tensor.2d (SASS UTMALDG) per strip row and the bytes land in a per-warp shared-memory ring while the
+// warp works on the rows before; an mbarrier per ring stage signals arrival (complete_tx).  A tightly packed RGB page has
+// a row pitch of 3 W bytes (7650 at 300 DPI), not a multiple of 16, so the pages cannot be described as a 2-D image
+// tensor; the tensor map instead views the whole batch as rows of 16 bytes ({16, total / 16} u8, box {16, 98}): a box is
+// the 16-byte-aligned superset of the 1536 bytes a strip row needs, and whatever lies beyond the end of the batch is
+// zero-filled by the hardware (no guard code for the last rows).  Each lane then takes its 64-byte window with four
+// LDS.128, realigns it in registers (the misalignment is uniform per row), converts its 16 pixels with cv2's 15-bit
+// fixed-point formula (pixel.cuh) and -- lanes 1..30, rows of the own band -- stores them into the grey plane the
+// threshold kernel reads afterwards.  From there on the row goes through exactly the arithmetic of
+// canny_classes_kernel above.  Compared with rgb2gray + canny_classes the grey plane is written once and read once
+// instead of twice, and the RGB read overlaps the issue-bound stencil instead of being a kernel of its own.
+#ifndef SYNSEG_CR_DEPTH
+#define SYNSEG_CR_DEPTH 3
+#endif
+constexpr int CR_DEPTH = SYNSEG_CR_DEPTH;          // RGB rows in flight per warp
+constexpr int CR_UNITS = 98;                       // 16-byte units per box: ceil((15 + 1536) / 16) = 97, +1 so a lane window never leaves the box
+constexpr int CR_BOX = CR_UNITS * 16;              // 1568 bytes per TMA box
+constexpr int CR_STAGE = 1664;                     // ring stage: the box rounded up to the 128-byte alignment a TMA destination needs
+constexpr int CR_MINBLOCKS = CR_DEPTH <= 3 ? 16 : 14;
+
+struct CrParams {
+    CnParams c;
+    Plane gray;                                    // grey plane written (16-byte aligned pitch >= round_up(width, 16))
+    int64_t src_bs, src_rs;                        // RGB batch / row stride in bytes
+    int64_t total_bytes;                           // bytes of the whole batch (the tensor map covers floor(total / 16) units)
+    const uint8_t *src;                            // for the <= 15 tail bytes the tensor map cannot cover
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_units(void *dst, const CUtensorMap *map, int unit, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(0), "r"(unit), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 12 RGB bytes = 4 pixels -> 4 cv2 grey bytes (same arithmetic as gray.cu:gray4)
+__device__ __forceinline__ uint32_t cv_gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const uint32_t y0 = gray1<SYNSEG_GRAY_CV>(w0);
+    const uint32_t y1 = gray1<SYNSEG_GRAY_CV>(__funnelshift_r(w0, w1, 24));
+    const uint32_t y2 = gray1<SYNSEG_GRAY_CV>(__funnelshift_r(w1, w2, 16));
+    const uint32_t y3 = gray1<SYNSEG_GRAY_CV>(w2 >> 8);
+    return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+}
+
+struct CrSmem {
+    MagRing ring;
+    NmsStage stage;
+    alignas(128) uint8_t rows[CR_DEPTH][CR_STAGE];
+    alignas(8) uint64_t bar[CR_DEPTH];
+};
+
+__global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __grid_constant__ CUtensorMap tmap, CrParams q)
+{
+    __shared__ CrSmem sm;
+    const CnParams &p = q.c;
+    const int lane = threadIdx.x;
+    int64_t task = blockIdx.x;
+    const int strip = (int)(task % p.strips); task /= p.strips;
+    const int band = (int)(task % p.bands);
+    const int img = (int)(task / p.bands);
+    MagRing &R = sm.ring;
+    NmsStage &S = sm.stage;
+
+    const int W = p.width, H = p.height;
+    const int hi = p.hi;
+    const int x = strip * CN_OUT_W - 16 + 16 * lane;  // first of this lane's 16 columns
+    const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
+    const bool out_lane = lane >= 1 && lane <= 30 && x < W;
+    const bool writer = out_lane && (lane & 1) && lane <= 29;
+
+    CnState st;
+    st.zmask = 0;
+    const int lo = p.lo < 0 ? 0 : (p.lo > 4095 ? 4095 : p.lo);
+    st.kpair = (uint32_t)(0x7FFF - lo) * 0x00010001u;
+    st.cv16 = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) st.cv16 |= (x + c >= 0 && x + c < W) ? (1u << c) : 0u;
+
+    // the strip's bytes of a row start at column cb; this lane's (clamped) 16-pixel group starts 3 (xl - cb) bytes further
+    const int cb = max(strip * CN_OUT_W - 16, 0);
+    const int xl = clamp16_x(x, W);
+    const EdgeFix efix = make_edge_fix(x, W);
+    const int lane_off = 3 * (xl - cb);               // multiple of 48
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < CR_DEPTH; ++d) mbar_init(&sm.bar[d], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // byte offset (from the start of the batch) of the strip's first byte in the row being fetched; rows are clamped into the image
+    int y_pf = y0 - 2;
+    int64_t off_pf = (int64_t)img * q.src_bs + (int64_t)min(max(y_pf, 0), H - 1) * q.src_rs + 3 * (int64_t)cb;
+    const int64_t tail_start = q.total_bytes & ~(int64_t)15;      // bytes from here on are not covered by the tensor map
+    auto issue = [&](int slot) {
+        // rows beyond y1 + 1 are never consumed: nothing may be in flight into this CTA's shared memory when it exits
+        if (lane == 0 && y_pf <= y1 + 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
+            mbar_expect_tx(&sm.bar[slot], CR_BOX);
+            tma_load_units(sm.rows[slot], &tmap, (int)(off_pf >> 4), &sm.bar[slot]);
+        }
+        ++y_pf;
+        if (y_pf >= 1 && y_pf <= H - 1) off_pf += q.src_rs;
+    };
+    int64_t off_cur = off_pf;                          // offset of the row consumed next (same recurrence, CR_DEPTH rows behind)
+    int y_cur = y_pf;
+#pragma unroll
+    for (int d = 0; d < CR_DEPTH; ++d) issue(d);
+    uint32_t *kp = p.kept.p + img * p.kept.bs + (int64_t)y0 * p.kept.wpr + (max(x, 0) >> 5);
+    uint32_t *sp = p.strong.p + img * p.strong.bs + (int64_t)y0 * p.strong.wpr + (max(x, 0) >> 5);
+    const int k_wpr = p.kept.wpr, s_wpr = p.strong.wpr;
+    uint8_t *gp = q.gray.p + img * q.gray.bs + (int64_t)y0 * q.gray.rs + max(x, 0);     // grey row y0 of this lane's group
+    const int64_t g_rs = q.gray.rs;
+
+    HRow A, B, C;
+    A.uni = false; B.uni = false; A.rep = 0; B.rep = 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { A.s[i] = 0; A.d[i] = 0; B.s[i] = 0; B.d[i] = 0; }
+    int slot = 0;
+    uint32_t phases = 0;                               // bit d: parity the next wait on stage d expects
+    uint32_t cand_cur = 0;
+#pragma unroll 1
+    for (int y = y0 - 4; y < y1; ++y) {
+        // ---- grey row y + 2 from the RGB stage ------------------------------------------------------------------
+        mbar_wait(&sm.bar[slot], (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        const int a = (int)(off_cur & 15);
+        const int64_t row_end_need = off_cur + 3 * (int64_t)(CN_OUT_W + 32);
+        if (row_end_need > tail_start && tail_start < q.total_bytes) {
+            // last rows of the batch: the final partial 16-byte unit is outside the tensor map (zero-filled); patch it in
+            if (lane == 0) {
+                const int64_t first = (off_cur & ~(int64_t)15);
+                for (int64_t b = tail_start; b < q.total_bytes; ++b) {
+                    const int64_t o = b - first;
+                    if (o >= 0 && o < CR_BOX) sm.rows[slot][o] = q.src[b];
+                }
+            }
+            __syncwarp();
+        }
+        uint4 vcur;
+        {
+            const uint4 *wp = (const uint4 *)(sm.rows[slot] + lane_off);
+            const uint4 q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3];
+            const uint32_t w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+            const int ws = a >> 2, bsh = (a & 3) * 8;
+            uint32_t v[12];
+            switch (ws) {                                  // uniform over the warp: v[] stays in registers
+            case 0:
+#pragma unroll
+                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], bsh);
+                break;
+            case 1:
+#pragma unroll
+                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 1], w[i + 2], bsh);
+                break;
+            case 2:
+#pragma unroll
+                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 2], w[i + 3], bsh);
+                break;
+            default:
+#pragma unroll
+                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 3], i + 4 < 16 ? w[i + 4] : 0u, bsh);
+                break;
+            }
+            uint32_t diff = 0;
+#pragma unroll
+            for (int i = 1; i < 12; ++i) diff |= v[i] ^ v[0];
+            if ((diff | (v[0] ^ __byte_perm(v[0], 0, 0x0000))) == 0u) {
+                vcur = make_uint4(v[0], v[0], v[0], v[0]);             // 16 equal grey pixels (R = G = B = c): cv2 grey is c
+            } else {
+                vcur.x = cv_gray4(v[0], v[1], v[2]); vcur.y = cv_gray4(v[3], v[4], v[5]);
+                vcur.z = cv_gray4(v[6], v[7], v[8]); vcur.w = cv_gray4(v[9], v[10], v[11]);
+            }
+        }
+        __syncwarp();                                      // every lane has read its window: the stage can be refilled
+        issue(slot);
+        slot = (slot + 1 == CR_DEPTH) ? 0 : slot + 1;
+        ++y_cur;
+        if (y_cur >= 1 && y_cur <= H - 1) off_cur += q.src_rs;
+        if (y + 2 >= y0 && y + 2 < y1 && out_lane) *(uint4 *)(gp + (int64_t)(y + 2 - y0) * g_rs) = vcur;      // grey plane, own rows only
+        vcur = apply_edge_fix(vcur, efix);
+        const uint32_t wl = __shfl_up_sync(FULL, vcur.w, 1), wr = __shfl_down_sync(FULL, vcur.x, 1);
+        if (y < y0 - 2) {                                  // priming: rows y0-2, y0-1 only become partials
+            make_hrow(C, vcur, wl, wr);
+            const HRow t = A; A = B; B = C; C = t;
+            continue;
+        }
+        {
+            const uint32_t rep = __byte_perm(vcur.x, 0, 0x0000);
+            const bool uni = (((vcur.x ^ rep) | (vcur.y ^ rep) | (vcur.z ^ rep)) | ((vcur.w ^ rep) | (wl ^ rep) | (wr ^ rep))) == 0u;
+            if (__all_sync(FULL, uni & A.uni & B.uni & (rep == B.rep) & (A.rep == B.rep) & (cand_cur == 0u))) {
+                st.zmask |= 1u << ((y + 4) % 3);
+                if (y >= y0) {
+                    if (writer) { *kp = 0u; *sp = 0u; }
+                    kp += k_wpr; sp += s_wpr;
+                }
+                continue;
+            }
+        }
+        make_hrow(C, vcur, wl, wr);
+        const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, (y + 1) & 1, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
+        __syncwarp();
+        if (y >= y0) {
+            uint32_t kept16 = 0, strong16 = 0;
+            const uint32_t mycand = out_lane ? cand_cur : 0u;
+            if (__any_sync(FULL, mycand != 0u)) {
+                const int cnt = __popc(mycand);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
+                const int total = __shfl_sync(FULL, incl, 31);
+                int pos = incl - cnt;
+                for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1));
+                S.kept[lane] = 0u; S.strong[lane] = 0u;
+                __syncwarp();
+                for (int qq = lane; qq < total; qq += 32) { const int id = S.list[qq]; nms_one(R, st, S, y, id >> 4, id & 15, hi); }
+                __syncwarp();
+                kept16 = S.kept[lane]; strong16 = S.strong[lane];
+            }
+            const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
+            if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }
+            kp += k_wpr; sp += s_wpr;
+        }
+        cand_cur = cand_next;
+        __syncwarp();
+        const HRow t = A; A = B; B = C; C = t;
+    }
+}
+
 }  // namespace
+
+// ---- host side of the fused front end ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// Can the fused RGB front end take these pages?  (16-byte aligned batch base, flat size below the coordinate range of a tensor map.)
+bool canny_rgb_supported(const synseg_img *rgb, const synseg_img *gray)
+{
+    if (getenv("SYNSEG_NO_TMA")) return false;
+    if (((uintptr_t)rgb->data & 15) != 0) return false;
+    const int64_t total = (int64_t)(rgb->batch - 1) * rgb->batch_stride + (int64_t)(rgb->height - 1) * rgb->row_stride + 3 * (int64_t)rgb->width;
+    if (total < 16 * CR_UNITS || (total >> 4) >= 0x7fffffffLL) return false;
+    if (!plane_aligned(gray, 16) || gray->row_stride < (int64_t)align_up((size_t)rgb->width, 16)) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+// RGB pages -> cv2 grey plane + Canny classes (kept / strong bit planes), one TMA-fed kernel.
+int launch_canny_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, BitPlane kept, BitPlane strong, int lo, int hi, cudaStream_t st)
+{
+    CrParams q;
+    CnParams &p = q.c;
+    p.src = plane_of(gray);
+    p.kept = kept; p.strong = strong;
+    p.width = rgb->width; p.height = rgb->height; p.lo = lo; p.hi = hi;
+    p.strips = cdiv(rgb->width, CN_OUT_W);
+    const int64_t rows_total = (int64_t)rgb->height * rgb->batch * p.strips;
+    int band_h = (int)(rows_total / (64 * (int64_t)ctx->sm_count));
+    band_h = band_h < 16 ? 16 : (band_h > 32 ? 32 : band_h);
+    if (ctx->tune_canny_band > 0) band_h = ctx->tune_canny_band;
+    if (band_h > rgb->height) band_h = rgb->height;
+    p.band_h = band_h;
+    p.bands = cdiv(rgb->height, band_h);
+    p.tasks = (int64_t)rgb->batch * p.bands * p.strips;
+    q.gray = plane_of(gray);
+    q.src_bs = rgb->batch_stride; q.src_rs = rgb->row_stride;
+    q.total_bytes = (int64_t)(rgb->batch - 1) * rgb->batch_stride + (int64_t)(rgb->height - 1) * rgb->row_stride + 3 * (int64_t)rgb->width;
+    q.src = (const uint8_t *)rgb->data;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {16, (cuuint64_t)(q.total_bytes >> 4)};
+    const cuuint64_t gstride[1] = {16};
+    const cuuint32_t box[2] = {16, (cuuint32_t)CR_UNITS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, rgb->data, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { synseg_set_error("canny_rgb: cuTensorMapEncodeTiled failed (%d)", (int)r); return SYNSEG_E_CUDA; }
+    if (p.tasks > 0x7fffffffLL) { synseg_set_error("canny_rgb: batch too large"); return SYNSEG_E_INVALID; }
+    canny_rgb_kernel<<<(unsigned)p.tasks, 32, 0, st>>>(tmap, q);
+    SS_LAUNCH_CHECK(ctx, "canny_rgb", st);
+    return SYNSEG_OK;
+}
+
+// The fused front end of the page pipeline: RGB -> grey plane + Canny classes (TMA-fed), adaptive threshold of the grey plane
+// into `mask`, hysteresis OR-ed into `mask`.  Scratch (two bit planes + the hysteresis arrays) comes from the arena top.
+int run_front_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, BitPlane mask, int block_size, int C, int lo, int hi, cudaStream_t st)
+{
+    const int W = rgb->width, H = rgb->height, B = rgb->batch;
+    const int wpr = bit_wpr(W);
+    const size_t plane_bytes = (size_t)wpr * H * B * 4;
+    void *p;
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane kept{(uint32_t *)p, wpr, (int64_t)wpr * H, nullptr};
+    SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
+    BitPlane strong{(uint32_t *)p, wpr, (int64_t)wpr * H, nullptr};
+    SS_TRY(launch_canny_rgb(ctx, rgb, gray, kept, strong, lo, hi, st));
+    SS_TRY(launch_adaptive_mean(ctx, gray, nullptr, mask, block_size, C, 1, st));
+    return run_hysteresis(ctx, kept, strong, W, H, B, nullptr, mask, true, st);
+}
 
 int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept, BitPlane strong, int lo, int hi, cudaStream_t st)
 {

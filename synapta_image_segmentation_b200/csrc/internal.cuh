@@ -205,6 +205,11 @@ int launch_canny_classes(synseg_ctx *ctx, const synseg_img *gray, BitPlane kept,
 int run_canny(synseg_ctx *ctx, const synseg_img *gray, const synseg_img *edges_u8, BitPlane edges_bits, bool or_bits,
               int lo, int hi, cudaStream_t st);
 
+// Fused RGB front end (canny.cu): TMA-fed RGB -> grey + Canny classes, then threshold + hysteresis into `mask`.
+bool canny_rgb_supported(const synseg_img *rgb, const synseg_img *gray);
+int launch_canny_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, BitPlane kept, BitPlane strong, int lo, int hi, cudaStream_t st);
+int run_front_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *gray, BitPlane mask, int block_size, int C, int lo, int hi, cudaStream_t st);
+
 // bit packing
 int launch_pack_bits(synseg_ctx *ctx, const synseg_img *src, BitPlane dst, cudaStream_t st);
 int launch_unpack_bits(synseg_ctx *ctx, BitPlane src, const synseg_img *dst, cudaStream_t st);

@@ -74,10 +74,15 @@ static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_det
     SS_TRY(arena_alloc(ctx, plane_bytes, &p, st));
     BitPlane other{(uint32_t *)p, wpr, (int64_t)wpr * H};
 
-    if (!grey_in) SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
-    SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
     const size_t mark = arena_mark(ctx);
-    SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
+    if (!grey_in && canny_rgb_supported(rgb, &gray)) {
+        // one TMA-fed pass over the RGB bytes writes the grey plane and the Canny classes; the threshold reads the grey plane once
+        SS_TRY(run_front_rgb(ctx, rgb, &gray, cur, prm->block_size, prm->C, prm->canny_lo, prm->canny_hi, st));
+    } else {
+        if (!grey_in) SS_TRY(launch_rgb2gray(ctx, rgb, &gray, SYNSEG_GRAY_CV, st));
+        SS_TRY(launch_adaptive_mean(ctx, &gray, nullptr, cur, prm->block_size, prm->C, 1, st));
+        SS_TRY(run_canny(ctx, &gray, nullptr, cur, /*or_bits=*/true, prm->canny_lo, prm->canny_hi, st));
+    }
     arena_release(ctx, mark);
     // dilate(k) then close(k) = dilate(k), dilate(k), erode(k) = dilate(2k-1, anchor 2*(k/2)), erode(k)
     const int k = prm->k;
