@@ -47,6 +47,8 @@ ALG_BYTES_PER_PX = {
     "ccl_init": 0.125, "ccl_merge": 0.125, "ccl_compress": 0.125,   # bit plane read; parent array touched at run starts only
     "hyst_flag": 0.25, "hyst_final": 0.375,                          # kept (+ strong) read; edges OR-ed into the mask plane
     "bitmorph_h": 0.25, "bitmorph_v": 0.25,                          # bit plane read + written
+    "bit_dilate_erode": 0.25,                                        # the four passes fused: bit plane read + written once
+    "canny_rgb": 4.25,                                               # RGB read (3) + grey plane written (1) + kept / strong bit planes written
     "ccl_scan": 0.0, "ccl_assign": 0.0, "stats_init": 0.0, "ccl_final": 0.125, "stats_finalize": 0.0,
 }
 

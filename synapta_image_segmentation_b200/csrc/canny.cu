@@ -313,13 +313,19 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 // canny_classes_kernel above.  Compared with rgb2gray + canny_classes the grey plane is written once and read once
 // instead of twice, and the RGB read overlaps the issue-bound stencil instead of being a kernel of its own.
 #ifndef SYNSEG_CR_DEPTH
-#define SYNSEG_CR_DEPTH 3
+#define SYNSEG_CR_DEPTH 2
 #endif
 constexpr int CR_DEPTH = SYNSEG_CR_DEPTH;          // RGB rows in flight per warp
 constexpr int CR_UNITS = 98;                       // 16-byte units per box: ceil((15 + 1536) / 16) = 97, +1 so a lane window never leaves the box
 constexpr int CR_BOX = CR_UNITS * 16;              // 1568 bytes per TMA box
 constexpr int CR_STAGE = 1664;                     // ring stage: the box rounded up to the 128-byte alignment a TMA destination needs
-constexpr int CR_MINBLOCKS = CR_DEPTH <= 3 ? 16 : 14;
+// measured on B200 (profiles/r2_front_end_experiments.txt): 2 stages are enough -- the kernel is bound by instruction issue, not by
+// the latency of the loads; deeper rings only cost resident warps (3: +1 %, 4: +3 %, 6: +19 %), an L2 prefetch 8 rows ahead +26 %
+constexpr int CR_MINBLOCKS = CR_DEPTH <= 3 ? 16 : (CR_DEPTH == 4 ? 14 : (CR_DEPTH == 5 ? 13 : 12));
+#ifndef SYNSEG_CR_PREFETCH
+#define SYNSEG_CR_PREFETCH 0
+#endif
+constexpr int CR_PREFETCH = SYNSEG_CR_PREFETCH;    // rows ahead of the TMA loads whose boxes are prefetched into L2 (0 = off)
 
 struct CrParams {
     CnParams c;
@@ -347,6 +353,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_units(const CUtensorMap *map, int unit)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(0), "r"(unit) : "memory");
 }
 __device__ __forceinline__ void tma_load_units(void *dst, const CUtensorMap *map, int unit, uint64_t *bar)
 {
@@ -414,6 +424,15 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     int y_pf = y0 - 2;
     int64_t off_pf = (int64_t)img * q.src_bs + (int64_t)min(max(y_pf, 0), H - 1) * q.src_rs + 3 * (int64_t)cb;
     const int64_t tail_start = q.total_bytes & ~(int64_t)15;      // bytes from here on are not covered by the tensor map
+    int y_l2 = y_pf;
+    int64_t off_l2 = off_pf;
+    if (CR_PREFETCH > 0) {
+        for (int d = 0; d < CR_DEPTH + CR_PREFETCH; ++d) {
+            if (lane == 0 && d >= CR_DEPTH && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 4));
+            ++y_l2;
+            if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
+        }
+    }
     auto issue = [&](int slot) {
         // rows beyond y1 + 1 are never consumed: nothing may be in flight into this CTA's shared memory when it exits
         if (lane == 0 && y_pf <= y1 + 1) {
@@ -423,6 +442,11 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         }
         ++y_pf;
         if (y_pf >= 1 && y_pf <= H - 1) off_pf += q.src_rs;
+        if (CR_PREFETCH > 0) {                             // the row CR_PREFETCH rows further on starts its way from HBM to L2 now
+            if (lane == 0 && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 4));
+            ++y_l2;
+            if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
+        }
     };
     int64_t off_cur = off_pf;                          // offset of the row consumed next (same recurrence, CR_DEPTH rows behind)
     int y_cur = y_pf;
@@ -431,8 +455,11 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     uint32_t *kp = p.kept.p + img * p.kept.bs + (int64_t)y0 * p.kept.wpr + (max(x, 0) >> 5);
     uint32_t *sp = p.strong.p + img * p.strong.bs + (int64_t)y0 * p.strong.wpr + (max(x, 0) >> 5);
     const int k_wpr = p.kept.wpr, s_wpr = p.strong.wpr;
-    uint8_t *gp = q.gray.p + img * q.gray.bs + (int64_t)y0 * q.gray.rs + max(x, 0);     // grey row y0 of this lane's group
+    uint8_t *gp = q.gray.p + img * q.gray.bs + (int64_t)y0 * q.gray.rs + max(x, 0);     // grey row y0 of this lane's group (advances with the own rows)
     const int64_t g_rs = q.gray.rs;
+    // the last 16-byte unit of the batch may be partial and then lies outside the tensor map: only the band holding the last rows checks for it
+    const bool tail_band = (q.total_bytes & 15) != 0 &&
+                           (int64_t)img * q.src_bs + (int64_t)min(y1 + 1, H - 1) * q.src_rs + 3 * (int64_t)(cb + CN_OUT_W + 32) > (q.total_bytes & ~(int64_t)15);
 
     HRow A, B, C;
     A.uni = false; B.uni = false; A.rep = 0; B.rep = 1;
@@ -447,8 +474,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         mbar_wait(&sm.bar[slot], (phases >> slot) & 1u);
         phases ^= 1u << slot;
         const int a = (int)(off_cur & 15);
-        const int64_t row_end_need = off_cur + 3 * (int64_t)(CN_OUT_W + 32);
-        if (row_end_need > tail_start && tail_start < q.total_bytes) {
+        if (tail_band && off_cur + 3 * (int64_t)(CN_OUT_W + 32) > tail_start) {
             // last rows of the batch: the final partial 16-byte unit is outside the tensor map (zero-filled); patch it in
             if (lane == 0) {
                 const int64_t first = (off_cur & ~(int64_t)15);
@@ -499,7 +525,10 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         slot = (slot + 1 == CR_DEPTH) ? 0 : slot + 1;
         ++y_cur;
         if (y_cur >= 1 && y_cur <= H - 1) off_cur += q.src_rs;
-        if (y + 2 >= y0 && y + 2 < y1 && out_lane) *(uint4 *)(gp + (int64_t)(y + 2 - y0) * g_rs) = vcur;      // grey plane, own rows only
+        if (y + 2 >= y0 && y + 2 < y1) {                   // grey plane, own rows only
+            if (out_lane) *(uint4 *)gp = vcur;
+            gp += g_rs;
+        }
         vcur = apply_edge_fix(vcur, efix);
         const uint32_t wl = __shfl_up_sync(FULL, vcur.w, 1), wr = __shfl_down_sync(FULL, vcur.x, 1);
         if (y < y0 - 2) {                                  // priming: rows y0-2, y0-1 only become partials
@@ -590,9 +619,10 @@ int launch_canny_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *g
     p.kept = kept; p.strong = strong;
     p.width = rgb->width; p.height = rgb->height; p.lo = lo; p.hi = hi;
     p.strips = cdiv(rgb->width, CN_OUT_W);
+    // bands of up to 48 rows: a band converts 4 halo rows besides its own (32-row bands: 0.817 ms, 48: 0.807, 64: 0.842 per 50 pages)
     const int64_t rows_total = (int64_t)rgb->height * rgb->batch * p.strips;
-    int band_h = (int)(rows_total / (64 * (int64_t)ctx->sm_count));
-    band_h = band_h < 16 ? 16 : (band_h > 32 ? 32 : band_h);
+    int band_h = (int)(rows_total / (48 * (int64_t)ctx->sm_count));
+    band_h = band_h < 16 ? 16 : (band_h > 48 ? 48 : band_h);
     if (ctx->tune_canny_band > 0) band_h = ctx->tune_canny_band;
     if (band_h > rgb->height) band_h = rgb->height;
     p.band_h = band_h;

@@ -222,6 +222,9 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
                       int anchor, cudaStream_t st);
 int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, int height, int batch, int op, int k,
                       int anchor, cudaStream_t st);
+// dilate(K1 x K1, a1) then erode(k2 x k2, a2) in one shared-memory kernel (morph_fused.cu); *done = false: not applicable, nothing launched
+int launch_bit_dilate_erode(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, int height, int batch, int K1, int a1, int k2, int a2,
+                            bool *done, cudaStream_t st);
 // Generic 8-bit 1-D passes.
 int launch_morph_u8_h(synseg_ctx *ctx, const synseg_img *src, const synseg_img *dst, int op, int k, int anchor,
                       cudaStream_t st);

@@ -86,8 +86,13 @@ static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_det
     arena_release(ctx, mark);
     // dilate(k) then close(k) = dilate(k), dilate(k), erode(k) = dilate(2k-1, anchor 2*(k/2)), erode(k)
     const int k = prm->k;
-    SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_DILATE, k, k, k / 2, k / 2, 2, st));
-    SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_ERODE, k, k, k / 2, k / 2, 1, st));
+    bool fused = false;                 // all four 1-D passes in one shared-memory kernel when the geometry fits (morph_fused.cu)
+    SS_TRY(launch_bit_dilate_erode(ctx, cur, other, W, H, B, 2 * (k - 1) + 1, 2 * (k / 2), k, k / 2, &fused, st));
+    if (fused) { const BitPlane t = cur; cur = other; other = t; }
+    else {
+        SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_DILATE, k, k, k / 2, k / 2, 2, st));
+        SS_TRY(run_bitmorph(ctx, cur, other, W, H, B, SYNSEG_MORPH_ERODE, k, k, k / 2, k / 2, 1, st));
+    }
     CclMask m; m.u8 = nullptr; m.bits = cur; m.width = W; m.height = H; m.batch = B;
     return run_ccl_stats(ctx, m, nullptr, n_labels, stats, centroids, prm->max_labels, st);
 }

@@ -420,3 +420,47 @@ def test_dedup_exchange_equals_sorted_all_pairs(ctx):
     ex.run(hb.cuda(), kb.cuda(), torch.zeros(1, dtype=torch.int32, device="cuda"))
     k, keep = ex.result()
     assert k.numel() == 0
+
+
+def test_fused_morphology_and_separate_front_end_variants(ctx, monkeypatch):
+    """The opt-in one-kernel dilate + close (SYNSEG_FUSED_MORPH=1, csrc/morph_fused.cu) and the non-TMA front end (SYNSEG_NO_TMA=1:
+    rgb2gray + canny_classes) give the tables of the default path (TMA-fed fused front end, four morphology passes) on odd sizes,
+    several element sizes (even k included) and a size whose last 16-byte unit is partial."""
+    from oracle import cv2_chain
+    import cv2
+    rng = np.random.default_rng(12)
+    for (h, w, bs, k) in [(333, 517, 15, 7), (200, 1100, 25, 12), (792, 612, 13, 11), (97, 131, 15, 5), (1650, 1275, 25, 21)]:
+        page = synth_page(int(rng.integers(100)), 150 if h == 1650 else 72, n_figures=2)[0][:h, :w]
+        if page.shape[0] < h or page.shape[1] < w:
+            page = np.ascontiguousarray(np.pad(page, ((0, h - page.shape[0]), (0, w - page.shape[1]), (0, 0)), constant_values=255))
+        page = np.ascontiguousarray(page)
+        t = torch.from_numpy(np.stack([page, page[::-1].copy(), page[:, ::-1].copy()])).cuda()
+        results = []
+        for env in ({}, {"SYNSEG_FUSED_MORPH": "1"}, {"SYNSEG_NO_TMA": "1"}, {"SYNSEG_FUSED_MORPH": "1", "SYNSEG_NO_TMA": "1"}):
+            for kk in ("SYNSEG_FUSED_MORPH", "SYNSEG_NO_TMA"):
+                monkeypatch.delenv(kk, raising=False)
+            for kk, vv in env.items():
+                monkeypatch.setenv(kk, vv)
+            l0 = ctx.launches
+            gray = torch.empty((3, h, (w + 15) // 16 * 16), dtype=torch.uint8, device="cuda")[:, :, :w]
+            n, st, ce = ctx.detect_pages(t, bs, 10, k, max_labels=2048, gray_out=gray)
+            torch.cuda.synchronize()
+            results.append((n.cpu(), st.cpu(), ce.cpu(), gray.cpu(), ctx.launches - l0))
+        for kk in ("SYNSEG_FUSED_MORPH", "SYNSEG_NO_TMA"):
+            monkeypatch.delenv(kk, raising=False)
+        n0, st0, ce0, g0, launches0 = results[0]
+        assert np.array_equal(g0[0].numpy(), cv2.cvtColor(page, cv2.COLOR_RGB2GRAY))      # the TMA kernel writes cv2's grey plane
+        for n, st, ce, g, launches in results[1:]:
+            assert torch.equal(n, n0) and torch.equal(g, g0)
+            for j in range(3):
+                m = int(n0[j])
+                assert torch.equal(st[j, :m], st0[j, :m]) and torch.equal(ce[j, :m], ce0[j, :m])
+        assert results[1][4] == launches0 - 3 and results[2][4] == launches0 + 1      # 4 morphology passes -> 1 kernel; 1 front kernel -> 2
+        # and the cv2 chain itself (dilate k, close k)
+        g = cv2.cvtColor(page, cv2.COLOR_RGB2GRAY)
+        thr = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, bs, 10)
+        ink = cv2.bitwise_or(thr, cv2.Canny(g, 50, 150))
+        se = cv2.getStructuringElement(cv2.MORPH_RECT, (k, k))
+        closed = cv2.morphologyEx(cv2.dilate(ink, se), cv2.MORPH_CLOSE, se)
+        nn, _, ss, cc = cv2.connectedComponentsWithStats(closed, 8, cv2.CV_32S)
+        assert int(n0[0]) == nn and np.array_equal(st0[0, :nn].numpy(), ss) and np.array_equal(ce0[0, :nn].numpy(), cc)
