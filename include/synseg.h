@@ -72,6 +72,11 @@ size_t synseg_scratch_bytes(int32_t width, int32_t height, int32_t batch);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t synseg_launch_count(const synseg_ctx *ctx);
 
+/* Memory-safety build (compile with -DSYNSEG_GUARD, tools/guard_run.sh): every scratch allocation sits between canary zones that are
+ * compared when the public call returns, and the kernels' index assertions are real device asserts.  Returns the number of
+ * damaged zones seen so far; *zones_checked = zones compared; *guard_build = 1 in such a build (a normal build returns 0 / 0 / 0). */
+int64_t synseg_guard_violations(const synseg_ctx *ctx, int64_t *zones_checked, int32_t *guard_build);
+
 /* Per-kernel device timing for bench.py: begin records a start event on `stream`; every kernel the
  * library launches afterwards is followed by an event; end returns (kernel name, milliseconds) pairs in
  * launch order (value = number of launches, <0 on error). */

@@ -59,6 +59,7 @@ SIGNATURES = {
     "synseg_reserve": (C.c_int, [C.c_void_p, C.c_size_t]),
     "synseg_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "synseg_launch_count": (C.c_int64, [C.c_void_p]),
+    "synseg_guard_violations": (C.c_int64, [C.c_void_p, _P(C.c_int64), _P(C.c_int32)]),
     "synseg_profile_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "synseg_profile_end": (C.c_int, [C.c_void_p, _P(C.c_char_p), _P(C.c_float), C.c_int]),
     "synseg_select_rois": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
                 kept16 = S.kept[lane]; strong16 = S.strong[lane];
             }
             const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
+            SS_DEVICE_ASSERT(!writer || (y < H && (max(x, 0) >> 5) < k_wpr));
             if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }
             kp += k_wpr; sp += s_wpr;
         }
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     const int xl = clamp16_x(x, W);
     const EdgeFix efix = make_edge_fix(x, W);
     const int lane_off = 3 * (xl - cb);               // multiple of 48
+    SS_DEVICE_ASSERT(lane_off >= 0 && lane_off + 64 <= CR_BOX && (lane_off & 15) == 0);
     if (lane == 0) {
 #pragma unroll
         for (int d = 0; d < CR_DEPTH; ++d) mbar_init(&sm.bar[d], 1);
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         ++y_cur;
         if (y_cur >= 1 && y_cur <= H - 1) off_cur += q.src_rs;
         if (y + 2 >= y0 && y + 2 < y1) {                   // grey plane, own rows only
+            SS_DEVICE_ASSERT(!out_lane || (y + 2 < H && x >= 0 && x + 16 <= g_rs));
             if (out_lane) *(uint4 *)gp = vcur;
             gp += g_rs;
         }

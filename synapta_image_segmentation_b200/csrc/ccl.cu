@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g_, int32_t *Lal
         while (st) {
             const int bx = chunk * 32 + ((__ffsll((long long)st) - 1) >> 1);
             st &= st - 1;
+            SS_DEVICE_ASSERT(bx >= 0 && bx < g.bw && by < g.bh);
             L[bx] = by * g.bw + bx;
         }
     }
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g_, int32_t *La
             if (HYST && ux >= 0 && (sc & piece_range(rc, x & ~1)) && (su & piece_range(ru, ux & ~1))) continue;
             const int cs = run_start(rc, chunk, x & ~1);
             const int us = (ux >= 0) ? run_start(ru, chunk, ux & ~1) : ru.carryIn;
+            SS_DEVICE_ASSERT(cs >= 0 && cs < g.bw && us >= 0 && us < g.bw);
             uf_union(L, cur_base + cs, up_base + us);
         }
         while (ev_b) {

@@ -45,6 +45,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     c->prof_on = false; c->prof_start = nullptr; c->prof_used = 0;
     c->device = device;
     c->comm = nullptr; c->comm_world = 1; c->comm_rank = 0;
+    c->guard_violations = 0; c->guard_checked = 0;
     c->attr_done = 0; c->last_stream = nullptr; c->ev_last = nullptr; c->last_valid = false;
     memset(&c->hs, 0, sizeof(c->hs));
     const char *e1 = getenv("SYNSEG_TUNE_AD_BAND"), *e2 = getenv("SYNSEG_TUNE_CANNY_BAND");
@@ -94,15 +95,15 @@ extern "C" SYNSEG_EXPORT int synseg_destroy(synseg_ctx *ctx)
 
 extern "C" SYNSEG_EXPORT int64_t synseg_launch_count(const synseg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-void arena_begin(synseg_ctx *ctx) { ctx->arena_top = 0; }
+void arena_begin(synseg_ctx *ctx) { guard_flush(ctx); ctx->arena_top = 0; }
 
 int arena_ensure(synseg_ctx *ctx, size_t bytes)
 {
-    if (bytes <= ctx->arena_bytes) return SYNSEG_OK;
+    if (bytes + SS_GUARD_SLACK <= ctx->arena_bytes) return SYNSEG_OK;
     DeviceScope scope(ctx->device);
     SS_CUDA(cudaDeviceSynchronize());
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
-    size_t want = align_up(bytes, (size_t)1 << 20);
+    size_t want = align_up(bytes + SS_GUARD_SLACK, (size_t)1 << 20);
     cudaError_t e = cudaMalloc(&ctx->arena, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -113,16 +114,67 @@ int arena_ensure(synseg_ctx *ctx, size_t bytes)
     return SYNSEG_OK;
 }
 
-int arena_alloc(synseg_ctx *ctx, size_t bytes, void **out, cudaStream_t)
+int arena_alloc(synseg_ctx *ctx, size_t bytes, void **out, cudaStream_t st)
 {
-    size_t off = align_up(ctx->arena_top, 256);
-    if (off + bytes > ctx->arena_bytes) {
-        synseg_set_error("scratch arena overflow: need %zu, have %zu (internal sizing error)", off + bytes, ctx->arena_bytes);
+    size_t off = align_up(ctx->arena_top, 256) + SS_GUARD_ZONE;
+    const size_t end = align_up(off + bytes, 256) + SS_GUARD_ZONE;
+    if (end > ctx->arena_bytes) {
+        synseg_set_error("scratch arena overflow: need %zu, have %zu (internal sizing error)", end, ctx->arena_bytes);
         return SYNSEG_E_NOMEM;
     }
     *out = ctx->arena + off;
-    ctx->arena_top = off + bytes;
+    ctx->arena_top = end;
+#ifdef SYNSEG_GUARD
+    // canary zones right below the payload and right above its 256-byte rounded end, filled in stream order before any kernel of this call
+    SS_CUDA(cudaMemsetAsync(ctx->arena + off - SS_GUARD_ZONE, 0xA5, SS_GUARD_ZONE, st));
+    SS_CUDA(cudaMemsetAsync(ctx->arena + end - SS_GUARD_ZONE, 0xA5, SS_GUARD_ZONE, st));
+    ctx->guard_recs.push_back(synseg_ctx::GuardRec{off, end - SS_GUARD_ZONE - off});
+#else
+    (void)st;
+#endif
     return SYNSEG_OK;
+}
+
+// Guard build: called when a public call returns and wherever scratch is about to be reused (arena_begin / arena_release /
+// arena_rebase).  Waits for the device, compares every canary zone of the allocations made since the last flush, counts and
+// reports the damaged ones.
+void guard_flush(synseg_ctx *ctx)
+{
+#ifdef SYNSEG_GUARD
+    if (ctx->guard_recs.empty()) return;
+    std::vector<synseg_ctx::GuardRec> recs;
+    recs.swap(ctx->guard_recs);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return; }
+    unsigned char host[2 * 256];
+    for (const synseg_ctx::GuardRec &r : recs) {
+        if (r.off + r.bytes + SS_GUARD_ZONE > ctx->arena_bytes) continue;            // the arena was re-allocated meanwhile
+        if (cudaMemcpy(host, ctx->arena + r.off - SS_GUARD_ZONE, SS_GUARD_ZONE, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(host + 256, ctx->arena + r.off + r.bytes, SS_GUARD_ZONE, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); continue; }
+        ctx->guard_checked += 2;
+        int bad_lo = -1, bad_hi = -1;
+        for (int i = 0; i < 256; ++i) { if (host[i] != 0xA5 && bad_lo < 0) bad_lo = i; if (host[256 + i] != 0xA5 && bad_hi < 0) bad_hi = i; }
+        if (bad_lo >= 0 || bad_hi >= 0) {
+            ctx->guard_violations++;
+            synseg_set_error("SYNSEG_GUARD: canary of the scratch allocation at arena offset %zu (%zu bytes) was overwritten (%s zone, byte %d)",
+                             r.off, r.bytes, bad_lo >= 0 ? "lower" : "upper", bad_lo >= 0 ? bad_lo : bad_hi);
+            fprintf(stderr, "%s\n", synseg_last_error());
+        }
+    }
+#else
+    (void)ctx;
+#endif
+}
+
+// Number of damaged canary zones seen so far / zones compared (both 0 in a normal build); *guard_build = 1 in a SYNSEG_GUARD build.
+extern "C" SYNSEG_EXPORT int64_t synseg_guard_violations(const synseg_ctx *ctx, int64_t *zones_checked, int32_t *guard_build)
+{
+#ifdef SYNSEG_GUARD
+    if (guard_build) *guard_build = 1;
+#else
+    if (guard_build) *guard_build = 0;
+#endif
+    if (zones_checked) *zones_checked = ctx ? ctx->guard_checked : 0;
+    return ctx ? ctx->guard_violations : 0;
 }
 
 extern "C" SYNSEG_EXPORT int synseg_reserve(synseg_ctx *ctx, size_t bytes)

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) exchange_compact_kernel(const u64 *blocks
     const int cnt = (int)blocks[r * stride];
     if (j >= cnt) return;
     const u64 *b = blocks + r * stride + 2 + 2 * (int64_t)j;
+    SS_DEVICE_ASSERT(cnt <= capacity && off + j < world * capacity);
     dkeys[off + j] = b[0]; dhash[off + j] = b[1];
     rank[off + j] = 0; dkeep[off + j] = 1;
 }
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const u64 *dkeys,
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= *n_total) return;
     const int r = rank[i];
+    SS_DEVICE_ASSERT(r >= 0 && r < *n_total);
     all_keys[r] = dkeys[i];
     if (all_hashes) all_hashes[r] = dhash[i];
     keep[r] = dkeep[i];

@@ -19,6 +19,23 @@
 #define SYNSEG_HOST 1
 #endif
 
+// ---- memory-safety build (SYNSEG_NVCC_EXTRA="-DSYNSEG_GUARD", see tools/guard_run.sh) -------------------------------
+// compute-sanitizer is closed on this pool; this build is the substitute:
+//  * every scratch-arena allocation sits between two 256-byte canary zones (0xA5) that are filled when the allocation is
+//    made and compared on the host when the public call that made it returns (the call synchronises its stream first);
+//    a changed canary is counted (synseg_guard_violations) and described in synseg_last_error;
+//  * SS_DEVICE_ASSERT(index in range) inside the kernels is a real device assert (the kernel stops, every later call fails).
+#ifdef SYNSEG_GUARD
+#include <assert.h>
+#define SS_DEVICE_ASSERT(cond) assert(cond)
+constexpr size_t SS_GUARD_ZONE = 256;
+constexpr size_t SS_GUARD_SLACK = (size_t)1 << 20;     // added to every scratch estimate: room for the canary zones
+#else
+#define SS_DEVICE_ASSERT(cond) ((void)0)
+constexpr size_t SS_GUARD_ZONE = 0;
+constexpr size_t SS_GUARD_SLACK = 0;
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -30,6 +47,9 @@ struct synseg_ctx {
     size_t arena_top;     // bump pointer, reset at the start of every public call
     int64_t launches;     // kernels launched through this context
     int32_t *phash_basis; // device int32[8*32]
+    struct GuardRec { size_t off, bytes; };             // guard build: payload offsets of the allocations of the running call
+    std::vector<GuardRec> guard_recs;
+    int64_t guard_violations, guard_checked;
     void *comm;           // ncclComm_t of the dedup exchange (exchange.cu), NULL on a single GPU
     int comm_world, comm_rank;
     uint32_t attr_done;   // ATTR_* bits: cudaFuncSetAttribute calls already made on THIS device (the attribute is per device)
@@ -94,6 +114,8 @@ enum : uint32_t { ATTR_BITMORPH_H = 1u, ATTR_BITMORPH_VH = 2u, ATTR_BITMORPH_V =
 //    (a context for GPU 1 used under current device 0 must neither change the caller's device nor mix devices);
 //  * orders the call behind the previous call on this context when that one was issued to a DIFFERENT stream -- all calls
 //    share one scratch arena, so two in-flight calls are only safe when the second waits for the first.
+void guard_flush(synseg_ctx *ctx);
+
 struct CallGuard {
     synseg_ctx *c;
     cudaStream_t st;
@@ -106,6 +128,9 @@ struct CallGuard {
     }
     ~CallGuard()
     {
+#ifdef SYNSEG_GUARD
+        guard_flush(c);
+#endif
         if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
         else cudaGetLastError();
         if (switched) cudaSetDevice(prev);
@@ -151,7 +176,10 @@ int synseg_check_cuda(cudaError_t e, const char *what);
 void arena_begin(synseg_ctx *ctx);
 int arena_alloc(synseg_ctx *ctx, size_t bytes, void **out, cudaStream_t stream);
 static inline size_t arena_mark(const synseg_ctx *ctx) { return ctx->arena_top; }
-static inline void arena_release(synseg_ctx *ctx, size_t mark) { ctx->arena_top = mark; }
+// Every point where scratch is about to be reused first compares the canaries of what was allocated so far (guard build; no-op otherwise).
+void guard_flush(synseg_ctx *ctx);
+static inline void arena_release(synseg_ctx *ctx, size_t mark) { guard_flush(ctx); ctx->arena_top = mark; }
+static inline void arena_rebase(synseg_ctx *ctx, size_t base) { guard_flush(ctx); ctx->arena_top = base; }
 // Grows the arena to hold `bytes` in total (synchronises the device when it has to reallocate).
 int arena_ensure(synseg_ctx *ctx, size_t bytes);
 

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(MF_THREADS, 2) bit_dilate_erode_kernel(MfParam
         const int y = yA0 + r;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (y >= 0 && y < p.height) v = __ldg((const uint4 *)(sp + (int64_t)y * pitch) + q);
+        SS_DEVICE_ASSERT(r < p.TH + p.k2 + p.K1 - 2 && 4 * q + 4 <= pitch);
         *(uint4 *)(A + r * pitch + 4 * q) = v;
     }
     __syncthreads();

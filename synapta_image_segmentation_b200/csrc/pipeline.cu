@@ -55,7 +55,7 @@ static int detect_chain(synseg_ctx *ctx, const synseg_img *rgb, const synseg_det
 {
     const int W = rgb->width, H = rgb->height, B = rgb->batch;
     const bool grey_in = prm->channels == 1;
-    ctx->arena_top = arena_base;
+    arena_rebase(ctx, arena_base);
     void *p;
     synseg_img gray;
     if (grey_in) gray = *rgb;
@@ -130,7 +130,7 @@ static int detect_pages_impl(synseg_ctx *ctx, const synseg_img *rgb, const synse
         SS_TRY(overlap_streams(ctx));
         const int ns = chunks < ctx->overlap_streams ? chunks : ctx->overlap_streams;
         const int per = cdiv(B, chunks);
-        const size_t region = align_up(detect_scratch_bytes(W, H, per, ml, need_gray), 256);
+        const size_t region = align_up(detect_scratch_bytes(W, H, per, ml, need_gray) + SS_GUARD_SLACK, 256);
         const size_t total = ns * region;
         SS_TRY(arena_ensure(ctx, total > extra_scratch ? total : extra_scratch));
         SS_CUDA(cudaEventRecord(ctx->ev_split_fork, st));

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(RG_THREADS) regions_kernel(const int32_t *n_la
             if (off_b < p.max_regions) emit_region(out + off_b, p, b, SYNSEG_REGION_CC, area);
             else atomicOr(&sh_flags, SYNSEG_REGION_FLAG_CAPACITY);
         }
+        SS_DEVICE_ASSERT(!sm || off_s < p.max_labels);
         if (sm) small[off_s] = make_int4(x, y, x + w, y + h);
         __syncthreads();
         if (tid == 0) {
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(RG_THREADS) regions_kernel(const int32_t *n_la
         }
         __syncthreads();
         if (tid == 0 && cl_cnt >= 3) {
+            SS_DEVICE_ASSERT(2 * n_clusters + 1 < p.max_labels);
             clusters[2 * n_clusters] = make_int4(cl_minx, cl_miny, cl_maxx, cl_maxy);
             clusters[2 * n_clusters + 1] = make_int4(cl_cnt, 0, 0, 0);
             ++n_clusters;

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
         }
         if (OUT_BITS) {
             const uint32_t other = __shfl_xor_sync(FULL, bits16, 1);
+            SS_DEVICE_ASSERT(!(out_lane && !(lane & 1)) || (y < H && (max(x, 0) >> 5) < p.bits.wpr));
             if (out_lane && !(lane & 1)) obits[(int64_t)(y - y0) * p.bits.wpr] = bits16 | (other << 16);
         } else if (out_lane) {
             uint8_t *drow = p.dst.p + img * p.dst.bs + (int64_t)y * p.dst.rs + x;
