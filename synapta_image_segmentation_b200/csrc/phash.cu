@@ -18,14 +18,11 @@ constexpr int PH_MAXW = 8192;
 // Stage 1: cell means.  grid = (32 row groups, regions): CTA (i, r) reduces row group i of region r to its
 // 32 cell values q[i][0..31] (thread per column, rows of the group unrolled by 4 for memory-level parallelism).
 template <int SRC_KIND>
-__global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, int height, const synseg_roi *rois,
-                                                          int32_t *qbuf, const int32_t *count)
+__device__ __forceinline__ void phash_cells_one(uint32_t *colsum, const Plane &src, int width, int height, const synseg_roi *rois, int32_t *qbuf, int ri)
 {
-    if (count && (int)blockIdx.y >= *count) return;
-    __shared__ uint32_t colsum[PH_MAXW];
     synseg_roi r;
-    if (rois) r = rois[blockIdx.y];
-    else { r.image = blockIdx.y; r.x = 0; r.y = 0; r.width = width; r.height = height; }
+    if (rois) r = rois[ri];
+    else { r.image = ri; r.x = 0; r.y = 0; r.width = width; r.height = height; }
     const int tid = threadIdx.x, i = blockIdx.x;
     const uint8_t *base = src.p + r.image * src.bs;
     const int w = r.width, h = r.height;
@@ -89,15 +86,29 @@ __global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, 
         unsigned long long s = 0;
         for (int x = x0; x < x1; ++x) s += colsum[x];
         const unsigned long long c = (unsigned long long)(y1 - y0) * (unsigned long long)(x1 - x0);
-        qbuf[((int64_t)blockIdx.y * 32 + i) * 32 + j] = (int32_t)((256ull * s + c / 2) / c);
+        qbuf[((int64_t)ri * 32 + i) * 32 + j] = (int32_t)((256ull * s + c / 2) / c);
+    }
+}
+
+// grid = (32 row groups, G): CTA (i, g) handles regions g, g + G, ... below n = min(*count, n_rois) (count: device-resident
+// list length of the indirect form, or NULL).  A list whose length is only known on the device is launched with G <= 1024, not
+// with one grid row per capacity slot: 8,000 slots x 32 empty CTAs cost 0.37 ms per call (profiles/r2_launches_summary.txt).
+template <int SRC_KIND>
+__global__ void __launch_bounds__(256) phash_cells_kernel(Plane src, int width, int height, const synseg_roi *rois,
+                                                          int32_t *qbuf, const int32_t *count, int n_rois)
+{
+    __shared__ uint32_t colsum[PH_MAXW];
+    const int n = count ? min(max(*count, 0), n_rois) : n_rois;
+    for (int ri = blockIdx.y; ri < n; ri += gridDim.y) {
+        phash_cells_one<SRC_KIND>(colsum, src, width, height, rois, qbuf, ri);
+        __syncthreads();
     }
 }
 
 // Stage 2: one CTA per region: integer DCT of the 32x32 cell values, low 8x8 block, median bits.
 __global__ void __launch_bounds__(256) phash_dct_kernel(const int32_t *qbuf, const int32_t *basis, unsigned long long *out,
-                                                        const int32_t *count)
+                                                        const int32_t *count, int n_rois)
 {
-    if (count && (int)blockIdx.x >= *count) return;
     __shared__ int32_t q[32][33];
     __shared__ long long T[8][33];
     __shared__ long long F[64];
@@ -106,8 +117,10 @@ __global__ void __launch_bounds__(256) phash_dct_kernel(const int32_t *qbuf, con
     __shared__ unsigned int hbits[2];
     const int tid = threadIdx.x;
     cb[tid] = basis[tid];
+    const int n = count ? min(max(*count, 0), n_rois) : n_rois;
+    for (int ri = blockIdx.x; ri < n; ri += gridDim.x) {
     if (tid == 0) med2 = 0;
-    for (int k = tid; k < 1024; k += 256) q[k >> 5][k & 31] = qbuf[(int64_t)blockIdx.x * 1024 + k];
+    for (int k = tid; k < 1024; k += 256) q[k >> 5][k & 31] = qbuf[(int64_t)ri * 1024 + k];
     __syncthreads();
     // T[v][y] = sum_x C[v][x] q[y][x]
     {
@@ -142,7 +155,9 @@ __global__ void __launch_bounds__(256) phash_dct_kernel(const int32_t *qbuf, con
     if (tid == 0) {
         // bit k of the hash (MSB first) is coefficient k; ballot bit l of word wv is coefficient 32*wv + l
         const unsigned long long hi = __brev(hbits[0]), lo = __brev(hbits[1]);
-        out[blockIdx.x] = (hi << 32) | lo;
+        out[ri] = (hi << 32) | lo;
+    }
+    __syncthreads();
     }
 }
 
@@ -195,11 +210,12 @@ static int run_phash(synseg_ctx *ctx, const synseg_img *src, int src_kind, const
     void *p;
     SS_TRY(arena_alloc(ctx, (size_t)n * 1024 * sizeof(int32_t), &p, st));
     int32_t *qbuf = (int32_t *)p;
-    if (src_kind == 0) phash_cells_kernel<0><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
-    else if (src_kind == 1) phash_cells_kernel<1><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
-    else phash_cells_kernel<2><<<dim3(32, n), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count);
+    const int gy = count ? (n < 1024 ? n : 1024) : n;          // device-resident length: a fixed grid that strides over the list
+    if (src_kind == 0) phash_cells_kernel<0><<<dim3(32, gy), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count, n);
+    else if (src_kind == 1) phash_cells_kernel<1><<<dim3(32, gy), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count, n);
+    else phash_cells_kernel<2><<<dim3(32, gy), 256, 0, st>>>(plane_of(src), src->width, src->height, rois, qbuf, count, n);
     SS_LAUNCH_CHECK(ctx, "phash_cells", st);
-    phash_dct_kernel<<<n, 256, 0, st>>>(qbuf, ctx->phash_basis, (unsigned long long *)out, count);
+    phash_dct_kernel<<<count ? (n < 4096 ? n : 4096) : n, 256, 0, st>>>(qbuf, ctx->phash_basis, (unsigned long long *)out, count, n);
     SS_LAUNCH_CHECK(ctx, "phash_dct", st);
     return SYNSEG_OK;
 }
