@@ -337,8 +337,13 @@ def main():
         sys.stdout.flush()
         json_fd = os.dup(1)
         os.dup2(2, 1)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        preset = os.environ.get("NCCL_DEBUG", "")
+        if os.environ.get("SYNSEG_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["SYNSEG_NCCL_DEBUG"]
+        elif preset.upper() in ("", "VERSION", "WARN"):          # quieter than INFO: the communicator lines would be missing
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        print(f"[rank {rank}] NCCL_DEBUG={os.environ['NCCL_DEBUG']} (was {preset or 'unset'}); NCCL output goes to stderr", file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = Context(local)
