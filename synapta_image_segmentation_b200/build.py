@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsynseg.so")
-SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "morph_fused.cu", "ccl.cu", "reduce.cu", "phash.cu", "colors.cu", "regions.cu", "exchange.cu", "pipeline.cu"]
+SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "morph_fused.cu", "ccl.cu", "hyst_sweep.cu", "reduce.cu", "phash.cu", "colors.cu", "regions.cu", "exchange.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("SYNSEG_NVCC_EXTRA", "").split()
 

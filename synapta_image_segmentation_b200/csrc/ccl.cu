@@ -28,6 +28,8 @@
 //
 // Roofline: HBM/L2-bound on the bit plane; algorithmic bytes 1/8 per pixel read (+4 per pixel when a
 // label image is requested).  The parent array is touched only at run starts.
+#include <stdlib.h>
+
 #include "internal.cuh"
 
 namespace {
@@ -45,6 +47,8 @@ struct RowGeom {
     int nseg;          // segments per row: G lanes x 64 pixels each (G = lanes per block row, 32 or 16)
     int cpr;           // 64-pixel chunks per row = cdiv(width, 64)
     const int2 *dims;  // ragged batch (internal.cuh): per-image width / height; everything above then describes the canvas
+    const int32_t *need;   // hysteresis behind the propagation sweeps (hyst_sweep.cu): the kernels return at once for image i when need[i * need_stride] == 0
+    int need_stride;
 };
 
 // Lanes per block row.  G = 32: one warp per block row.  G = 16: a warp owns two consecutive block rows, one per
@@ -157,6 +161,7 @@ __device__ __forceinline__ void uf_union(int32_t *L, int32_t a, int32_t b)
 // lane = lane within the group (0..G-1); rows outside the image read as empty (null row pointers) so that a half-warp
 // whose block row does not exist still takes part in the warp-wide intrinsics
 #define ROW_PROLOGUE(first_row)                                                             \
+    if (g_.need && __ldg(g_.need + blockIdx.y * g_.need_stride) == 0) return;      /* the sweeps converged for this image */ \
     RowGeom g = g_;                                                                          \
     if (g_.dims) { const int2 d_ = g_.dims[blockIdx.y]; g.width = d_.x; g.height = d_.y; g.bh = (d_.y + 1) >> 1; } \
     const int lane = threadIdx.x & (G - 1);                                                  \
@@ -634,6 +639,7 @@ RowGeom geom_of(BitPlane bits, int width, int height, int G)
     g.nseg = cdiv(width, 64 * G);
     g.cpr = cdiv(width, 64);
     g.dims = bits.dims;
+    g.need = nullptr; g.need_stride = 0;
     return g;
 }
 
@@ -675,7 +681,7 @@ size_t ccl_label_scratch_bytes(int width, int height, int batch)
 size_t hysteresis_scratch_bytes(int width, int height, int batch)
 {
     const int64_t bw = (width + 1) / 2, bh = (height + 1) / 2;
-    return ccl_label_scratch_bytes(width, height, batch) + (size_t)cdiv(bw * bh, 32) * 4 * batch + 512;
+    return ccl_label_scratch_bytes(width, height, batch) + (size_t)cdiv(bw * bh, 32) * 4 * batch + 32 * (size_t)batch + 1024;
 }
 
 size_t ccl_stats_scratch_bytes(int width, int height, int batch, int max_labels)
@@ -746,13 +752,23 @@ int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, i
                    BitPlane edges_bits, bool or_bits, cudaStream_t st)
 {
     const int G = pick_group(width);
-    const RowGeom g = geom_of(kept, width, height, G);
+    RowGeom g = geom_of(kept, width, height, G);
     void *p;
     SS_TRY(arena_alloc(ctx, (size_t)g.bper * batch * 4, &p, st));
     int32_t *L = (int32_t *)p;
     const int64_t fper = cdiv((int64_t)g.bw * g.bh, 32);
     SS_TRY(arena_alloc(ctx, (size_t)fper * 4 * batch, &p, st));
     uint32_t *flags = (uint32_t *)p;
+    // Propagation sweeps first (hyst_sweep.cu): on print nearly every kept pixel is strong or touches a strong one and a few
+    // bit-parallel sweeps reach the fixed point; the union-find below then finds *need == 0 and its kernels return at once.
+    constexpr int N_SWEEPS = 4;
+    if (!edges_u8 && !getenv("SYNSEG_NO_HYST_SWEEPS")) {
+        SS_TRY(arena_alloc(ctx, sizeof(int32_t) * (N_SWEEPS + 1) * (size_t)batch, &p, st));
+        int32_t *sw = (int32_t *)p;
+        bool used = false;
+        SS_TRY(launch_hyst_sweeps(ctx, kept, strong, edges_bits, or_bits, width, height, batch, sw, N_SWEEPS, &used, st));
+        if (used) { g.need = sw + (N_SWEEPS - 1); g.need_stride = N_SWEEPS + 1; }
+    }
     SS_CUDA(cudaMemsetAsync(flags, 0, (size_t)fper * 4 * batch, st));
     SS_TRY(run_union_find(ctx, g, G, batch, L, &strong, st));
     const dim3 grid = row_grid(g, batch, 0, G);

@@ -275,6 +275,10 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
 int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, int height, int batch, const synseg_img *edges_u8,
                    BitPlane edges_bits, bool or_bits, cudaStream_t st);
 
+// Hysteresis by propagation sweeps (hyst_sweep.cu); sw: device int32[n_sweeps]; sw[n_sweeps - 1] != 0 afterwards = not converged
+int launch_hyst_sweeps(synseg_ctx *ctx, BitPlane kept, BitPlane strong, BitPlane out, bool or_bits, int width, int height, int batch,
+                       int32_t *sw, int n_sweeps, bool *used, cudaStream_t st);
+
 size_t ccl_label_scratch_bytes(int width, int height, int batch);
 size_t hysteresis_scratch_bytes(int width, int height, int batch);
 size_t canny_scratch_bytes(int width, int height, int batch);

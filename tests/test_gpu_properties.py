@@ -124,3 +124,57 @@ def test_page_pipeline_property(ctx, page, bs, k, batch):
         assert np.array_equal(stats[j, :n_w].cpu().numpy(), st_w)
         if closed.any() and not closed.all():
             assert np.array_equal(cent[j, :n_w].cpu().numpy(), ce_w)
+
+
+def _weak_chain_image(h, w, seed, vertical):
+    """Long WEAK edges (step of 20 grey levels: |gradient| = 80, between 50 and 150) that cross many 32-row bands / 32-pixel
+    words and touch a STRONG edge (step of 120) at one end only, plus weak edges that touch nothing strong (must vanish)."""
+    rng = np.random.default_rng(seed)
+    a = np.full((h, w), 200, np.uint8)
+    if vertical:
+        for x in range(20, w - 20, 37):
+            a[10:h - 10, x:x + 9] = 180                      # weak stripes over the whole height
+        a[10:14, :] = 60                                     # strong bar across the top: connected stripes survive
+        a[h // 2:h // 2 + 3, 20:w - 20:74] = 200             # cut every second stripe: its lower half hangs on nothing strong
+    else:
+        for y in range(20, h - 20, 23):
+            a[y:y + 7, 10:w - 10] = 180
+        a[:, 10:14] = 60
+        a[20:h - 20:46, w // 2:w // 2 + 3] = 200
+    return a
+
+
+@pytest.mark.parametrize("vertical", [True, False])
+@pytest.mark.parametrize("hw", [(700, 500), (333, 1300)])
+def test_hysteresis_sweeps_and_union_find_fallback(ctx, hw, vertical, monkeypatch):
+    """Weak chains longer than the propagation sweeps reach (hyst_sweep.cu) fall through to the union-find; both paths and the
+    sweeps-off path give cv2.Canny's edges."""
+    h, w = hw
+    img = _weak_chain_image(h, w, 1, vertical)
+    want = cv2.Canny(img, 50, 150)
+    assert 0 < int((want > 0).sum())
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("SYNSEG_NO_HYST_SWEEPS", env)
+        else:
+            monkeypatch.delenv("SYNSEG_NO_HYST_SWEEPS", raising=False)
+        counts, edges = ctx.grid_counts(dev(img), None, 1, 25, 25, True, channels=1)
+        assert np.array_equal(edges[0].cpu().numpy(), want), env
+        assert int(counts[0, 2]) == int((want > 0).sum())
+    monkeypatch.delenv("SYNSEG_NO_HYST_SWEEPS", raising=False)
+    # through the page pipeline (edges OR-ed into the threshold plane): same components with and without the sweeps
+    rgb = dev(np.repeat(img[None, :, :, None], 3, axis=3))
+    a = ctx.detect_pages(rgb, 15, 10, 5, max_labels=4096)
+    monkeypatch.setenv("SYNSEG_NO_HYST_SWEEPS", "1")
+    b = ctx.detect_pages(rgb, 15, 10, 5, max_labels=4096)
+    monkeypatch.delenv("SYNSEG_NO_HYST_SWEEPS", raising=False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1][0, :int(a[0][0])], b[1][0, :int(a[0][0])])
+
+
+@settings(max_examples=60, **COMMON)
+@given(img=grey_images(), lo=st.integers(0, 120), span=st.integers(0, 200))
+def test_canny_bit_path_property(ctx, img, lo, span):
+    """The bit-plane Canny path (propagation sweeps + union-find behind them) that the pipelines use, against cv2.Canny(50, 150)."""
+    want = cv2.Canny(img, 50, 150)
+    _, edges = ctx.grid_counts(dev(img), None, 1, 25, 25, True, channels=1)
+    assert np.array_equal(edges[0].cpu().numpy(), want)
