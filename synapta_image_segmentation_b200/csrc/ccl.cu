@@ -761,7 +761,10 @@ int run_hysteresis(synseg_ctx *ctx, BitPlane kept, BitPlane strong, int width, i
     uint32_t *flags = (uint32_t *)p;
     // Propagation sweeps first (hyst_sweep.cu): on print nearly every kept pixel is strong or touches a strong one and a few
     // bit-parallel sweeps reach the fixed point; the union-find below then finds *need == 0 and its kernels return at once.
-    constexpr int N_SWEEPS = 4;
+#ifndef SYNSEG_HS_SWEEPS
+#define SYNSEG_HS_SWEEPS 4
+#endif
+    constexpr int N_SWEEPS = SYNSEG_HS_SWEEPS;
     if (!edges_u8 && !getenv("SYNSEG_NO_HYST_SWEEPS")) {
         SS_TRY(arena_alloc(ctx, sizeof(int32_t) * (N_SWEEPS + 1) * (size_t)batch, &p, st));
         int32_t *sw = (int32_t *)p;

@@ -17,9 +17,18 @@
 
 namespace {
 
-constexpr int HS_TR = 32;          // rows per band
+#ifndef SYNSEG_HS_TR
+#define SYNSEG_HS_TR 32
+#endif
+#ifndef SYNSEG_HS_MAX_IT
+#define SYNSEG_HS_MAX_IT 24
+#endif
+constexpr int HS_TR = SYNSEG_HS_TR;          // rows per band
 constexpr int HS_ROWS_PER_THREAD = 8;
-constexpr int HS_MAX_IT = 6;       // rounds inside a band per sweep
+constexpr int HS_MAX_IT = SYNSEG_HS_MAX_IT;  // rounds inside a band per sweep
+// Measured on B200, ms per 50-page step, text pages / dense pages (profiles/r2_tune_hysteresis_sweeps.txt); sweeps x rounds:
+// 4 x 3: 1.984 / 2.85, 4 x 6: 1.987 / 2.72, 4 x 12: 1.922 / 2.74, 4 x 16: 1.918 / 2.60, 4 x 24: 1.915 / 2.63, 3 x 32: 1.908 / 2.67,
+// 6 x 6: 1.940 / 2.70; 16-row bands 2.002.  Without the sweeps: 2.13 / 2.67.
 
 __device__ __forceinline__ uint32_t flood_word(uint32_t m, uint32_t s)
 {
