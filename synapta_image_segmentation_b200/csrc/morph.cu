@@ -19,6 +19,8 @@
 //    stay in L2.
 //  * generic 8-bit path: per-thread in-place doubling (sparse-table) over packed bytes in shared
 //    memory with __vmaxu4/__vminu4 -- any grey image, any k.
+#include <stdlib.h>
+
 #include "internal.cuh"
 #include "pixel.cuh"
 
@@ -207,7 +209,9 @@ __global__ void __launch_bounds__(32) bitmorph_v_kernel(BitPlane src, BitPlane d
 // (in-place doubling: after the step with shift s every bit holds the OR of the 2s bits starting there), finishes
 // with the shift k - span and extracts its four words.  No shared memory, no synchronisation: every output word
 // costs ~45 instructions for k = 81 and the kernel runs at full occupancy.  NW = 8 serves k <= 98, NW = 12 k <= 226.
-template <int NW>
+// NOUT = 8 output words per thread (k <= 98, NW = 12) shares the doubling steps among twice as many outputs: 12 x 2 instructions
+// per step for 8 words instead of 8 x 2 for 4 (measured on B200: see DESIGN.md section 6).
+template <int NW, int NOUT>
 __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nq,
                                                           int64_t total, int erode, int k, int anchor)
 {
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
     const int64_t row = i / nq;
     const int img = (int)(row / height);
     const int y = (int)(row - (int64_t)img * height);
-    const int w0 = 4 * q4;
+    const int w0 = NOUT * q4;
     if (src.dims) {                                                   // ragged batch: this image may be smaller than the canvas
         const int2 d = src.dims[img];
         width = d.x; nw = (d.x + 31) >> 5;
@@ -263,20 +267,20 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
         for (int j = 0; j < NW; ++j) D[j] |= D[j + 4 < NW ? j + 4 : NW];
         span *= 2;
     }
-    // E = D | (D >> (k - span)), words 0..4
+    // E = D | (D >> (k - span)), words 0..NOUT
     const int t = k - span, tw = t >> 5, tb = t & 31;
-    uint32_t E[5];
+    uint32_t E[NOUT + 1];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
+    for (int j = 0; j < NOUT + 1; ++j) {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m)
             if (tw == m) { lo = D[j + m < NW ? j + m : NW]; hi = D[j + m + 1 < NW ? j + m + 1 : NW]; }
         E[j] = D[j] | __funnelshift_r(lo, hi, tb);
     }
-    uint32_t o[4];
+    uint32_t o[NOUT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NOUT; ++q) {
         uint32_t v = __funnelshift_r(E[q], E[q + 1], sft);
         if (erode) v = ~v;
         const int w = w0 + q;
@@ -284,7 +288,9 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
         if (w >= nw) v = 0;
         o[q] = v;
     }
-    *(uint4 *)(dst.p + img * dst.bs + (int64_t)y * dst.wpr + w0) = make_uint4(o[0], o[1], o[2], o[3]);
+    uint32_t *dp = dst.p + img * dst.bs + (int64_t)y * dst.wpr + w0;
+    *(uint4 *)dp = make_uint4(o[0], o[1], o[2], o[3]);
+    if (NOUT == 8 && w0 + 4 < dst.wpr) *(uint4 *)(dp + 4) = make_uint4(o[NOUT - 4], o[NOUT - 3], o[NOUT - 2], o[NOUT - 1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,11 +515,13 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
 {
     const int nw = cdiv(width, 32);
     if (k <= 226 && src.p != dst.p) {                      // register kernel (not in place: threads read their neighbours' words)
-        const int nq = src.wpr / 4;
+        const bool wide = k <= 98 && !getenv("SYNSEG_MORPH_H4");          // 8 output words per thread
+        const int nq = wide ? cdiv(src.wpr, 8) : src.wpr / 4;
         const int64_t total = (int64_t)nq * height * batch;
         const unsigned grid = (unsigned)cdiv(total, 256);
-        if (k <= 98) bitmorph_h4_kernel<8><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
-        else bitmorph_h4_kernel<12><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        if (wide) bitmorph_h4_kernel<12, 8><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        else if (k <= 98) bitmorph_h4_kernel<8, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        else bitmorph_h4_kernel<12, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
         SS_LAUNCH_CHECK(ctx, "bitmorph_h", st);
         return SYNSEG_OK;
     }
@@ -538,7 +546,10 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
 {
     const int nw = cdiv(width, 32);
     if (k <= 384) {                                        // van Herk kernel, k words of shared memory per thread
-        const int T = k <= 190 ? 256 : 128;
+        // 128 threads per CTA: k words of shared memory per thread limit the CTAs per SM (k = 81: 2 CTAs of 256 threads = 512 threads,
+        // 5 CTAs of 128 = 640); measured 0.148 -> 0.127 ms per 50 pages for the two column passes of the page pipeline (64: 0.128)
+        int T = 128;
+        if (const char *e = getenv("SYNSEG_MORPH_VT")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256) T = v; }
         const int nseg = cdiv(height, k);
         const int64_t total = (int64_t)nw * nseg * batch;
         if (!(ctx->attr_done & ATTR_BITMORPH_VH)) {
