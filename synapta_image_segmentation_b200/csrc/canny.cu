@@ -240,6 +240,11 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
     for (int d = 0; d < CN_DEPTH; ++d) issue_async(d);                           // rows y0 .. y0+CN_DEPTH-1 in flight
     int slot = 0;
     uint32_t cand_cur = 0;
+    // Repeated rows (REPEAT_NOTE below): rep = number of consecutive grey rows, ending with the newest, that equal their predecessor in
+    // every lane of the strip; last_kw / last_sw = the words written for the previous output row.
+    int rep = 0;
+    uint4 vprev = load_now(y0 - 1);
+    uint32_t last_kw = 0, last_sw = 0;
 #pragma unroll 1
     for (int y = y0 - 2; y < y1; ++y) {
         uint4 vcur;
@@ -249,6 +254,21 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
             issue_async(slot);
             slot = (slot + 1) & (CN_DEPTH - 1);
         } else vcur = load16_rep(row_ptr(y + 2), x, W, false);
+        {
+            const bool same = ((vcur.x ^ vprev.x) | (vcur.y ^ vprev.y) | (vcur.z ^ vprev.z) | (vcur.w ^ vprev.w)) == 0u;
+            rep = __all_sync(FULL, same) ? rep + 1 : 0;
+            vprev = vcur;
+            // REPEAT_NOTE.  Output row y is a function of the grey rows y-2 .. y+2.  If the rows y-3 .. y+2 are all equal (rep >= 5) and all of
+            // them lie inside the image (no replicated or zero border row among them), output row y equals output row y-1, the
+            // magnitude row y+1 equals the three rows in the ring, its candidates equal the current ones and the partials rotate
+            // into themselves: nothing has to be computed -- the previous words are written again.  Vertical strokes, bars, rules, the
+            // inside of solid boxes: half of the rows of a page of print.
+            if (rep >= 5 && y - 3 >= 0 && y + 2 <= H - 1 && y >= y0 + 1) {
+                if (writer) { *kp = last_kw; *sp = last_sw; }
+                kp += k_wpr; sp += s_wpr;
+                continue;
+            }
+        }
         const uint32_t wl = __shfl_up_sync(FULL, vcur.w, 1), wr = __shfl_down_sync(FULL, vcur.x, 1);
         {
             // Blank paper (45 % of the rows of a text page): the new row is the same constant as the two rows above it in
@@ -262,6 +282,7 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
                 if (y >= y0) {
                     if (writer) { *kp = 0u; *sp = 0u; }
                     kp += k_wpr; sp += s_wpr;
+                    last_kw = 0u; last_sw = 0u;
                 }
                 continue;
             }
@@ -289,7 +310,8 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
             }
             const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
             SS_DEVICE_ASSERT(!writer || (y < H && (max(x, 0) >> 5) < k_wpr));
-            if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }
+            last_kw = kept16 | (k_up << 16); last_sw = strong16 | (s_up << 16);
+            if (writer) { *kp = last_kw; *sp = last_sw; }
             kp += k_wpr; sp += s_wpr;
         }
         cand_cur = cand_next;
@@ -470,6 +492,9 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     int slot = 0;
     uint32_t phases = 0;                               // bit d: parity the next wait on stage d expects
     uint32_t cand_cur = 0;
+    int rep = 0;                                       // repeated rows, see REPEAT_NOTE in canny_classes_kernel
+    uint4 vprev = make_uint4(0, 0, 0, 0);
+    uint32_t last_kw = 0, last_sw = 0;
 #pragma unroll 1
     for (int y = y0 - 4; y < y1; ++y) {
         // ---- grey row y + 2 from the RGB stage ------------------------------------------------------------------
@@ -533,6 +558,16 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
             gp += g_rs;
         }
         vcur = apply_edge_fix(vcur, efix);
+        {
+            const bool same = ((vcur.x ^ vprev.x) | (vcur.y ^ vprev.y) | (vcur.z ^ vprev.z) | (vcur.w ^ vprev.w)) == 0u;
+            rep = (y > y0 - 4 && __all_sync(FULL, same)) ? rep + 1 : 0;
+            vprev = vcur;
+            if (rep >= 5 && y - 3 >= 0 && y + 2 <= H - 1 && y >= y0 + 1) {      // output row y == output row y - 1 (REPEAT_NOTE)
+                if (writer) { *kp = last_kw; *sp = last_sw; }
+                kp += k_wpr; sp += s_wpr;
+                continue;
+            }
+        }
         const uint32_t wl = __shfl_up_sync(FULL, vcur.w, 1), wr = __shfl_down_sync(FULL, vcur.x, 1);
         if (y < y0 - 2) {                                  // priming: rows y0-2, y0-1 only become partials
             make_hrow(C, vcur, wl, wr);
@@ -547,6 +582,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
                 if (y >= y0) {
                     if (writer) { *kp = 0u; *sp = 0u; }
                     kp += k_wpr; sp += s_wpr;
+                    last_kw = 0u; last_sw = 0u;
                 }
                 continue;
             }
@@ -572,7 +608,8 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
                 kept16 = S.kept[lane]; strong16 = S.strong[lane];
             }
             const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
-            if (writer) { *kp = kept16 | (k_up << 16); *sp = strong16 | (s_up << 16); }
+            last_kw = kept16 | (k_up << 16); last_sw = strong16 | (s_up << 16);
+            if (writer) { *kp = last_kw; *sp = last_sw; }
             kp += k_wpr; sp += s_wpr;
         }
         cand_cur = cand_next;
