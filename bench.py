@@ -212,6 +212,7 @@ def workload_config(args, world, h, w):
             "pages_per_step_per_gpu": B, "dpi": args.dpi, "parallelism": f"pages sharded over {world} GPU(s)",
             "l2": f"inputs larger than L2: {B * h * w * 3 / 1e6:.0f} MB RGB per step vs 126 MB L2",
             "streams": "synseg_detect_pages runs the two halves of a step's pages as independent chains on two CUDA streams",
+            "cuda_graph": "the detection chain of a step is captured once (Context.capture) and replayed: one graph launch per step" if os.environ.get("SYNSEG_NO_GRAPH") != "1" else "off (SYNSEG_NO_GRAPH=1)",
             "chain": "gray(cv2) -> adaptive(51,10,INV)|Canny(50,150) -> dilate(k) -> close(k) -> CCL8+stats" if args.dpi == 300 else "see DetectConfig"}
 
 
@@ -374,8 +375,22 @@ def main():
     min_area, max_area = int(5000 * s * s), int(0.8 * npx)
     min_ext = int(50 * s)
 
+    # the detection chain of a step (fixed tensors, ~45 launches) is captured into ONE CUDA graph; SYNSEG_NO_GRAPH=1 launches it kernel by kernel
+    use_graph = os.environ.get("SYNSEG_NO_GRAPH") != "1"
+    replay = None
+    if use_graph:
+        try:
+            replay = ctx.capture(lambda: det.detect_components(pages, out=out))
+        except Exception as exc:                       # loud, and on record in config.cuda_graph
+            print(f"[rank {rank}] CUDA graph capture failed, launching kernel by kernel: {exc}", file=sys.stderr)
+            torch.cuda.synchronize()
+            use_graph = False
+
     def step(i, src=pages):
-        det.detect_components(src, out=out)
+        if replay is not None and src is pages:
+            replay()
+        else:
+            det.detect_components(src, out=out)
         ctx.select_rois(out[0], out[1], (rank * K + i) * B, min_area, max_area, min_ext, min_ext, rois, keys, count)
 
     def dedup_exchange(src=pages):
@@ -409,9 +424,18 @@ def main():
     e1.record()
     barrier()
     launches = ctx.launches - launches0
+    if replay is not None:                      # kernels inside the replayed graph are not counted by the context: add what one direct step launches
+        l1 = ctx.launches
+        det.detect_components(pages, out=out)
+        torch.cuda.synchronize()
+        launches += K * (ctx.launches - l1)
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank = [ms_total / K]
     if world > 1:
+        allt = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank = [float(v) / K for v in allt.tolist()]          # every rank's own device time per step (the value uses the slowest)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * K * B / (ms_total / 1000.0)
@@ -611,7 +635,8 @@ def main():
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": workload_config(args, world, h, w),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "ms_per_step_by_rank": [round(v, 4) for v in per_rank]}
         info = dedup.comm_info(ctx)
         line["dedup"] = {"regions_hashed": n_hashed, "survivors": n_survivors, "capacity_overflow": overflow,
                          "collective": (f"ncclAllGather inside synseg_dedup_exchange (library communicator, {info['world']} ranks, NCCL {info['nccl_version']})"

@@ -120,19 +120,25 @@ struct CallGuard {
     synseg_ctx *c;
     cudaStream_t st;
     int prev;
-    bool switched;
-    CallGuard(synseg_ctx *ctx, cudaStream_t stream) : c(ctx), st(stream), prev(-1), switched(false)
+    bool switched, capturing;
+    CallGuard(synseg_ctx *ctx, cudaStream_t stream) : c(ctx), st(stream), prev(-1), switched(false), capturing(false)
     {
         if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) { cudaSetDevice(c->device); switched = true; }
-        if (c->last_valid && c->last_stream != st && c->ev_last) cudaStreamWaitEvent(st, c->ev_last, 0);
+        // A call that is being captured into a CUDA graph is ordered by the graph: an event recorded during capture must not be waited
+        // for by streams outside it (and vice versa), so the cross-stream ordering of the scratch arena is left to whoever replays.
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess) capturing = cs != cudaStreamCaptureStatusNone; else cudaGetLastError();
+        if (!capturing && c->last_valid && c->last_stream != st && c->ev_last) cudaStreamWaitEvent(st, c->ev_last, 0);
     }
     ~CallGuard()
     {
 #ifdef SYNSEG_GUARD
-        guard_flush(c);
+        if (!capturing) guard_flush(c);
 #endif
-        if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
-        else cudaGetLastError();
+        if (!capturing) {
+            if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
+            else cudaGetLastError();
+        }
         if (switched) cudaSetDevice(prev);
     }
 };

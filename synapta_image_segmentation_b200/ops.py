@@ -114,6 +114,23 @@ class Context:
     def reserve(self, width: int, height: int, batch: int):
         check(self.lib.synseg_reserve(self._h, self.lib.synseg_scratch_bytes(width, height, batch)), "synseg_reserve")
 
+    # ---- CUDA graphs -----------------------------------------------------------------------------
+    def capture(self, fn, warmup: int = 2):
+        """Captures the library calls `fn()` makes on this context's device into a CUDA graph and returns `replay()`.
+        One graph launch instead of ~45 kernel launches per 50-page step: the launch-bound inner loop of a resident pipeline
+        (at 8 ranks on one host the per-launch cost of the driver, not the GPUs, limits the step otherwise).  `fn` must use
+        fixed tensors (the graph bakes pointers and shapes in) and must not synchronise; it runs `warmup` times first so
+        that scratch, side streams and kernel attributes exist before the capture.  The caller orders replays against other
+        work on the context (calls inside a capture skip the context's cross-stream event, see csrc/internal.cuh)."""
+        for _ in range(max(1, warmup)):
+            fn()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            fn()
+        return g.replay
+
     # ---- per-kernel timing ---------------------------------------------------------------------
     def profile_begin(self):
         check(self.lib.synseg_profile_begin(self._h, self._s()), "synseg_profile_begin")

@@ -464,3 +464,30 @@ def test_fused_morphology_and_separate_front_end_variants(ctx, monkeypatch):
         closed = cv2.morphologyEx(cv2.dilate(ink, se), cv2.MORPH_CLOSE, se)
         nn, _, ss, cc = cv2.connectedComponentsWithStats(closed, 8, cv2.CV_32S)
         assert int(n0[0]) == nn and np.array_equal(st0[0, :nn].numpy(), ss) and np.array_equal(ce0[0, :nn].numpy(), cc)
+
+
+def test_cuda_graph_capture_of_the_detection_chain(ctx):
+    """Context.capture: the ~45 launches of a detection step (two chains on two streams, TMA kernel, hysteresis sweeps, union-find)
+    replayed as ONE CUDA graph give the tables of the direct call -- also after the input pages change in place."""
+    dpi = 150
+    det = RasterRegionDetector(DetectConfig(dpi=dpi, max_labels=512), ctx=ctx)
+    a = synth_pages(6, dpi, base_seed=51)
+    b = synth_pages(6, dpi, base_seed=52)
+    pages = torch.from_numpy(a).cuda()
+    out = (torch.empty(6, dtype=torch.int32, device="cuda"), torch.empty((6, 512, 5), dtype=torch.int32, device="cuda"),
+           torch.empty((6, 512, 2), dtype=torch.float64, device="cuda"))
+    replay = ctx.capture(lambda: det.detect_components(pages, out=out))
+    for src in (a, b, a):
+        pages.copy_(torch.from_numpy(src).cuda())
+        for t_ in out:
+            t_.zero_()
+        l0 = ctx.launches
+        replay()
+        torch.cuda.synchronize()
+        assert ctx.launches == l0                           # nothing launched kernel by kernel
+        got = [t_.clone() for t_ in out]
+        want = det.detect_components(torch.from_numpy(src).cuda())
+        assert torch.equal(got[0], want[0])
+        for j in range(6):
+            m = int(want[0][j])
+            assert m > 1 and torch.equal(got[1][j, :m], want[1][j, :m]) and torch.equal(got[2][j, :m], want[2][j, :m])
