@@ -327,9 +327,10 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 // cp.async.bulk.tensor.2d (SASS UTMALDG) per strip row and the bytes land in a per-warp shared-memory ring while the
 // warp works on the rows before; an mbarrier per ring stage signals arrival (complete_tx).  A tightly packed RGB page has
 // a row pitch of 3 W bytes (7650 at 300 DPI), not a multiple of 16, so the pages cannot be described as a 2-D image
-// tensor; the tensor map instead views the whole batch as rows of 16 bytes ({16, total / 16} u8, box {16, 98}): a box is
-// the 16-byte-aligned superset of the 1536 bytes a strip row needs, and whatever lies beyond the end of the batch is
-// zero-filled by the hardware (no guard code for the last rows).  Each lane then takes its 64-byte window with four
+// tensor; the tensor map instead views the whole batch as rows of 128 bytes ({128, total / 128} u8, box {128, 13}): a box is
+// the 128-byte-aligned superset of the 1536 bytes a strip row needs (13 requests of 128 bytes to the memory system), and
+// whatever lies beyond the end of the batch is zero-filled by the hardware (no guard code for the last rows).  Each lane then
+// takes its 64-byte window (16-byte aligned: the 16-byte part of the row's misalignment is an address offset) with four
 // LDS.128, realigns it in registers (the misalignment is uniform per row), converts its 16 pixels with cv2's 15-bit
 // fixed-point formula (pixel.cuh) and -- lanes 1..30, rows of the own band -- stores them into the grey plane the
 // threshold kernel reads afterwards.  From there on the row goes through exactly the arithmetic of
@@ -339,9 +340,12 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
 #define SYNSEG_CR_DEPTH 2
 #endif
 constexpr int CR_DEPTH = SYNSEG_CR_DEPTH;          // RGB rows in flight per warp
-constexpr int CR_UNITS = 98;                       // 16-byte units per box: ceil((15 + 1536) / 16) = 97, +1 so a lane window never leaves the box
-constexpr int CR_BOX = CR_UNITS * 16;              // 1568 bytes per TMA box
-constexpr int CR_STAGE = 1664;                     // ring stage: the box rounded up to the 128-byte alignment a TMA destination needs
+constexpr int CR_UNIT = 128;                       // bytes per tensor-map row (the unit a box is aligned to)
+constexpr int CR_UNITS = 13;                       // units per box: a strip row starts up to 127 bytes into its first unit; the last lane's 64-byte window ends at
+                                                   // 112 + 1488 + 64 = 1664 = 13 x 128
+constexpr int CR_BOX = CR_UNITS * CR_UNIT;         // 1664 bytes per TMA box (13 requests of 128 bytes; the first version used 98 units of 16 bytes and
+                                                   // kept the warps of blank pages waiting on the TMA unit: 15 % of the stall samples sat in mbar_wait)
+constexpr int CR_STAGE = CR_BOX;                   // ring stage (a multiple of the 128-byte alignment a TMA destination needs)
 // measured on B200 (profiles/r2_front_end_experiments.txt): 2 stages are enough -- the kernel is bound by instruction issue, not by
 // the latency of the loads; deeper rings only cost resident warps (3: +1 %, 4: +3 %, 6: +19 %), an L2 prefetch 8 rows ahead +26 %
 constexpr int CR_MINBLOCKS = CR_DEPTH <= 3 ? 16 : (CR_DEPTH == 4 ? 14 : (CR_DEPTH == 5 ? 13 : 12));
@@ -388,14 +392,22 @@ __device__ __forceinline__ void tma_load_units(void *dst, const CUtensorMap *map
                  : "memory");
 }
 
-// 12 RGB bytes = 4 pixels -> 4 cv2 grey bytes (same arithmetic as gray.cu:gray4)
+// 12 RGB bytes = 4 pixels -> 4 cv2 grey bytes.  Same value as gray.cu:gray4 with every term doubled,
+// (19596 R + 38470 G + 7470 B + 32768) >> 16 == (9798 R + 19235 G + 3735 B + 16384) >> 15, so that the grey level is byte 2 of the
+// sum (< 2^24) and four of them are gathered with three PRMT instead of four shifts and three merges.
+__device__ __forceinline__ uint32_t cv_gray_b2(uint32_t rgbx)
+{
+    constexpr uint32_t lo = (19596u & 255u) | ((38470u & 255u) << 8) | ((7470u & 255u) << 16);
+    constexpr uint32_t hi = (19596u >> 8) | ((38470u >> 8) << 8) | ((7470u >> 8) << 16);
+    return __dp4a(rgbx, lo, 32768u) + (__dp4a(rgbx, hi, 0u) << 8);
+}
 __device__ __forceinline__ uint32_t cv_gray4(uint32_t w0, uint32_t w1, uint32_t w2)
 {
-    const uint32_t y0 = gray1<SYNSEG_GRAY_CV>(w0);
-    const uint32_t y1 = gray1<SYNSEG_GRAY_CV>(__funnelshift_r(w0, w1, 24));
-    const uint32_t y2 = gray1<SYNSEG_GRAY_CV>(__funnelshift_r(w1, w2, 16));
-    const uint32_t y3 = gray1<SYNSEG_GRAY_CV>(w2 >> 8);
-    return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+    const uint32_t y0 = cv_gray_b2(w0);
+    const uint32_t y1 = cv_gray_b2(__funnelshift_r(w0, w1, 24));
+    const uint32_t y2 = cv_gray_b2(__funnelshift_r(w1, w2, 16));
+    const uint32_t y3 = cv_gray_b2(w2 >> 8);
+    return __byte_perm(__byte_perm(y0, y1, 0x0062), __byte_perm(y2, y3, 0x0062), 0x5410);
 }
 
 struct CrSmem {
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     const int xl = clamp16_x(x, W);
     const EdgeFix efix = make_edge_fix(x, W);
     const int lane_off = 3 * (xl - cb);               // multiple of 48
-    SS_DEVICE_ASSERT(lane_off >= 0 && lane_off + 64 <= CR_BOX && (lane_off & 15) == 0);
+    SS_DEVICE_ASSERT(lane_off >= 0 && lane_off + 64 + (CR_UNIT - 16) <= CR_BOX && (lane_off & 15) == 0);
     if (lane == 0) {
 #pragma unroll
         for (int d = 0; d < CR_DEPTH; ++d) mbar_init(&sm.bar[d], 1);
@@ -447,12 +459,12 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     // byte offset (from the start of the batch) of the strip's first byte in the row being fetched; rows are clamped into the image
     int y_pf = y0 - 2;
     int64_t off_pf = (int64_t)img * q.src_bs + (int64_t)min(max(y_pf, 0), H - 1) * q.src_rs + 3 * (int64_t)cb;
-    const int64_t tail_start = q.total_bytes & ~(int64_t)15;      // bytes from here on are not covered by the tensor map
+    const int64_t tail_start = q.total_bytes & ~(int64_t)(CR_UNIT - 1);      // bytes from here on are not covered by the tensor map
     int y_l2 = y_pf;
     int64_t off_l2 = off_pf;
     if (CR_PREFETCH > 0) {
         for (int d = 0; d < CR_DEPTH + CR_PREFETCH; ++d) {
-            if (lane == 0 && d >= CR_DEPTH && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 4));
+            if (lane == 0 && d >= CR_DEPTH && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 7));
             ++y_l2;
             if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
         }
@@ -462,12 +474,12 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         if (lane == 0 && y_pf <= y1 + 1) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
             mbar_expect_tx(&sm.bar[slot], CR_BOX);
-            tma_load_units(sm.rows[slot], &tmap, (int)(off_pf >> 4), &sm.bar[slot]);
+            tma_load_units(sm.rows[slot], &tmap, (int)(off_pf >> 7), &sm.bar[slot]);
         }
         ++y_pf;
         if (y_pf >= 1 && y_pf <= H - 1) off_pf += q.src_rs;
         if (CR_PREFETCH > 0) {                             // the row CR_PREFETCH rows further on starts its way from HBM to L2 now
-            if (lane == 0 && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 4));
+            if (lane == 0 && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 7));
             ++y_l2;
             if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
         }
@@ -481,9 +493,9 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
     const int k_wpr = p.kept.wpr, s_wpr = p.strong.wpr;
     uint8_t *gp = q.gray.p + img * q.gray.bs + (int64_t)y0 * q.gray.rs + max(x, 0);     // grey row y0 of this lane's group (advances with the own rows)
     const int64_t g_rs = q.gray.rs;
-    // the last 16-byte unit of the batch may be partial and then lies outside the tensor map: only the band holding the last rows checks for it
-    const bool tail_band = (q.total_bytes & 15) != 0 &&
-                           (int64_t)img * q.src_bs + (int64_t)min(y1 + 1, H - 1) * q.src_rs + 3 * (int64_t)(cb + CN_OUT_W + 32) > (q.total_bytes & ~(int64_t)15);
+    // the last 128-byte unit of the batch may be partial and then lies outside the tensor map: only the band holding the last rows checks for it
+    const bool tail_band = (q.total_bytes & (CR_UNIT - 1)) != 0 &&
+                           (int64_t)img * q.src_bs + (int64_t)min(y1 + 1, H - 1) * q.src_rs + 3 * (int64_t)(cb + CN_OUT_W + 32) > tail_start;
 
     HRow A, B, C;
     A.uni = false; B.uni = false; A.rep = 0; B.rep = 1;
@@ -501,20 +513,19 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         mbar_wait(&sm.bar[slot], (phases >> slot) & 1u);
         phases ^= 1u << slot;
         const int a = (int)(off_cur & 15);
+        const int a_unit = (int)(off_cur & (CR_UNIT - 16));       // 16-byte pieces between the start of the box and the strip's first byte
         if (tail_band && off_cur + 3 * (int64_t)(CN_OUT_W + 32) > tail_start) {
-            // last rows of the batch: the final partial 16-byte unit is outside the tensor map (zero-filled); patch it in
-            if (lane == 0) {
-                const int64_t first = (off_cur & ~(int64_t)15);
-                for (int64_t b = tail_start; b < q.total_bytes; ++b) {
-                    const int64_t o = b - first;
-                    if (o >= 0 && o < CR_BOX) sm.rows[slot][o] = q.src[b];
-                }
+            // last rows of the batch: the final partial 128-byte unit is outside the tensor map (zero-filled); patch it in
+            const int64_t first = (off_cur & ~(int64_t)(CR_UNIT - 1));
+            for (int64_t b = tail_start + lane; b < q.total_bytes; b += 32) {
+                const int64_t o = b - first;
+                if (o >= 0 && o < CR_BOX) sm.rows[slot][o] = q.src[b];
             }
             __syncwarp();
         }
         uint4 vcur;
         {
-            const uint4 *wp = (const uint4 *)(sm.rows[slot] + lane_off);
+            const uint4 *wp = (const uint4 *)(sm.rows[slot] + lane_off + a_unit);
             const uint4 q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3];
             const uint32_t w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
             const int ws = a >> 2, bsh = (a & 3) * 8;
@@ -645,7 +656,7 @@ bool canny_rgb_supported(const synseg_img *rgb, const synseg_img *gray)
     if (getenv("SYNSEG_NO_TMA")) return false;
     if (((uintptr_t)rgb->data & 15) != 0) return false;
     const int64_t total = (int64_t)(rgb->batch - 1) * rgb->batch_stride + (int64_t)(rgb->height - 1) * rgb->row_stride + 3 * (int64_t)rgb->width;
-    if (total < 16 * CR_UNITS || (total >> 4) >= 0x7fffffffLL) return false;
+    if (total < CR_BOX || (total >> 7) >= 0x7fffffffLL) return false;
     if (!plane_aligned(gray, 16) || gray->row_stride < (int64_t)align_up((size_t)rgb->width, 16)) return false;
     return tensor_map_encoder() != nullptr;
 }
@@ -673,9 +684,9 @@ int launch_canny_rgb(synseg_ctx *ctx, const synseg_img *rgb, const synseg_img *g
     q.total_bytes = (int64_t)(rgb->batch - 1) * rgb->batch_stride + (int64_t)(rgb->height - 1) * rgb->row_stride + 3 * (int64_t)rgb->width;
     q.src = (const uint8_t *)rgb->data;
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {16, (cuuint64_t)(q.total_bytes >> 4)};
-    const cuuint64_t gstride[1] = {16};
-    const cuuint32_t box[2] = {16, (cuuint32_t)CR_UNITS};
+    const cuuint64_t gdim[2] = {(cuuint64_t)CR_UNIT, (cuuint64_t)(q.total_bytes / CR_UNIT)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)CR_UNIT};
+    const cuuint32_t box[2] = {(cuuint32_t)CR_UNIT, (cuuint32_t)CR_UNITS};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, rgb->data, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -211,16 +211,17 @@ __global__ void __launch_bounds__(32) bitmorph_v_kernel(BitPlane src, BitPlane d
 // costs ~45 instructions for k = 81 and the kernel runs at full occupancy.  NW = 8 serves k <= 98, NW = 12 k <= 226.
 // NOUT = 8 output words per thread (k <= 98, NW = 12) shares the doubling steps among twice as many outputs: 12 x 2 instructions
 // per step for 8 words instead of 8 x 2 for 4 (measured on B200: see DESIGN.md section 6).
+// Grid: x over the (row, thread-of-row) pairs of one image, y = image -- the index arithmetic stays 32-bit (two 64-bit divisions per
+// thread cost as much as the morphology of its eight words).
 template <int NW, int NOUT>
 __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nq,
-                                                          int64_t total, int erode, int k, int anchor)
+                                                          unsigned per_image, int erode, int k, int anchor)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= total) return;
-    const int q4 = (int)(i % nq);
-    const int64_t row = i / nq;
-    const int img = (int)(row / height);
-    const int y = (int)(row - (int64_t)img * height);
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= per_image) return;
+    const int y = (int)(i / (unsigned)nq);
+    const int q4 = (int)(i - (unsigned)y * (unsigned)nq);
+    const int img = blockIdx.y;
     const int w0 = NOUT * q4;
     if (src.dims) {                                                   // ragged batch: this image may be smaller than the canvas
         const int2 d = src.dims[img];
@@ -300,16 +301,20 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
 // [u0, u0 + k) from i on, and the prefix OR of block [u0 + k, u0 + 2k) up to i - 1.  The thread loads the first block
 // into its private shared-memory column (conflict-free: [row][thread]), turns it into suffix ORs in place, then
 // streams the second block keeping the running prefix OR in a register: ~12 instructions per output word for any k.
+// Grid: x over the (segment, word column) pairs of one image, y = image (32-bit index arithmetic).  A segment whose 2k - 1 input rows
+// and k output rows all lie inside the image (all but the first and last one or two) takes a path without any bounds test: running
+// pointers, cp.async for the first block, eight loads of the second block in flight per batch.
+template <bool ERODE>
 __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nseg,
-                                                            int64_t total, int erode, int k, int anchor)
+                                                            unsigned per_image, int k, int anchor)
 {
     extern __shared__ uint32_t sm[];
     const int T = blockDim.x, tid = threadIdx.x;
-    const int64_t id = (int64_t)blockIdx.x * T + tid;
-    if (id >= total) return;
-    const int w = (int)(id % nw);
-    const int seg = (int)((id / nw) % nseg);
-    const int img = (int)(id / ((int64_t)nw * nseg));
+    const unsigned id = blockIdx.x * (unsigned)T + tid;
+    if (id >= per_image) return;
+    const int seg = (int)(id / (unsigned)nw);
+    const int w = (int)(id - (unsigned)seg * (unsigned)nw);
+    const int img = blockIdx.y;
     if (src.dims) {                                                   // ragged batch: this image may be smaller than the canvas
         const int2 d = src.dims[img];
         width = d.x; height = d.y; nw = (d.x + 31) >> 5;
@@ -320,46 +325,91 @@ __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPla
     const uint32_t *sp = src.p + img * src.bs + w;
     uint32_t *dp = dst.p + img * dst.bs + w;
     const int ys = seg * k, u0 = ys - anchor;
-    // first block -> private shared-memory column with 4-byte cp.async copies (all k loads in flight at once, no
-    // registers); rows outside the image hold the identity of the raw domain (0 for dilate, all ones for erode)
-    const uint32_t ident_raw = erode ? 0xffffffffu : 0u;
+    const int swpr = src.wpr, dwpr = dst.wpr;
+    uint32_t *col = sm + tid;                                         // private column: row j at col[j * T]
+    if (u0 >= 0 && u0 + 2 * k - 1 <= height && ys + k <= height) {
+        // ---- interior segment ----
+        const uint32_t *p = sp + (int64_t)u0 * swpr;
+        {
+            uint32_t *c = col;
+#pragma unroll 4
+            for (int j = 0; j < k; ++j) { cp_async4(c, p); c += T; p += swpr; }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        {   // suffix ORs in place (erode: on the complemented rows)
+            uint32_t acc = 0;
+            uint32_t *c = col + (k - 1) * T;
+#pragma unroll 4
+            for (int j = k - 1; j >= 0; --j) {
+                const uint32_t v = *c;
+                acc |= ERODE ? (~v & vmask) : v;
+                *c = acc;
+                c -= T;
+            }
+        }
+        // p = row u0 + k, the first row of the second block; output row ys + i = suffix[i] | OR(second block rows 0 .. i - 1)
+        uint32_t *o = dp + (int64_t)ys * dwpr;
+        const uint32_t *c = col;
+        {
+            const uint32_t v0 = *c;
+            *o = ERODE ? (~v0 & vmask) : v0;
+            o += dwpr; c += T;
+        }
+        uint32_t g = 0;
+        int i = 1;
+        for (; i + 8 <= k; i += 8) {
+            uint32_t t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = __ldg(p + q * swpr);
+            p += 8 * swpr;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                g |= ERODE ? (~t[q] & vmask) : t[q];
+                const uint32_t v = c[q * T] | g;
+                o[q * dwpr] = ERODE ? (~v & vmask) : v;
+            }
+            c += 8 * T; o += 8 * dwpr;
+        }
+        for (; i < k; ++i) {
+            const uint32_t t = __ldg(p);
+            g |= ERODE ? (~t & vmask) : t;
+            const uint32_t v = *c | g;
+            *o = ERODE ? (~v & vmask) : v;
+            p += swpr; c += T; o += dwpr;
+        }
+        return;
+    }
+    // ---- segment touching the top or bottom border: rows outside the image hold the identity of the raw domain ----
+    const uint32_t ident_raw = ERODE ? 0xffffffffu : 0u;
     for (int j = 0; j < k; ++j) {
         const int u = u0 + j;
-        if (u >= 0 && u < height) cp_async4(&sm[j * T + tid], sp + (int64_t)u * src.wpr);
-        else sm[j * T + tid] = ident_raw;
+        if (u >= 0 && u < height) cp_async4(&col[j * T], sp + (int64_t)u * swpr);
+        else col[j * T] = ident_raw;
     }
     cp_async_commit();
     cp_async_wait<0>();
-    {   // suffix ORs in place (erode: on the complemented rows)
+    {
         uint32_t acc = 0;
         for (int j = k - 1; j >= 0; --j) {
-            uint32_t v = sm[j * T + tid];
-            if (erode) v = ~v & vmask;
+            uint32_t v = col[j * T];
+            if (ERODE) v = ~v & vmask;
             acc |= v;
-            sm[j * T + tid] = acc;
+            col[j * T] = acc;
         }
     }
     auto ld = [&](int u) -> uint32_t {
         if (u < 0 || u >= height) return 0u;
-        const uint32_t v = __ldg(sp + (int64_t)u * src.wpr);
-        return erode ? (~v & vmask) : v;
+        const uint32_t v = __ldg(sp + (int64_t)u * swpr);
+        return ERODE ? (~v & vmask) : v;
     };
     uint32_t g = 0;
     const int n_out = min(k, height - ys);
-    for (int i0 = 0; i0 < n_out; i0 += 8) {            // eight loads of the second block in flight per batch
-        uint32_t t[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = (i0 + q > 0 && i0 + q < n_out) ? ld(u0 + k + i0 + q - 1) : 0u;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int i = i0 + q;
-            if (i < n_out) {
-                g |= t[q];
-                uint32_t v = sm[i * T + tid] | g;
-                if (erode) v = ~v;
-                dp[(int64_t)(ys + i) * dst.wpr] = v & vmask;
-            }
-        }
+    for (int i = 0; i < n_out; ++i) {
+        if (i > 0) g |= ld(u0 + k + i - 1);
+        uint32_t v = col[i * T] | g;
+        if (ERODE) v = ~v;
+        dp[(int64_t)(ys + i) * dwpr] = v & vmask;
     }
 }
 
@@ -517,11 +567,12 @@ int launch_bitmorph_h(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
     if (k <= 226 && src.p != dst.p) {                      // register kernel (not in place: threads read their neighbours' words)
         const bool wide = k <= 98 && !getenv("SYNSEG_MORPH_H4");          // 8 output words per thread
         const int nq = wide ? cdiv(src.wpr, 8) : src.wpr / 4;
-        const int64_t total = (int64_t)nq * height * batch;
-        const unsigned grid = (unsigned)cdiv(total, 256);
-        if (wide) bitmorph_h4_kernel<12, 8><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
-        else if (k <= 98) bitmorph_h4_kernel<8, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
-        else bitmorph_h4_kernel<12, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, total, op == SYNSEG_MORPH_ERODE, k, anchor);
+        if (batch > 65535 || (int64_t)nq * height > 0x7fffffffLL) { synseg_set_error("bitmorph_h: batch > 65535 or image too large"); return SYNSEG_E_INVALID; }
+        const unsigned per_image = (unsigned)nq * (unsigned)height;
+        const dim3 grid((unsigned)cdiv(per_image, 256), (unsigned)batch);
+        if (wide) bitmorph_h4_kernel<12, 8><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, per_image, op == SYNSEG_MORPH_ERODE, k, anchor);
+        else if (k <= 98) bitmorph_h4_kernel<8, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, per_image, op == SYNSEG_MORPH_ERODE, k, anchor);
+        else bitmorph_h4_kernel<12, 4><<<grid, 256, 0, st>>>(src, dst, width, height, nw, nq, per_image, op == SYNSEG_MORPH_ERODE, k, anchor);
         SS_LAUNCH_CHECK(ctx, "bitmorph_h", st);
         return SYNSEG_OK;
     }
@@ -551,12 +602,17 @@ int launch_bitmorph_v(synseg_ctx *ctx, BitPlane src, BitPlane dst, int width, in
         int T = 128;
         if (const char *e = getenv("SYNSEG_MORPH_VT")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256) T = v; }
         const int nseg = cdiv(height, k);
-        const int64_t total = (int64_t)nw * nseg * batch;
+        if (batch > 65535 || (int64_t)nw * nseg > 0x7fffffffLL) { synseg_set_error("bitmorph_v: batch > 65535 or image too large"); return SYNSEG_E_INVALID; }
+        const unsigned per_image = (unsigned)nw * (unsigned)nseg;
         if (!(ctx->attr_done & ATTR_BITMORPH_VH)) {
-            SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); ctx->attr_done |= ATTR_BITMORPH_VH;
+            SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SS_CUDA(cudaFuncSetAttribute(bitmorph_v_vh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->attr_done |= ATTR_BITMORPH_VH;
         }
-        bitmorph_v_vh_kernel<<<(unsigned)cdiv(total, T), T, (size_t)k * T * sizeof(uint32_t), st>>>(src, dst, width, height, nw, nseg, total,
-                                                                                                   op == SYNSEG_MORPH_ERODE, k, anchor);
+        const dim3 grid((unsigned)cdiv(per_image, T), (unsigned)batch);
+        const size_t smem = (size_t)k * T * sizeof(uint32_t);
+        if (op == SYNSEG_MORPH_ERODE) bitmorph_v_vh_kernel<true><<<grid, T, smem, st>>>(src, dst, width, height, nw, nseg, per_image, k, anchor);
+        else bitmorph_v_vh_kernel<false><<<grid, T, smem, st>>>(src, dst, width, height, nw, nseg, per_image, k, anchor);
         SS_LAUNCH_CHECK(ctx, "bitmorph_v", st);
         return SYNSEG_OK;
     }

@@ -17,6 +17,8 @@
 // g <= 255 - C (blank paper: the mean cannot exceed 255) skip the prefix and the test altogether (warp-uniform).
 // Every source byte comes from HBM once; the "row out" and centre-row reads of a band hit L2.
 // Output is either a u8 {0,255} plane or a bit plane (two lanes -> one 32-bit word).
+#include <stdlib.h>
+
 #include "internal.cuh"
 #include "pixel.cuh"
 
@@ -73,11 +75,18 @@ __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 
 
 // ALIGNED (source rows 16-byte aligned) is a template parameter so that the byte-load fallback does not sit between
 // the hot instructions of the common case (the loop body has to stay inside the instruction cache).
-template <bool OUT_BITS, bool ALIGNED>
+//
+// R > 0 fixes the window radius at compile time (the page pipeline's block sizes, 51 at 300 DPI and 25 at 150 DPI).  The prefix
+// tile is then lane-major with a pitch of 20 words (five 16-byte units: eight consecutive lanes hit eight different bank groups, so
+// 128-bit accesses are conflict-free): a lane parks its 16 prefixes with 4 STS.128 and fetches the 2 x 16 prefixes its window
+// sums need (columns x + R and x - R - 1, statically known words of the neighbouring lanes' chunks) with 2 x 5 LDS.128 instead of
+// 32 scalar loads at run-time computed addresses (per tested pixel: PRMT, IMAD, IADD3, SHF).  R = 0 is the generic kernel.
+constexpr int PL_PITCH = 20;
+template <bool OUT_BITS, bool ALIGNED, int R>
 __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool dst_aligned)
 {
     constexpr bool src_aligned = ALIGNED;
-    __shared__ uint32_t Psm[AD_WARPS][2][16 * 33];   // [column within lane][lane], padded: conflict-free both ways
+    __shared__ __align__(16) uint32_t Psm[AD_WARPS][2][32 * PL_PITCH];   // R = 0: [column within lane][lane], pitch 33: conflict-free both ways
     __shared__ uint4 Ring[AD_WARPS][AD_DEPTH][3][32]; // cp.async row ring: [step][new | old | centre][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t task = (int64_t)blockIdx.x * AD_WARPS + warp;
@@ -86,7 +95,8 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     const int band = (int)(task % p.bands);
     const int img = (int)(task / p.bands);
 
-    const int W = p.width, H = p.height, r = p.r;
+    const int W = p.width, H = p.height, r = R ? R : p.r;
+    const int n = R ? (2 * R + 1) * (2 * R + 1) : p.n;
     const int x = strip * p.out_w - p.lead + CPL * lane;     // first of this lane's 16 columns
     const int y0 = band * p.band_h, y1 = min(y0 + p.band_h, H);
     const uint8_t *base = p.src.p + img * p.src.bs;
@@ -206,23 +216,54 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
             if (lane >= d) v += nb;
         }
         const uint32_t off = v - a[15];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) Pb[j * 33 + lane] = off + a[j];
-        __syncwarp();
-
         uint32_t bits16 = 0;
-        if (out_lane) {
-            const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
-            // mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + k2  (n odd)  <=>  sign(n g + k2 - 1 - s) set
+        // mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + k2  (n odd)  <=>  sign(n g + k2 - 1 - s) set
+        if (R > 0) {
+            uint4 *own = (uint4 *)(Pb + lane * PL_PITCH);
 #pragma unroll
-            for (int j = 15; j >= 0; --j) {
-                const int X = kx + j, Y = ky + j;              // Y >= 0 because lead >= r + 1
-                const int g = (int)((cw[j >> 2] >> (8 * (j & 3))) & 255u);
-                const int e = g * p.n + p.k2m1 - (int)Pb[(X & 15) * 33 + (X >> 4)] + (int)Pb[(Y & 15) * 33 + (Y >> 4)];
-                bits16 = __funnelshift_l((uint32_t)e, bits16, 1);
+            for (int c = 0; c < 4; ++c) own[c] = make_uint4(off + a[4 * c], off + a[4 * c + 1], off + a[4 * c + 2], off + a[4 * c + 3]);
+            __syncwarp();
+            if (out_lane) {
+                // prefix word 16 lane + R + j (window end) and 16 lane - R - 1 + j (one before the window start), j = 0 .. 15
+                constexpr int XF = R >> 2;                     // first 4-word chunk holding a window-end word (counted from the own chunk 0)
+                constexpr int LB = (R + 16) / 16;              // lanes back to the chunk row of the first window-start word
+                constexpr int Y0 = 16 * LB - R - 1;            // its word in that row (>= 0)
+                constexpr int YF = Y0 >> 2;
+                uint32_t xw[20], yw[20];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const int fx = XF + c, fy = YF + c;
+                    const uint4 tx = *(const uint4 *)(Pb + (lane + (fx >> 2)) * PL_PITCH + 4 * (fx & 3));
+                    const uint4 ty = *(const uint4 *)(Pb + (lane - LB + (fy >> 2)) * PL_PITCH + 4 * (fy & 3));
+                    xw[4 * c] = tx.x; xw[4 * c + 1] = tx.y; xw[4 * c + 2] = tx.z; xw[4 * c + 3] = tx.w;
+                    yw[4 * c] = ty.x; yw[4 * c + 1] = ty.y; yw[4 * c + 2] = ty.z; yw[4 * c + 3] = ty.w;
+                }
+                const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
+#pragma unroll
+                for (int j = 15; j >= 0; --j) {
+                    const int g = (int)__byte_perm(cw[j >> 2], 0, 0x4440 + (j & 3));
+                    const int e = g * n + p.k2m1 - (int)xw[(R & 3) + j] + (int)yw[(Y0 & 3) + j];
+                    bits16 = __funnelshift_l((uint32_t)e, bits16, 1);
+                }
+                if (!p.invert) bits16 = ~bits16;
+                bits16 &= colmask;
             }
-            if (!p.invert) bits16 = ~bits16;
-            bits16 &= colmask;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) Pb[j * 33 + lane] = off + a[j];
+            __syncwarp();
+            if (out_lane) {
+                const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
+#pragma unroll
+                for (int j = 15; j >= 0; --j) {
+                    const int X = kx + j, Y = ky + j;              // Y >= 0 because lead >= r + 1
+                    const int g = (int)((cw[j >> 2] >> (8 * (j & 3))) & 255u);
+                    const int e = g * n + p.k2m1 - (int)Pb[(X & 15) * 33 + (X >> 4)] + (int)Pb[(Y & 15) * 33 + (Y >> 4)];
+                    bits16 = __funnelshift_l((uint32_t)e, bits16, 1);
+                }
+                if (!p.invert) bits16 = ~bits16;
+                bits16 &= colmask;
+            }
         }
         if (OUT_BITS) {
             const uint32_t other = __shfl_xor_sync(FULL, bits16, 1);
@@ -262,7 +303,8 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     // bands win because the cost of a band depends on its content (blank rows skip the prefix and the test), so
     // many small tasks balance the SMs better (measured on B200: 320 rows 1.16 ms, 64 rows 0.81 ms per 50 pages with the first strip kernel; 64-96 rows stay best).
     const int64_t rows_total = (int64_t)gray->height * gray->batch * p.strips;
-    int band_h = (int)(rows_total / (64 * (int64_t)ctx->sm_count));
+    // (the prologue of a band, 2r + 1 latency-bound row loads, is 13 % of the stall samples at 52-row bands: 25-page chains now get 96 rows too)
+    int band_h = (int)(rows_total / (32 * (int64_t)ctx->sm_count));
     band_h = band_h < 32 ? 32 : (band_h > 96 ? 96 : band_h);
     if (ctx->tune_ad_band > 0) band_h = ctx->tune_ad_band;
     if (band_h > gray->height) band_h = gray->height;
@@ -278,12 +320,17 @@ int launch_adaptive_mean(synseg_ctx *ctx, const synseg_img *gray, const synseg_i
     const bool sal = plane_aligned(gray, 16);
     const bool dal = to_bits ? true : plane_aligned(out_u8, 16);
     const unsigned nblocks = (unsigned)cdiv(p.tasks, AD_WARPS);
+    static const bool generic_only = getenv("SYNSEG_AD_GENERIC") != nullptr;      // parity / tuning: always the run-time radius kernel
     if (to_bits) {
-        if (sal) adaptive_mean_kernel<true, true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
-        else adaptive_mean_kernel<true, false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        if (sal && p.r == 25 && !generic_only) adaptive_mean_kernel<true, true, 25><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else if (sal && p.r == 12 && !generic_only) adaptive_mean_kernel<true, true, 12><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else if (sal) adaptive_mean_kernel<true, true, 0><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else adaptive_mean_kernel<true, false, 0><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
     } else {
-        if (sal) adaptive_mean_kernel<false, true><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
-        else adaptive_mean_kernel<false, false><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        if (sal && p.r == 25 && !generic_only) adaptive_mean_kernel<false, true, 25><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else if (sal && p.r == 12 && !generic_only) adaptive_mean_kernel<false, true, 12><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else if (sal) adaptive_mean_kernel<false, true, 0><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
+        else adaptive_mean_kernel<false, false, 0><<<nblocks, 32 * AD_WARPS, 0, st>>>(p, dal);
     }
     SS_LAUNCH_CHECK(ctx, "adaptive_mean", st);
     return SYNSEG_OK;
