@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsynseg.so")
+LIB_PATH = os.environ.get("SYNSEG_LIB") or os.path.join(_HERE, "libsynseg.so")   # SYNSEG_LIB: a variant built with SYNSEG_BUILD_TAG (tuning)
 
 
 class Img(C.Structure):

@@ -14,8 +14,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libsynseg.so")
+# SYNSEG_BUILD_TAG=<tag> builds a variant (other -D flags through SYNSEG_NVCC_EXTRA) beside the product library:
+# libsynseg_<tag>.so, selected at run time with SYNSEG_LIB=<path> (tuning experiments: the variants are built here and travel to the GPU box)
+_TAG = os.environ.get("SYNSEG_BUILD_TAG", "")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libsynseg" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["ctx.cu", "gray.cu", "threshold.cu", "canny.cu", "morph.cu", "morph_fused.cu", "ccl.cu", "hyst_sweep.cu", "reduce.cu", "phash.cu", "colors.cu", "regions.cu", "exchange.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden"] + os.environ.get("SYNSEG_NVCC_EXTRA", "").split()

@@ -456,17 +456,20 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    // byte offset (from the start of the batch) of the strip's first byte in the row being fetched; rows are clamped into the image
+    // byte offset (from the start of the batch) of the strip's first byte in the row being fetched = off0 + rel, rel = (row clamped into the
+    // image) x row stride < 2^31 (canny_rgb_supported): the row loop tracks 32-bit quantities only -- tensor-map row unit0 + (lo0 + rel) / 128
     int y_pf = y0 - 2;
-    int64_t off_pf = (int64_t)img * q.src_bs + (int64_t)min(max(y_pf, 0), H - 1) * q.src_rs + 3 * (int64_t)cb;
+    const int64_t off0 = (int64_t)img * q.src_bs + 3 * (int64_t)cb;
+    const int unit0 = (int)(off0 >> 7), lo0 = (int)(off0 & (CR_UNIT - 1)), rs32 = (int)q.src_rs;
+    int rel_pf = min(max(y_pf, 0), H - 1) * rs32;
     const int64_t tail_start = q.total_bytes & ~(int64_t)(CR_UNIT - 1);      // bytes from here on are not covered by the tensor map
     int y_l2 = y_pf;
-    int64_t off_l2 = off_pf;
+    int rel_l2 = rel_pf;
     if (CR_PREFETCH > 0) {
         for (int d = 0; d < CR_DEPTH + CR_PREFETCH; ++d) {
-            if (lane == 0 && d >= CR_DEPTH && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 7));
+            if (lane == 0 && d >= CR_DEPTH && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, unit0 + ((lo0 + rel_l2) >> 7));
             ++y_l2;
-            if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
+            if ((unsigned)(y_l2 - 1) < (unsigned)(H - 1)) rel_l2 += rs32;
         }
     }
     auto issue = [&](int slot) {
@@ -474,17 +477,17 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         if (lane == 0 && y_pf <= y1 + 1) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
             mbar_expect_tx(&sm.bar[slot], CR_BOX);
-            tma_load_units(sm.rows[slot], &tmap, (int)(off_pf >> 7), &sm.bar[slot]);
+            tma_load_units(sm.rows[slot], &tmap, unit0 + ((lo0 + rel_pf) >> 7), &sm.bar[slot]);
         }
         ++y_pf;
-        if (y_pf >= 1 && y_pf <= H - 1) off_pf += q.src_rs;
+        if ((unsigned)(y_pf - 1) < (unsigned)(H - 1)) rel_pf += rs32;      // the offset only moves while the row index is inside [1, H-1]
         if (CR_PREFETCH > 0) {                             // the row CR_PREFETCH rows further on starts its way from HBM to L2 now
-            if (lane == 0 && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, (int)(off_l2 >> 7));
+            if (lane == 0 && y_l2 <= y1 + 1) tma_prefetch_units(&tmap, unit0 + ((lo0 + rel_l2) >> 7));
             ++y_l2;
-            if (y_l2 >= 1 && y_l2 <= H - 1) off_l2 += q.src_rs;
+            if ((unsigned)(y_l2 - 1) < (unsigned)(H - 1)) rel_l2 += rs32;
         }
     };
-    int64_t off_cur = off_pf;                          // offset of the row consumed next (same recurrence, CR_DEPTH rows behind)
+    int rel_cur = rel_pf;                              // offset of the row consumed next (same recurrence, CR_DEPTH rows behind)
     int y_cur = y_pf;
 #pragma unroll
     for (int d = 0; d < CR_DEPTH; ++d) issue(d);
@@ -512,11 +515,11 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         // ---- grey row y + 2 from the RGB stage ------------------------------------------------------------------
         mbar_wait(&sm.bar[slot], (phases >> slot) & 1u);
         phases ^= 1u << slot;
-        const int a = (int)(off_cur & 15);
-        const int a_unit = (int)(off_cur & (CR_UNIT - 16));       // 16-byte pieces between the start of the box and the strip's first byte
-        if (tail_band && off_cur + 3 * (int64_t)(CN_OUT_W + 32) > tail_start) {
+        const int a = (lo0 + rel_cur) & 15;
+        const int a_unit = (lo0 + rel_cur) & (CR_UNIT - 16);      // 16-byte pieces between the start of the box and the strip's first byte
+        if (tail_band && off0 + rel_cur + 3 * (int64_t)(CN_OUT_W + 32) > tail_start) {
             // last rows of the batch: the final partial 128-byte unit is outside the tensor map (zero-filled); patch it in
-            const int64_t first = (off_cur & ~(int64_t)(CR_UNIT - 1));
+            const int64_t first = ((off0 + rel_cur) & ~(int64_t)(CR_UNIT - 1));
             for (int64_t b = tail_start + lane; b < q.total_bytes; b += 32) {
                 const int64_t o = b - first;
                 if (o >= 0 && o < CR_BOX) sm.rows[slot][o] = q.src[b];
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         issue(slot);
         slot = (slot + 1 == CR_DEPTH) ? 0 : slot + 1;
         ++y_cur;
-        if (y_cur >= 1 && y_cur <= H - 1) off_cur += q.src_rs;
+        if ((unsigned)(y_cur - 1) < (unsigned)(H - 1)) rel_cur += rs32;
         if (y + 2 >= y0 && y + 2 < y1) {                   // grey plane, own rows only
             SS_DEVICE_ASSERT(!out_lane || (y + 2 < H && x >= 0 && x + 16 <= g_rs));
             if (out_lane) *(uint4 *)gp = vcur;
@@ -657,6 +660,7 @@ bool canny_rgb_supported(const synseg_img *rgb, const synseg_img *gray)
     if (((uintptr_t)rgb->data & 15) != 0) return false;
     const int64_t total = (int64_t)(rgb->batch - 1) * rgb->batch_stride + (int64_t)(rgb->height - 1) * rgb->row_stride + 3 * (int64_t)rgb->width;
     if (total < CR_BOX || (total >> 7) >= 0x7fffffffLL) return false;
+    if ((int64_t)rgb->height * rgb->row_stride >= 0x7fffff00LL || rgb->row_stride < 0) return false;      // 32-bit row offsets inside an image
     if (!plane_aligned(gray, 16) || gray->row_stride < (int64_t)align_up((size_t)rgb->width, 16)) return false;
     return tensor_map_encoder() != nullptr;
 }

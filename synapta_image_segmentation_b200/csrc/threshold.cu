@@ -70,6 +70,10 @@ __device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
 }
 
 constexpr int AD_DEPTH = 4;             // rows in flight per warp (cp.async ring)
+#ifndef SYNSEG_AD_PRO
+#define SYNSEG_AD_PRO 0
+#endif
+constexpr int AD_PRO = SYNSEG_AD_PRO;   // prologue of a band (the 2r + 1 rows of the first window): 0 = cp.async through shared memory, n = n loads in registers
 
 __device__ __forceinline__ uint32_t bytes_of_nib(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
@@ -86,8 +90,12 @@ template <bool OUT_BITS, bool ALIGNED, int R>
 __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_mean_kernel(AdParams p, bool dst_aligned)
 {
     constexpr bool src_aligned = ALIGNED;
-    __shared__ __align__(16) uint32_t Psm[AD_WARPS][2][32 * PL_PITCH];   // R = 0: [column within lane][lane], pitch 33: conflict-free both ways
-    __shared__ uint4 Ring[AD_WARPS][AD_DEPTH][3][32]; // cp.async row ring: [step][new | old | centre][lane]
+    struct WarpSmem {
+        uint4 ring[AD_DEPTH][3][32];                 // cp.async row ring: [step][new | old | centre][lane]
+        uint32_t P[2][32 * PL_PITCH];                // prefix tile, double-buffered (R = 0: [column within lane][lane], pitch 33: conflict-free both ways)
+    };
+    __shared__ __align__(16) WarpSmem Sm[AD_WARPS];
+    constexpr int PRO_SLOTS = (int)(sizeof(WarpSmem) / 512);          // the whole per-warp area as row slots for the prologue (22)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t task = (int64_t)blockIdx.x * AD_WARPS + warp;
     if (task >= p.tasks) return;                      // warp-uniform
@@ -110,12 +118,25 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     // running column sums over rows [y - r, y + r] (replicate)
     uint32_t cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (src_aligned) {
-        for (int dy = -r; dy <= r; dy += 8) {            // eight loads in flight, then eight accumulations
-            uint4 t[8];
+        if (AD_PRO == 0) {
+            // the 2r + 1 rows of the first window through cp.async: the whole per-warp shared-memory area serves as 22 row slots, so
+            // the prologue of a band waits for memory three times (r = 25) instead of seven times with eight loads in registers
+            uint4 *scr = (uint4 *)&Sm[warp] + lane;
+            for (int dy = -r; dy <= r; dy += PRO_SLOTS) {
+                const int cnt = min(PRO_SLOTS, r - dy + 1);
+                for (int q = 0; q < cnt; ++q) cp_async16(scr + q * 32, base + (int64_t)min(max(y0 + dy + q, 0), H - 1) * p.src.rs + xl);
+                cp_async_commit();
+                cp_async_wait<0>();
+                for (int q = 0; q < cnt; ++q) add16(cs, apply_edge_fix(scr[q * 32], efix));
+            }
+        } else {
+            for (int dy = -r; dy <= r; dy += (AD_PRO ? AD_PRO : 1)) {       // AD_PRO loads in flight, then as many accumulations
+                uint4 t[AD_PRO ? AD_PRO : 1];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) if (dy + q <= r) t[q] = ldraw(min(max(y0 + dy + q, 0), H - 1));
+                for (int q = 0; q < AD_PRO; ++q) if (dy + q <= r) t[q] = ldraw(min(max(y0 + dy + q, 0), H - 1));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) if (dy + q <= r) add16(cs, apply_edge_fix(t[q], efix));
+                for (int q = 0; q < AD_PRO; ++q) if (dy + q <= r) add16(cs, apply_edge_fix(t[q], efix));
+            }
         }
     } else {
         for (int dy = -r; dy <= r; ++dy) add16(cs, load16_rep(base + (int64_t)min(max(y0 + dy, 0), H - 1) * p.src.rs, x, W, false));
@@ -127,7 +148,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     // Software pipeline (aligned rows): the three row loads of step y + AD_DEPTH are issued with cp.async into a
     // per-warp shared-memory ring while step y is computed -- four rows of latency cover without a single extra
     // register (every lane reads back only what it copied itself, so no barrier is needed).
-    uint4 *ring = &Ring[warp][0][0][lane];
+    uint4 *ring = &Sm[warp].ring[0][0][lane];
     // running pointers (no 64-bit multiplies in the row loop): rows y+r+1 (clamped to H-1), y-r (clamped to 0) and y
     int y_pf = y0;                                                    // next step to prefetch
     const uint8_t *p_new = base + (int64_t)min(y0 + r + 1, H - 1) * p.src.rs + xl;
@@ -154,7 +175,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
     uint32_t *obits = OUT_BITS ? p.bits.p + img * p.bits.bs + (int64_t)y0 * p.bits.wpr + (max(x, 0) >> 5) : nullptr;
 
     for (int y = y0; y < y1; ++y) {
-        uint32_t *Pb = Psm[warp][y & 1];
+        uint32_t *Pb = Sm[warp].P[y & 1];
         uint4 vnew, vold, vcen;
         if (src_aligned) {
             cp_async_wait<AD_DEPTH - 1>();
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
             }
         }
 
-        // inclusive prefix of the 16 column sums of this lane, then across the warp
+        // inclusive prefix of the 16 column sums of this lane
         uint32_t a[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -209,26 +230,30 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
             a[4 * q + 2] = a[4 * q + 1] + (e >> 16);
             a[4 * q + 3] = a[4 * q + 2] + (o >> 16);
         }
-        uint32_t v = a[15];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t nb = __shfl_up_sync(FULL, v, d);
-            if (lane >= d) v += nb;
-        }
-        const uint32_t off = v - a[15];
         uint32_t bits16 = 0;
         // mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + k2  (n odd)  <=>  sign(n g + k2 - 1 - s) set
         if (R > 0) {
+            // No warp-wide scan: a window spans at most LB + LXMAX + 1 lanes, so the tile holds the lane-LOCAL prefixes and the
+            // difference of the two lanes' offsets -- a sum of a few neighbouring lane totals, fetched with independent shuffles
+            // instead of five dependent ones -- is folded into the constant of the test.
+            constexpr int XF = R >> 2;                     // first 4-word chunk holding a window-end word (counted from the own chunk 0)
+            constexpr int LB = (R + 16) / 16;              // lanes back to the chunk row of the first window-start word
+            constexpr int Y0 = 16 * LB - R - 1;            // its word in that row (>= 0)
+            constexpr int YF = Y0 >> 2;
+            constexpr int LXMIN = R >> 4, LXMAX = (R + 15) >> 4;      // lane offsets of the window-end words
             uint4 *own = (uint4 *)(Pb + lane * PL_PITCH);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) own[c] = make_uint4(off + a[4 * c], off + a[4 * c + 1], off + a[4 * c + 2], off + a[4 * c + 3]);
+            for (int c = 0; c < 4; ++c) own[c] = make_uint4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+            uint32_t Cs[LB + LXMAX + 1];                   // Cs[i] = totals of the lanes l - LB .. l - LB + i - 1
+            Cs[0] = 0;
+#pragma unroll
+            for (int m = -LB; m < LXMAX; ++m) {
+                const uint32_t t = m == 0 ? a[15] : (m < 0 ? __shfl_up_sync(FULL, a[15], m < 0 ? -m : 1) : __shfl_down_sync(FULL, a[15], m > 0 ? m : 1));
+                Cs[m + LB + 1] = Cs[m + LB] + t;
+            }
             __syncwarp();
             if (out_lane) {
-                // prefix word 16 lane + R + j (window end) and 16 lane - R - 1 + j (one before the window start), j = 0 .. 15
-                constexpr int XF = R >> 2;                     // first 4-word chunk holding a window-end word (counted from the own chunk 0)
-                constexpr int LB = (R + 16) / 16;              // lanes back to the chunk row of the first window-start word
-                constexpr int Y0 = 16 * LB - R - 1;            // its word in that row (>= 0)
-                constexpr int YF = Y0 >> 2;
+                // local prefix word 16 lane + R + j (window end) and 16 lane - R - 1 + j (one before the window start), j = 0 .. 15
                 uint32_t xw[20], yw[20];
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -238,17 +263,29 @@ __global__ void __launch_bounds__(32 * AD_WARPS, SYNSEG_AD_MINBLOCKS) adaptive_m
                     xw[4 * c] = tx.x; xw[4 * c + 1] = tx.y; xw[4 * c + 2] = tx.z; xw[4 * c + 3] = tx.w;
                     yw[4 * c] = ty.x; yw[4 * c + 1] = ty.y; yw[4 * c + 2] = ty.z; yw[4 * c + 3] = ty.w;
                 }
+                int K[2][2];                               // [window end in lane l + LXMIN + ix][window start in lane l - LB + iy]
+#pragma unroll
+                for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+                    for (int iy = 0; iy < 2; ++iy) K[ix][iy] = p.k2m1 - (int)(Cs[(LXMIN + ix <= LXMAX ? LXMIN + ix : LXMAX) + LB] - Cs[iy]);
                 const uint32_t cw[4] = {vcen.x, vcen.y, vcen.z, vcen.w};
 #pragma unroll
                 for (int j = 15; j >= 0; --j) {
                     const int g = (int)__byte_perm(cw[j >> 2], 0, 0x4440 + (j & 3));
-                    const int e = g * n + p.k2m1 - (int)xw[(R & 3) + j] + (int)yw[(Y0 & 3) + j];
+                    const int e = g * n + K[((R + j) >> 4) - LXMIN][(Y0 + j) >> 4] - (int)xw[(R & 3) + j] + (int)yw[(Y0 & 3) + j];
                     bits16 = __funnelshift_l((uint32_t)e, bits16, 1);
                 }
                 if (!p.invert) bits16 = ~bits16;
                 bits16 &= colmask;
             }
         } else {
+            uint32_t v = a[15];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t nb = __shfl_up_sync(FULL, v, d);
+                if (lane >= d) v += nb;
+            }
+            const uint32_t off = v - a[15];
 #pragma unroll
             for (int j = 0; j < 16; ++j) Pb[j * 33 + lane] = off + a[j];
             __syncwarp();
