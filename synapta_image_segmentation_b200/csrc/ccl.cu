@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g_, int32_t *La
         const int chunk = s * G + lane;
         const u64 t = load_chunk(r0, chunk, g.width), a1 = load_chunk(r1, chunk, g.width);
         const u64 u = load_chunk(u1, chunk, g.width), b0 = load_chunk(u0, chunk, g.width);
+        // (an early exit for segments without any pixel -- one vote after the four loads -- was measured slower: 0.117 -> 0.155 ms per 50 pages)
         const Runs rc = analyze_runs<G>(t | a1, chunk, lane, cc);
         const Runs ru = analyze_runs<G>(u | b0, chunk, lane, cu);
         const uint32_t th = (uint32_t)(t >> 63), uh = (uint32_t)(u >> 63);
@@ -380,6 +381,11 @@ struct SlotCache {
     int key[NSLOT];
     int minx[NSLOT], miny[NSLOT], maxx[NSLOT], maxy[NSLOT], area[NSLOT];
     u64 sumx[NSLOT], sumy[NSLOT];
+    // Background (label 0): only its bounding box is measured.  Its area and coordinate sums are the image totals minus the
+    // foreground's: every foreground contribution is also added here and leaves the CTA as ONE negative contribution to the
+    // accumulators of label 0 (two's complement, exact); stats_finalize adds W H, H W (W - 1) / 2 and W H (H - 1) / 2.
+    int bg_minx, bg_miny, bg_maxx, bg_maxy, fg_area;
+    u64 fg_sumx, fg_sumy;
 };
 
 struct Contrib { int minx, miny, maxx, maxy, area; unsigned int sumx, sumy; };
@@ -416,7 +422,9 @@ __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contri
     v.area = __reduce_add_sync(peers, v.area);
     v.sumx = __reduce_add_sync(peers, v.sumx); v.sumy = __reduce_add_sync(peers, v.sumy);
     if ((int)(threadIdx.x & 31) != __ffs((int)peers) - 1) return;
-    if (key >= a.cap || v.area == 0) return;            // over capacity: reported through n_labels
+    if (v.area == 0) return;
+    atomicAdd(&sc.fg_area, v.area); atomicAdd(&sc.fg_sumx, (u64)v.sumx); atomicAdd(&sc.fg_sumy, (u64)v.sumy);
+    if (key >= a.cap) return;                           // over capacity: reported through n_labels
     const int slot = key & (NSLOT - 1);
     const int old = atomicCAS(&sc.key[slot], -1, key);
     if (old == -1 || old == key) {
@@ -446,6 +454,7 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g_, const int32
         const int t = threadIdx.x;
         sc.key[t] = -1; sc.minx[t] = 0x7fffffff; sc.miny[t] = 0x7fffffff; sc.maxx[t] = -1; sc.maxy[t] = -1;
         sc.area[t] = 0; sc.sumx[t] = 0; sc.sumy[t] = 0;
+        if (t == 0) { sc.bg_minx = 0x7fffffff; sc.bg_miny = 0x7fffffff; sc.bg_maxx = -1; sc.bg_maxy = -1; sc.fg_area = 0; sc.fg_sumx = 0; sc.fg_sumy = 0; }
     }
     __syncthreads();
     ROW_PROLOGUE(0)
@@ -466,11 +475,14 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g_, const int32
             {
                 const int remw = row_ok ? g.width - x0 : 0;
                 const u64 vm = remw >= 64 ? ~0ULL : (remw <= 0 ? 0ULL : ((1ULL << remw) - 1ULL));
-                const u64 b0 = ~a0 & vm, b1 = has_row1 ? (~a1 & vm) : 0ULL;
-                Contrib v;
-                if (b0 | b1) v = contrib_of(b0, b1, x0, y);
-                else { v.minx = 0x7fffffff; v.miny = 0x7fffffff; v.maxx = -1; v.maxy = -1; v.area = 0; v.sumx = 0; v.sumy = 0; }
-                accumulate_group(FULL, 0, v, sc, a, img_off);
+                const u64 b0 = ~a0 & vm, b1 = has_row1 ? (~a1 & vm) : 0ULL, bb = b0 | b1;
+                int mnx = bb ? x0 + __ffsll((long long)bb) - 1 : 0x7fffffff, mxx = bb ? x0 + 63 - __clzll((long long)bb) : -1;
+                int mny = b0 ? y : (b1 ? y + 1 : 0x7fffffff), mxy = b1 ? y + 1 : (b0 ? y : -1);
+                mnx = __reduce_min_sync(FULL, mnx); mny = __reduce_min_sync(FULL, mny);
+                mxx = __reduce_max_sync(FULL, mxx); mxy = __reduce_max_sync(FULL, mxy);
+                if ((threadIdx.x & 31) == 0 && mxx >= 0) {
+                    atomicMin(&sc.bg_minx, mnx); atomicMin(&sc.bg_miny, mny); atomicMax(&sc.bg_maxx, mxx); atomicMax(&sc.bg_maxy, mxy);
+                }
             }
             if (WRITE_LABELS) {
                 int4 *z = (int4 *)(stage->lab + lane * 32);
@@ -534,9 +546,21 @@ __global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g_, const int32
         atomicAdd(&a.area[i], sc.area[t]);
         atomicAdd(&a.sumx[i], sc.sumx[t]); atomicAdd(&a.sumy[i], sc.sumy[t]);
     }
+    if (threadIdx.x == NSLOT) {                       // label 0: bounding box of the background, minus the foreground's sums
+        if (sc.bg_maxx >= 0) {
+            atomicMin(&a.minx[img_off], sc.bg_minx); atomicMin(&a.miny[img_off], sc.bg_miny);
+            atomicMax(&a.maxx[img_off], sc.bg_maxx); atomicMax(&a.maxy[img_off], sc.bg_maxy);
+        }
+        if (sc.fg_area) {
+            atomicAdd(&a.area[img_off], -sc.fg_area);
+            atomicAdd(&a.sumx[img_off], 0ULL - sc.fg_sumx); atomicAdd(&a.sumy[img_off], 0ULL - sc.fg_sumy);
+        }
+    }
 }
 
-__global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int batch, int32_t *n_labels, int32_t *stats, double *centroids)
+// width / height: of the image (per image from `dims` for a ragged batch): label 0 holds minus the foreground totals (see SlotCache)
+__global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int batch, int32_t *n_labels, int32_t *stats, double *centroids,
+                                      int width, int height, const int2 *dims)
 {
     const int img = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -545,6 +569,13 @@ __global__ void stats_finalize_kernel(StatAcc a, const int32_t *n_roots, int bat
     if (k >= a.cap || k >= n) return;
     const int64_t i = (int64_t)img * a.cap + k;
     int32_t *s = stats + i * 5;
+    if (k == 0) {
+        if (dims) { width = dims[img].x; height = dims[img].y; }
+        const u64 W = (u64)width, H = (u64)height;
+        a.area[i] += (int)(W * H);
+        a.sumx[i] += H * (W * (W - 1) / 2);
+        a.sumy[i] += W * (H * (H - 1) / 2);
+    }
     const int area = a.area[i];
     if (area > 0) {
         s[0] = a.minx[i]; s[1] = a.miny[i]; s[2] = a.maxx[i] - a.minx[i] + 1; s[3] = a.maxy[i] - a.miny[i] + 1; s[4] = area;
@@ -743,7 +774,7 @@ int run_ccl_stats(synseg_ctx *ctx, const CclMask &m, const synseg_img *labels, i
         LAUNCH_G(G, (rccl_final_kernel<false, 16>), (rccl_final_kernel<false, 32>), grid, 0, st, g, L, Plane{nullptr, 0, 0}, false, a);
     }
     SS_LAUNCH_CHECK(ctx, "ccl_final", st);
-    stats_finalize_kernel<<<dim3(cdiv(max_labels, 128), batch), 128, 0, st>>>(a, n_roots, batch, n_labels, stats, centroids);
+    stats_finalize_kernel<<<dim3(cdiv(max_labels, 128), batch), 128, 0, st>>>(a, n_roots, batch, n_labels, stats, centroids, m.width, m.height, g.dims);
     SS_LAUNCH_CHECK(ctx, "stats_finalize", st);
     return SYNSEG_OK;
 }

@@ -303,7 +303,11 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
 // streams the second block keeping the running prefix OR in a register: ~12 instructions per output word for any k.
 // Grid: x over the (segment, word column) pairs of one image, y = image (32-bit index arithmetic).  A segment whose 2k - 1 input rows
 // and k output rows all lie inside the image (all but the first and last one or two) takes a path without any bounds test: running
-// pointers, cp.async for the first block, eight loads of the second block in flight per batch.
+// pointers, cp.async for the first block, VB loads of the second block in flight per batch.
+#ifndef SYNSEG_MORPH_VB
+#define SYNSEG_MORPH_VB 8
+#endif
+constexpr int VB = SYNSEG_MORPH_VB;      // loads of the second block in flight per batch (interior segments; 16 measured 3 % slower)
 template <bool ERODE>
 __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPlane dst, int width, int height, int nw, int nseg,
                                                             unsigned per_image, int k, int anchor)
@@ -358,18 +362,18 @@ __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPla
         }
         uint32_t g = 0;
         int i = 1;
-        for (; i + 8 <= k; i += 8) {
-            uint32_t t[8];
+        for (; i + VB <= k; i += VB) {
+            uint32_t t[VB];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = __ldg(p + q * swpr);
-            p += 8 * swpr;
+            for (int q = 0; q < VB; ++q) t[q] = __ldg(p + q * swpr);
+            p += VB * swpr;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < VB; ++q) {
                 g |= ERODE ? (~t[q] & vmask) : t[q];
                 const uint32_t v = c[q * T] | g;
                 o[q * dwpr] = ERODE ? (~v & vmask) : v;
             }
-            c += 8 * T; o += 8 * dwpr;
+            c += VB * T; o += VB * dwpr;
         }
         for (; i < k; ++i) {
             const uint32_t t = __ldg(p);
@@ -405,11 +409,20 @@ __global__ void __launch_bounds__(256) bitmorph_v_vh_kernel(BitPlane src, BitPla
     };
     uint32_t g = 0;
     const int n_out = min(k, height - ys);
-    for (int i = 0; i < n_out; ++i) {
-        if (i > 0) g |= ld(u0 + k + i - 1);
-        uint32_t v = col[i * T] | g;
-        if (ERODE) v = ~v;
-        dp[(int64_t)(ys + i) * dwpr] = v & vmask;
+    for (int i0 = 0; i0 < n_out; i0 += 8) {            // eight loads of the second block in flight per batch (a load per step would make
+        uint32_t t[8];                                 // the two border segments of a column the critical path of the whole launch)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = (i0 + q > 0 && i0 + q < n_out) ? ld(u0 + k + i0 + q - 1) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q;
+            if (i < n_out) {
+                g |= t[q];
+                uint32_t v = col[i * T] | g;
+                if (ERODE) v = ~v;
+                dp[(int64_t)(ys + i) * dwpr] = v & vmask;
+            }
+        }
     }
 }
 
