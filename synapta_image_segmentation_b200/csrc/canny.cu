@@ -348,7 +348,13 @@ constexpr int CR_BOX = CR_UNITS * CR_UNIT;         // 1664 bytes per TMA box (13
 constexpr int CR_STAGE = CR_BOX;                   // ring stage (a multiple of the 128-byte alignment a TMA destination needs)
 // measured on B200 (profiles/r2_front_end_experiments.txt): 2 stages are enough -- the kernel is bound by instruction issue, not by
 // the latency of the loads; deeper rings only cost resident warps (3: +1 %, 4: +3 %, 6: +19 %), an L2 prefetch 8 rows ahead +26 %
-constexpr int CR_MINBLOCKS = CR_DEPTH <= 3 ? 16 : (CR_DEPTH == 4 ? 14 : (CR_DEPTH == 5 ? 13 : 12));
+#ifdef SYNSEG_CR_MINB
+constexpr int CR_MINBLOCKS = SYNSEG_CR_MINB;
+#else
+// 2 stages: 17 CTAs of 12.9 KB fit the 227 KB of an SM; asking for 17 makes ptxas settle on 96 registers (20 bytes of spills) instead of 128:
+// 0.615 -> 0.607 ms per 50 pages
+constexpr int CR_MINBLOCKS = CR_DEPTH <= 2 ? 17 : (CR_DEPTH == 3 ? 16 : (CR_DEPTH == 4 ? 14 : (CR_DEPTH == 5 ? 13 : 12)));
+#endif
 #ifndef SYNSEG_CR_PREFETCH
 #define SYNSEG_CR_PREFETCH 0
 #endif

@@ -107,7 +107,7 @@ struct synseg_ctx {
 };
 
 enum : uint32_t { ATTR_BITMORPH_H = 1u, ATTR_BITMORPH_VH = 2u, ATTR_BITMORPH_V = 4u, ATTR_MORPH_U8_H = 8u, ATTR_MORPH_U8_V = 16u, ATTR_HSV_HIST = 32u,
-                  ATTR_FRONT = 64u, ATTR_MORPH2D = 128u };
+                  ATTR_FRONT = 64u, ATTR_MORPH2D = 128u, ATTR_HYST_SWEEP = 256u };
 
 // Entry guard of every public call that queues work (SS_ENTER below):
 //  * makes the context's device current for the duration of the call and restores the caller's device afterwards

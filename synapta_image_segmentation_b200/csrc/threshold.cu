@@ -69,7 +69,10 @@ __device__ __forceinline__ void sub16(uint32_t cs[8], const uint4 v)
     cs[6] -= __byte_perm(v.w, 0, 0x4240); cs[7] -= __byte_perm(v.w, 0, 0x4341);
 }
 
-constexpr int AD_DEPTH = 4;             // rows in flight per warp (cp.async ring)
+#ifndef SYNSEG_AD_DEPTH
+#define SYNSEG_AD_DEPTH 4
+#endif
+constexpr int AD_DEPTH = SYNSEG_AD_DEPTH;   // rows in flight per warp (cp.async ring; a power of two)
 #ifndef SYNSEG_AD_PRO
 #define SYNSEG_AD_PRO 0
 #endif
