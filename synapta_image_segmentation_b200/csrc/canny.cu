@@ -163,6 +163,92 @@ __device__ __forceinline__ void nms_one(const MagRing &R, const CnState &st, Nms
     }
 }
 
+// sign bits of eight packed 16-bit pair registers -> 16-bit mask in gather order (see produce_row)
+__device__ __forceinline__ uint32_t sign_bits_gather(const uint32_t w[8])
+{
+    uint32_t z = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z |= ((__byte_perm(w[2 * i], w[2 * i + 1], 0x7531) & 0x80808080u) >> 7) << i;
+    z = (z | (z >> 4)) & 0x00FF00FFu;
+    return (z | (z >> 8)) & 0xFFFFu;
+}
+
+// gather order -> column order, both 16-bit halves of x at once: bit 4t + i -> bit 4i + (t >> 1) + 2 (t & 1), i.e. the index bits
+// (b3 b2 b1 b0) become (b1 b0 b2 b3): three delta swaps
+__device__ __forceinline__ uint32_t gather_to_columns(uint32_t x)
+{
+    uint32_t t;
+    t = ((x >> 6) ^ x) & 0x00CC00CCu; x ^= t ^ (t << 6);
+    t = ((x >> 3) ^ x) & 0x0A0A0A0Au; x ^= t ^ (t << 3);
+    t = ((x >> 1) ^ x) & 0x22222222u; x ^= t ^ (t << 1);
+    return x;
+}
+
+#ifndef SYNSEG_CN_VGATE
+#define SYNSEG_CN_VGATE 160
+#endif
+constexpr int CN_VGATE = SYNSEG_CN_VGATE;   // candidates in a strip row from which the packed pass below runs first (0 = never)
+
+// Candidates whose gradient is steep enough to be in cv2's vertical class without the 32-bit products -- |dy| >= 3 |dx| implies
+// |dy| << 15 > |dx| (13573 + 65536) -- are suppressed for all 16 pixels of a lane at once in packed 16-bit arithmetic: their two
+// neighbours are the pixels above and below, which sit in the same register position of the other ring rows (no list, no dealing
+// out, no per-candidate address arithmetic).  The tops and bottoms of words, rules, bars and frames put hundreds of such candidates
+// into one strip row (9 rounds of the list path, ~80 instructions each, against ~230 here).  Returns kept | strong << 16 in column
+// order and removes the candidates it decided from `cand` (gather order).  Every magnitude is < 2^15, so the sign of a packed
+// difference is the comparison.
+__device__ __forceinline__ uint32_t nms_vertical_packed(const MagRing &R, const CnState &st, int y, int lane, int hi, uint32_t &cand)
+{
+    const int sc = y % 3, su = (y + 2) % 3, sd = (y + 1) % 3, par = y & 1;
+    const bool zu = (st.zmask >> su) & 1u, zd = (st.zmask >> sd) & 1u;
+    const uint32_t hpair = (uint32_t)min(hi, 0x7FFF) * 0x00010001u;
+    uint32_t vs[8], ks[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t m = R.mag[sc][i][lane], up = zu ? 0u : R.mag[su][i][lane], dn = zd ? 0u : R.mag[sd][i][lane];
+        const uint32_t dx = R.dx[par][i][lane], dy = R.dy[par][i][lane];
+        const uint32_t ax = __vmaxs2(dx, __vneg2(dx)), ay = __vmaxs2(dy, __vneg2(dy));
+        const uint32_t t = __vsub2(ay, __vadd2(ax, ax << 1));          // sign: |dy| < 3 |dx| (not decided here)
+        const uint32_t c = __vadd2(m, st.kpair);                       // sign: candidate (m > lo)
+        const uint32_t d1 = __vsub2(up, m), d2 = __vsub2(m, dn);       // sign: m > up;  m < dn
+        const uint32_t h = __vsub2(hpair, m);                          // sign: m > hi
+        vs[i] = c & ~t;
+        ks[i] = vs[i] & d1 & ~d2;
+        ss[i] = ks[i] & h;
+    }
+    const uint32_t vmask = sign_bits_gather(vs) & cand;                // (halo lanes and lanes outside the image hold cand == 0)
+    const uint32_t res = gather_to_columns((sign_bits_gather(ks) & vmask) | ((sign_bits_gather(ss) & vmask) << 16));
+    cand &= ~vmask;
+    return res;
+}
+
+// Non-maximum suppression of strip row y: candidate mask of this lane (gather order) -> kept16 / strong16 (column order).
+__device__ __forceinline__ void nms_row(MagRing &R, const CnState &st, NmsStage &S, int y, int lane, uint32_t mycand, int hi,
+                                        uint32_t &kept16, uint32_t &strong16)
+{
+    kept16 = 0; strong16 = 0;
+    int cnt = __popc(mycand);
+    const int total0 = __reduce_add_sync(FULL, cnt);
+    if (total0 == 0) return;
+    if (CN_VGATE > 0 && total0 >= CN_VGATE) {
+        const uint32_t r = nms_vertical_packed(R, st, y, lane, hi, mycand);
+        kept16 = r & 0xFFFFu; strong16 = r >> 16;
+        cnt = __popc(mycand);
+        if (!__any_sync(FULL, cnt != 0)) return;
+    }
+    // balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int pos = incl - cnt;
+    for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1));
+    S.kept[lane] = 0u; S.strong[lane] = 0u;
+    __syncwarp();
+    for (int q = lane; q < total; q += 32) { const int id = S.list[q]; nms_one(R, st, S, y, id >> 4, id & 15, hi); }
+    __syncwarp();
+    kept16 |= S.kept[lane]; strong16 |= S.strong[lane];
+}
+
 // ALIGNED (source rows 16-byte aligned) is a template parameter: the byte-load fallback stays out of the hot code.
 template <bool ALIGNED>
 __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_classes_kernel(CnParams p)
@@ -291,23 +377,8 @@ __global__ void __launch_bounds__(32 * CN_WARPS, SYNSEG_CN_MINBLOCKS) canny_clas
         const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, (y + 1) & 1, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
         __syncwarp();
         if (y >= y0) {
-            uint32_t kept16 = 0, strong16 = 0;
-            const uint32_t mycand = out_lane ? cand_cur : 0u;
-            if (__any_sync(FULL, mycand != 0u)) {
-                // balanced NMS: list the candidates of the strip row, deal them out evenly to the 32 lanes
-                const int cnt = __popc(mycand);
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
-                const int total = __shfl_sync(FULL, incl, 31);
-                int pos = incl - cnt;
-                for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1));
-                S.kept[lane] = 0u; S.strong[lane] = 0u;
-                __syncwarp();
-                for (int q = lane; q < total; q += 32) { const int id = S.list[q]; nms_one(R, st, S, y, id >> 4, id & 15, hi); }
-                __syncwarp();
-                kept16 = S.kept[lane]; strong16 = S.strong[lane];
-            }
+            uint32_t kept16, strong16;
+            nms_row(R, st, S, y, lane, out_lane ? cand_cur : 0u, hi, kept16, strong16);
             const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
             SS_DEVICE_ASSERT(!writer || (y < H && (max(x, 0) >> 5) < k_wpr));
             last_kw = kept16 | (k_up << 16); last_sw = strong16 | (s_up << 16);
@@ -611,22 +682,8 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
         const uint32_t cand_next = produce_row(R, st, (y + 4) % 3, (y + 1) & 1, lane, A, B, C, y + 1 >= 0 && y + 1 < H);   // magnitude row y+1
         __syncwarp();
         if (y >= y0) {
-            uint32_t kept16 = 0, strong16 = 0;
-            const uint32_t mycand = out_lane ? cand_cur : 0u;
-            if (__any_sync(FULL, mycand != 0u)) {
-                const int cnt = __popc(mycand);
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int nb = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += nb; }
-                const int total = __shfl_sync(FULL, incl, 31);
-                int pos = incl - cnt;
-                for (uint32_t c = mycand; c; c &= c - 1) S.list[pos++] = (uint16_t)((lane << 4) | (__ffs((int)c) - 1));
-                S.kept[lane] = 0u; S.strong[lane] = 0u;
-                __syncwarp();
-                for (int qq = lane; qq < total; qq += 32) { const int id = S.list[qq]; nms_one(R, st, S, y, id >> 4, id & 15, hi); }
-                __syncwarp();
-                kept16 = S.kept[lane]; strong16 = S.strong[lane];
-            }
+            uint32_t kept16, strong16;
+            nms_row(R, st, S, y, lane, out_lane ? cand_cur : 0u, hi, kept16, strong16);
             const uint32_t k_up = __shfl_down_sync(FULL, kept16, 1), s_up = __shfl_down_sync(FULL, strong16, 1);
             last_kw = kept16 | (k_up << 16); last_sw = strong16 | (s_up << 16);
             if (writer) { *kp = last_kw; *sp = last_sw; }
