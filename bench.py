@@ -529,18 +529,28 @@ def main():
     achieved = alg_bytes / (launch_ms / 1000.0) / 1e9
     traffic = None                      # DRAM bytes per launch of that kernel from the committed ncu capture
     binding = None
+    issue_slots = None                  # the kernel against the resource that binds it: warp instructions vs the issue slots of the GPU
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tj.get("pages_per_launch") == B and dom in tj["kernels"]:
-            traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
-            binding = tj["kernels"][dom].get("binding")
+            tk = tj["kernels"][dom]
+            traffic = tk["dram_read_bytes"] + tk["dram_write_bytes"]
+            binding = tk.get("binding")
+            if tk.get("warp_instructions"):
+                props = torch.cuda.get_device_properties(dev)
+                mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+                floor_ms = tk["warp_instructions"] / (props.multi_processor_count * 4 * mhz * 1e6) * 1e3
+                issue_slots = {"warp_instructions_per_launch": tk["warp_instructions"], "schedulers": props.multi_processor_count * 4,
+                               "sm_mhz": mhz, "floor_ms": floor_ms, "frac": floor_ms / launch_ms,
+                               "what": "warp instructions of the committed ncu capture / (SMs x 4 schedulers x clock) = the time at one issue per "
+                                       "scheduler and cycle, over the launch time measured in this run"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "share_of_step": dk["share"],
                 "serial_step_ms": step_ms,
-                "binding_resource": binding,
+                "binding_resource": binding, "issue_slots": issue_slots,
                 "note": "frac is the HBM fraction the contract asks for; the kernel's BINDING resource (from the committed ncu capture, "
                         "profiles/traffic.json) is reported in binding_resource. Per-kernel times come from profiled steps that run every "
                         "kernel alone on one stream; the timed region runs the page chunks of a step on two streams (SYNSEG_OVERLAP)",
