@@ -268,14 +268,15 @@ __global__ void __launch_bounds__(256) bitmorph_h4_kernel(BitPlane src, BitPlane
         for (int j = 0; j < NW; ++j) D[j] |= D[j + 4 < NW ? j + 4 : NW];
         span *= 2;
     }
-    // E = D | (D >> (k - span)), words 0..NOUT
+    // E = D | (D >> (k - span)), words 0..NOUT.  k - span < span: the word part of the shift is 0 or 1 while span <= 64 (k <= 127)
     const int t = k - span, tw = t >> 5, tb = t & 31;
+    constexpr int MAXTW = (NW == 8 || NOUT == 8) ? 2 : 4;       // both are only launched for k <= 98
     uint32_t E[NOUT + 1];
 #pragma unroll
     for (int j = 0; j < NOUT + 1; ++j) {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < MAXTW; ++m)
             if (tw == m) { lo = D[j + m < NW ? j + m : NW]; hi = D[j + m + 1 < NW ? j + m + 1 : NW]; }
         E[j] = D[j] | __funnelshift_r(lo, hi, tb);
     }

@@ -116,6 +116,34 @@ def test_canny_weak_strong_mixtures(ctx, passes):
             assert np.array_equal(host(ctx.canny(dev(g), lo, hi)), cv2.Canny(g, lo, hi)), (passes, h, w, lo, hi)
 
 
+def test_canny_rows_full_of_candidates(ctx):
+    """Strip rows with hundreds of candidates take the packed vertical-class pass (|dy| >= 3 |dx|) before the candidate list:
+    horizontal edges of every contrast with slanted, noisy and tapering stretches (classes mixed inside one row), plateaus that tie
+    with the row above / below (m > up but m >= down), edges on the first and last image rows, widths of several strips."""
+    rng = np.random.default_rng(77)
+    for h, w in ((97, 481), (160, 1700), (64, 2550)):
+        g = np.full((h, w), 230, np.uint8)
+        y = 3
+        while y + 6 < h:
+            c = int(rng.integers(0, 200))
+            t = int(rng.integers(1, 5))
+            g[y:y + t, :] = c                                                    # a bar: two horizontal edges, equal magnitudes on two rows
+            if rng.random() < 0.5:                                               # a slanted stretch: the direction class changes along the row
+                x0 = int(rng.integers(0, w - 40))
+                for i in range(40):
+                    g[y + (i // 8) % (t + 1):y + t, x0 + i] = c
+            if rng.random() < 0.5:                                               # noise on top of a stretch
+                x0 = int(rng.integers(0, w - 64))
+                g[y - 1:y + t + 1, x0:x0 + 64] = rng.integers(0, 256, (t + 2, 64))
+            if rng.random() < 0.5:                                               # a horizontal ramp along the bar: |dx| > 0 everywhere
+                g[y:y + t, :] = np.clip(c + (np.arange(w) * int(rng.integers(1, 4))) % 120, 0, 255).astype(np.uint8)
+            y += t + int(rng.integers(2, 7))
+        g[0, :] = 10; g[h - 1, : w // 2] = 20                                    # edges against the zero ring outside the image
+        for lo, hi in ((50, 150), (10, 30), (100, 400)):
+            got = host(ctx.canny(dev(g), lo, hi))
+            assert np.array_equal(got, cv2.Canny(g, lo, hi)), (h, w, lo, hi)
+
+
 def test_canny_batch(ctx):
     g = np.stack([imgs.shapes(333, 517, s) for s in range(4)])
     got = host(ctx.canny(dev(g)))
