@@ -546,6 +546,16 @@ def main():
                                        "scheduler and cycle, over the launch time measured in this run"}
     except Exception:
         pass
+    issue_fracs = {}                    # every profiled kernel against the issue slots (warp instructions of the committed capture)
+    try:
+        props = torch.cuda.get_device_properties(dev)
+        mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+        for kname, tk in tj["kernels"].items():
+            if tj.get("pages_per_launch") == B and tk.get("warp_instructions") and kname in kernels:
+                floor_ms = tk["warp_instructions"] / (props.multi_processor_count * 4 * mhz * 1e6) * 1e3
+                issue_fracs[kname] = round(floor_ms / kernels[kname]["ms_per_step"], 3)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "share_of_step": dk["share"],
@@ -558,7 +568,8 @@ def main():
                                "frac": 19.0 * npx * B / (step_ms / 1000.0) / 1e9 / peak},
                 "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "share": round(v["share"], 4),
                                 "launches": v["launches_per_step"],
-                                "GBps": round(ALG_BYTES_PER_PX.get(k, 0.0) * npx * B / max(v["ms_per_step"] / max(1, v["launches_per_step"]), 1e-9) / 1e6, 1)}
+                                "GBps": round(ALG_BYTES_PER_PX.get(k, 0.0) * npx * B / max(v["ms_per_step"] / max(1, v["launches_per_step"]), 1e-9) / 1e6, 1),
+                                "issue_slot_frac": issue_fracs.get(k)}
                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
 
     # ---- dense pages: the content-dependent worst case (no blank paper anywhere), rank 0 at N=1 ----------------------

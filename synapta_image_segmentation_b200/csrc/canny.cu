@@ -448,8 +448,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef SYNSEG_CR_WAIT_HINT
+#define SYNSEG_CR_WAIT_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
+#if SYNSEG_CR_WAIT_HINT > 0
+    // with a suspend-time hint the warp sleeps in the barrier unit instead of re-issuing try_wait (7 % of the warp instructions of the kernel)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"((unsigned)SYNSEG_CR_WAIT_HINT) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -457,6 +470,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_prefetch_units(const CUtensorMap *map, int unit)
 {

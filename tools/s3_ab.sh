@@ -6,6 +6,7 @@ P=$PWD/synapta_image_segmentation_b200
 for round in 1 2; do
 for t in "$@"; do
   v=""; [ -n "$t" ] && [ "$t" != base ] && v="SYNSEG_LIB=$P/libsynseg_$t.so"
+  case "$t" in env:*) v="${t#env:}";; esac          # env:NAME=VALUE runs the product library with that variable set
   env $v $B 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
