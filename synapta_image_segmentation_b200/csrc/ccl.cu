@@ -200,8 +200,11 @@ __global__ void __launch_bounds__(256) rccl_init_kernel(RowGeom g_, int32_t *Lal
 // every weak run still reaches a strong run of its component through unions that involve at least one weak run
 // (take a path to the nearest strong run: all its edges but none beyond have a weak end).  The test is made on the
 // run pieces inside this lane's chunk (a subset of the runs), so it only ever skips safely.
+#ifndef SYNSEG_MERGE_MINB
+#define SYNSEG_MERGE_MINB 1
+#endif
 template <bool HYST, int G>
-__global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g_, int32_t *Lall, BitPlane strong)
+__global__ void __launch_bounds__(256, SYNSEG_MERGE_MINB) rccl_merge_kernel(RowGeom g_, int32_t *Lall, BitPlane strong)
 {
     ROW_PROLOGUE(1)
     if (!warp_ok) return;
@@ -247,6 +250,90 @@ __global__ void __launch_bounds__(256) rccl_merge_kernel(RowGeom g_, int32_t *La
             const int us = run_start(ru, chunk, x & ~1);
             const int cs = (x > 0) ? run_start(rc, chunk, (x - 1) & ~1) : rc.carryIn;
             uf_union(L, cur_base + cs, up_base + us);
+        }
+    }
+}
+
+// Two consecutive block rows per warp (G = 32): the pixel rows and the run analysis of block row `by` serve twice, as the lower
+// partner of by - 1 and as the upper partner of by + 1 -- six row loads and three analyses for two rows of unions instead of eight and
+// four, and all six loads of a segment are in flight together.  Same events, same unions as rccl_merge_kernel.
+template <bool HYST>
+__device__ __forceinline__ void merge_events(int32_t *L, int chunk, int width, u64 t, u64 u, uint32_t tp, uint32_t up, const Runs &rc, const Runs &ru,
+                                             int cur_base, int up_base, const uint32_t *s_cur0, const uint32_t *s_cur1, const uint32_t *s_up1,
+                                             const uint32_t *s_up0)
+{
+    const u64 tl = (t << 1) | tp, ul = (u << 1) | up;      // tl[x] = t[x-1]
+    u64 ev_a = t & ~tl & (u | ul);
+    u64 ev_b = u & ~ul & tl;
+    u64 sc = 0, su = 0;                                     // strong pixels of the current / upper block row
+    if (HYST && (ev_a | ev_b)) {
+        sc = load_chunk(s_cur0, chunk, width) | load_chunk(s_cur1, chunk, width);
+        su = load_chunk(s_up1, chunk, width) | load_chunk(s_up0, chunk, width);
+    }
+    while (ev_a) {
+        const int x = __ffsll((long long)ev_a) - 1;
+        ev_a &= ev_a - 1;
+        const int ux = ((u >> x) & 1ULL) ? x : x - 1;       // upper pixel of the contact (-1: last pixel of the previous chunk)
+        if (HYST && ux >= 0 && (sc & piece_range(rc, x & ~1)) && (su & piece_range(ru, ux & ~1))) continue;
+        const int cs = run_start(rc, chunk, x & ~1);
+        const int us = (ux >= 0) ? run_start(ru, chunk, ux & ~1) : ru.carryIn;
+        uf_union(L, cur_base + cs, up_base + us);
+    }
+    while (ev_b) {
+        const int x = __ffsll((long long)ev_b) - 1;
+        ev_b &= ev_b - 1;
+        if (HYST && x > 0 && (sc & piece_range(rc, (x - 1) & ~1)) && (su & piece_range(ru, x & ~1))) continue;
+        const int us = run_start(ru, chunk, x & ~1);
+        const int cs = (x > 0) ? run_start(rc, chunk, (x - 1) & ~1) : rc.carryIn;
+        uf_union(L, cur_base + cs, up_base + us);
+    }
+}
+
+template <bool HYST>
+__global__ void __launch_bounds__(256, HYST ? 1 : SYNSEG_MERGE_MINB) rccl_merge2_kernel(RowGeom g_, int32_t *Lall, BitPlane strong)
+{
+    constexpr int G = 32;
+    if (g_.need && __ldg(g_.need + blockIdx.y * g_.need_stride) == 0) return;      // the sweeps converged for this image
+    int width = g_.width, height = g_.height, bh = g_.bh;
+    if (g_.dims) { const int2 d_ = g_.dims[blockIdx.y]; width = d_.x; height = d_.y; bh = (d_.y + 1) >> 1; }
+    const int bw = g_.bw, wpr = g_.wpr, nseg = g_.nseg;
+    const int lane = threadIdx.x & 31;
+    const int by = 1 + 2 * (blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5));       // this warp: block rows by and by + 1
+    const int img = blockIdx.y;
+    if (by >= bh) return;                                                        // warp-uniform
+    const bool two = by + 1 < bh;
+    const uint32_t *pbase = g_.bits + img * g_.wbs;
+    // pixel rows p[i] = 2 by - 2 + i: block row by - 1 (0, 1), by (2, 3), by + 1 (4, 5); rows outside the image read as empty
+    const uint32_t *p[6], *sp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int y = 2 * by - 2 + i;
+        const bool ok = y < height && (i < 4 || two);
+        p[i] = ok ? pbase + (int64_t)y * wpr : nullptr;
+        sp[i] = (HYST && ok) ? strong.p + img * strong.bs + (int64_t)y * strong.wpr : nullptr;
+    }
+    int32_t *L = Lall + img * g_.bper;
+    RunCarry c0{0u, -1}, c1{0u, -1}, c2{0u, -1};
+    uint32_t top1 = 0, top2 = 0, top3 = 0, top4 = 0;       // last bit of the previous segment of the pixel rows p[1] .. p[4]
+    for (int s = 0; s < nseg; ++s) {
+        const int chunk = s * G + lane;
+        u64 v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = load_chunk(p[i], chunk, width);
+        const Runs r0 = analyze_runs<G>(v[0] | v[1], chunk, lane, c0);
+        const Runs r1 = analyze_runs<G>(v[2] | v[3], chunk, lane, c1);
+        const uint32_t h1 = (uint32_t)(v[1] >> 63), h2 = (uint32_t)(v[2] >> 63);
+        uint32_t up1 = __shfl_up_sync(FULL, h1, 1), tp2 = __shfl_up_sync(FULL, h2, 1);
+        if (lane == 0) { up1 = top1; tp2 = top2; }
+        top1 = __shfl_sync(FULL, h1, 31); top2 = __shfl_sync(FULL, h2, 31);
+        merge_events<HYST>(L, chunk, width, v[2], v[1], tp2, up1, r1, r0, by * bw, (by - 1) * bw, sp[2], sp[3], sp[1], sp[0]);
+        if (two) {                                          // warp-uniform
+            const Runs r2 = analyze_runs<G>(v[4] | v[5], chunk, lane, c2);
+            const uint32_t h3 = (uint32_t)(v[3] >> 63), h4 = (uint32_t)(v[4] >> 63);
+            uint32_t up3 = __shfl_up_sync(FULL, h3, 1), tp4 = __shfl_up_sync(FULL, h4, 1);
+            if (lane == 0) { up3 = top3; tp4 = top4; }
+            top3 = __shfl_sync(FULL, h3, 31); top4 = __shfl_sync(FULL, h4, 31);
+            merge_events<HYST>(L, chunk, width, v[4], v[3], tp4, up3, r2, r1, (by + 1) * bw, by * bw, sp[4], sp[5], sp[3], sp[2]);
         }
     }
 }
@@ -694,7 +781,17 @@ int run_union_find(synseg_ctx *ctx, const RowGeom &g, int G, int batch, int32_t 
         RowGeom g32 = g;
         g32.nseg = cdiv(g.width, 64 * 32);
         const dim3 grid = row_grid(g32, batch, 1, 32);
+#ifndef SYNSEG_MERGE1
+        const dim3 grid2(cdiv(cdiv(g32.bh - 1, 2), ROWS_PER_CTA), batch);
+        if (strong) rccl_merge2_kernel<true><<<grid2, 256, 0, st>>>(g32, L, *strong);
+        else rccl_merge2_kernel<false><<<grid2, 256, 0, st>>>(g32, L, BitPlane{nullptr, 0, 0});
+        SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
+        return SYNSEG_OK;
+#endif
         if (strong) rccl_merge_kernel<true, 32><<<grid, 256, 0, st>>>(g32, L, *strong);
+#ifdef SYNSEG_MERGE_G16
+        else if (G == 16) rccl_merge_kernel<false, 16><<<row_grid(g, batch, 1, 16), 256, 0, st>>>(g, L, BitPlane{nullptr, 0, 0});
+#endif
         else rccl_merge_kernel<false, 32><<<grid, 256, 0, st>>>(g32, L, BitPlane{nullptr, 0, 0});
         SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
     }
