@@ -622,32 +622,34 @@ __global__ void __launch_bounds__(32, CR_MINBLOCKS) canny_rgb_kernel(const __gri
             const uint4 *wp = (const uint4 *)(sm.rows[slot] + lane_off + a_unit);
             const uint4 q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3];
             const uint32_t w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-            const int ws = a >> 2, bsh = (a & 3) * 8;
-            uint32_t v[12];
-            switch (ws) {                                  // uniform over the warp: v[] stays in registers
-            case 0:
+            // 64 equal bytes: whatever the alignment, the 16 pixels are grey level c (R = G = B = c gives c exactly) -- blank paper and
+            // the inside of solid boxes skip the realignment and the conversion (the test used to come after the realignment)
+            uint32_t rd = 0;
 #pragma unroll
-                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], bsh);
-                break;
-            case 1:
-#pragma unroll
-                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 1], w[i + 2], bsh);
-                break;
-            case 2:
-#pragma unroll
-                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 2], w[i + 3], bsh);
-                break;
-            default:
-#pragma unroll
-                for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 3], i + 4 < 16 ? w[i + 4] : 0u, bsh);
-                break;
-            }
-            uint32_t diff = 0;
-#pragma unroll
-            for (int i = 1; i < 12; ++i) diff |= v[i] ^ v[0];
-            if ((diff | (v[0] ^ __byte_perm(v[0], 0, 0x0000))) == 0u) {
-                vcur = make_uint4(v[0], v[0], v[0], v[0]);             // 16 equal grey pixels (R = G = B = c): cv2 grey is c
+            for (int i = 1; i < 16; ++i) rd |= w[i] ^ w[0];
+            if ((rd | (w[0] ^ __byte_perm(w[0], 0, 0x0000))) == 0u) {
+                vcur = make_uint4(w[0], w[0], w[0], w[0]);
             } else {
+                const int ws = a >> 2, bsh = (a & 3) * 8;
+                uint32_t v[12];
+                switch (ws) {                                  // uniform over the warp: v[] stays in registers
+                case 0:
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], bsh);
+                    break;
+                case 1:
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 1], w[i + 2], bsh);
+                    break;
+                case 2:
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 2], w[i + 3], bsh);
+                    break;
+                default:
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = __funnelshift_r(w[i + 3], i + 4 < 16 ? w[i + 4] : 0u, bsh);
+                    break;
+                }
                 vcur.x = cv_gray4(v[0], v[1], v[2]); vcur.y = cv_gray4(v[3], v[4], v[5]);
                 vcur.z = cv_gray4(v[6], v[7], v[8]); vcur.w = cv_gray4(v[9], v[10], v[11]);
             }
