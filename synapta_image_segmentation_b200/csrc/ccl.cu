@@ -533,8 +533,11 @@ __device__ __forceinline__ void accumulate_group(unsigned peers, int key, Contri
 // Per-warp staging for the optional label image: block labels and pixel words of one 2048-pixel segment.
 struct LabelStage { int32_t lab[1024]; u64 px[2][32]; };
 
+#ifndef SYNSEG_FINAL_MINB
+#define SYNSEG_FINAL_MINB 5
+#endif
 template <bool WRITE_LABELS, int G>
-__global__ void __launch_bounds__(256) rccl_final_kernel(RowGeom g_, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
+__global__ void __launch_bounds__(256, WRITE_LABELS ? 1 : SYNSEG_FINAL_MINB) rccl_final_kernel(RowGeom g_, const int32_t *Lall, Plane labels, bool labels_al16, StatAcc a)
 {
     static_assert(!WRITE_LABELS || G == 32, "the label image path stages one block row per warp");
     __shared__ SlotCache sc;
