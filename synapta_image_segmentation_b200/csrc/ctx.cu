@@ -142,6 +142,7 @@ void guard_flush(synseg_ctx *ctx)
 {
 #ifdef SYNSEG_GUARD
     if (ctx->guard_recs.empty()) return;
+    if (ctx->in_capture) { ctx->guard_recs.clear(); return; }     // a captured call: no synchronisation allowed, its canaries are not compared
     std::vector<synseg_ctx::GuardRec> recs;
     recs.swap(ctx->guard_recs);
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return; }

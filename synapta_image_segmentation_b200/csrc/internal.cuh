@@ -49,6 +49,7 @@ struct synseg_ctx {
     int32_t *phash_basis; // device int32[8*32]
     struct GuardRec { size_t off, bytes; };             // guard build: payload offsets of the allocations of the running call
     std::vector<GuardRec> guard_recs;
+    bool in_capture = false;   // the current public call runs inside a stream capture (set by CallGuard): the guard build must not synchronise
     int64_t guard_violations, guard_checked;
     void *comm;           // ncclComm_t of the dedup exchange (exchange.cu), NULL on a single GPU
     int comm_world, comm_rank;
@@ -128,6 +129,7 @@ struct CallGuard {
         // for by streams outside it (and vice versa), so the cross-stream ordering of the scratch arena is left to whoever replays.
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(st, &cs) == cudaSuccess) capturing = cs != cudaStreamCaptureStatusNone; else cudaGetLastError();
+        c->in_capture = capturing;
         if (!capturing && c->last_valid && c->last_stream != st && c->ev_last) cudaStreamWaitEvent(st, c->ev_last, 0);
     }
     ~CallGuard()
@@ -135,6 +137,7 @@ struct CallGuard {
 #ifdef SYNSEG_GUARD
         if (!capturing) guard_flush(c);
 #endif
+        c->in_capture = false;
         if (!capturing) {
             if (c->ev_last && cudaEventRecord(c->ev_last, st) == cudaSuccess) { c->last_stream = st; c->last_valid = true; }
             else cudaGetLastError();
