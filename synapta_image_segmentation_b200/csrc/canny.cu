@@ -13,11 +13,13 @@
 //   d = [-1 0 1] are formed once from the even / odd byte lanes and kept for three rows in registers;
 //   dx = dA + 2 dB + dC, dy = sC - sA, mag = |dx| + |dy|.  mag / dx / dy go to a three-row, lane-transposed
 //   (conflict-free) shared-memory ring; the integer non-maximum suppression of the previous row runs for the
-//   candidate pixels (mag > lo) only, reading its neighbours from the ring.  Warp-uniform shortcuts: a row whose
-//   3x18 neighbourhood is constant in every lane (blank paper) skips the gradient and the ring stores.
+//   candidate pixels (mag > lo) only, reading its neighbours from the ring: a strip row full of candidates first has its steep
+//   vertical-gradient ones decided for whole lanes at once in packed arithmetic (nms_vertical_packed), the rest are listed and
+//   dealt out evenly to the lanes.  Warp-uniform shortcuts: a row whose 3x18 neighbourhood is constant in every lane (blank
+//   paper) skips the gradient and the ring stores; a row equal to the five before it repeats the previous output row.
 //   The result is two bit planes: kept = survived NMS, strong = kept and mag > hi (two lanes -> one word).
-// Stage 2 (ccl.cu): hysteresis = run-based union-find over the kept pixels + "component holds a strong
-//   pixel" flag; no host round trip, no iteration count that depends on the image.
+// Stage 2: hysteresis = bit-parallel propagation sweeps (hyst_sweep.cu), then, for the images they do not settle, the run-based
+//   union-find over the kept pixels + "component holds a strong pixel" flag (ccl.cu); no host round trip.
 //
 // Roofline: HBM-bound, 1.25 algorithmic bytes per pixel (1 read + two bit planes written) for stage 1.
 #include <cuda.h>

@@ -10,8 +10,10 @@
 // Design: warp-autonomous strips, no block-level barrier.  A warp owns a strip of 512 columns (16 per
 // lane, one 128-bit load per lane and row) and marches down a band of rows keeping the vertical running
 // column sums (row y+r+1 in, row y-r out) in registers, two 16-bit sums per register (255 rows x 255 fit).
-// Each row the horizontal window sums come from a warp-wide inclusive prefix of the column sums (local
-// prefix + shuffle scan) parked in a transposed, conflict-free shared-memory tile: S = P[x+r] - P[x-r-1].
+// Each row the horizontal window sums come from prefixes of the column sums parked in shared memory, S = P[x+r] - P[x-r-1]:
+// the generic kernel (any block size) scans them across the warp and keeps a transposed, conflict-free tile; the kernels with a
+// compile-time radius (the page pipeline's block sizes 51 and 25) keep lane-local prefixes in a lane-major tile read with 128-bit
+// loads at immediate offsets and fold the few neighbouring lane totals a window spans into the constant of the test.
 // The threshold test needs no division: mean >= g + C  <=>  2s + n >= 2n (g + C)  <=>  s >= n g + n C - (n-1)/2,
 // and its sign bit is funnel-shifted straight into the output word.  Rows on which no output pixel of the strip has
 // g <= 255 - C (blank paper: the mean cannot exceed 255) skip the prefix and the test altogether (warp-uniform).
