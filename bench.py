@@ -211,7 +211,7 @@ def workload_config(args, world, h, w):
                         f"assembled from {min(args.unique, B)} unique seeded pages",
             "pages_per_step_per_gpu": B, "dpi": args.dpi, "parallelism": f"pages sharded over {world} GPU(s)",
             "l2": f"inputs larger than L2: {B * h * w * 3 / 1e6:.0f} MB RGB per step vs 126 MB L2",
-            "streams": "synseg_detect_pages runs the two halves of a step's pages as independent chains on two CUDA streams",
+            "streams": "synseg_detect_pages runs the pages of a step as %s independent chains on %s CUDA streams" % (os.environ.get("SYNSEG_OVERLAP", "3"), os.environ.get("SYNSEG_STREAMS", "3")),
             "cuda_graph": "the detection chain of a step is captured once (Context.capture) and replayed: one graph launch per step" if os.environ.get("SYNSEG_NO_GRAPH") != "1" else "off (SYNSEG_NO_GRAPH=1)",
             "chain": "gray(cv2) -> adaptive(51,10,INV)|Canny(50,150) -> dilate(k) -> close(k) -> CCL8+stats" if args.dpi == 300 else "see DetectConfig"}
 
@@ -563,7 +563,7 @@ def main():
                 "binding_resource": binding, "issue_slots": issue_slots,
                 "note": "frac is the HBM fraction the contract asks for; the kernel's BINDING resource (from the committed ncu capture, "
                         "profiles/traffic.json) is reported in binding_resource. Per-kernel times come from profiled steps that run every "
-                        "kernel alone on one stream; the timed region runs the page chunks of a step on two streams (SYNSEG_OVERLAP)",
+                        "kernel alone on one stream; the timed region runs the page chunks of a step on several streams (SYNSEG_OVERLAP, SYNSEG_STREAMS)",
                 "page_level": {"algorithmic_bytes_per_page": 19.0 * npx, "achieved": 19.0 * npx * B / (step_ms / 1000.0) / 1e9,
                                "frac": 19.0 * npx * B / (step_ms / 1000.0) / 1e9 / peak},
                 "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "share": round(v["share"], 4),

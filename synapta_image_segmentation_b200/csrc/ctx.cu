@@ -55,7 +55,7 @@ extern "C" SYNSEG_EXPORT int synseg_create(int device, synseg_ctx **out)
     const char *e3 = getenv("SYNSEG_OVERLAP");
     const char *e4 = getenv("SYNSEG_STREAMS");
     c->overlap = e3 ? atoi(e3) : SYNSEG_OVERLAP_DEFAULT;
-    c->overlap_streams = e4 ? atoi(e4) : 2;
+    c->overlap_streams = e4 ? atoi(e4) : 3;      // 3 chunks on 3 streams: 1.34 ms per 50-page step against 1.39-1.41 with 2 on 2 (current kernels)
     if (c->overlap_streams < 2) c->overlap_streams = 2;
     if (c->overlap_streams > 4) c->overlap_streams = 4;
     c->ev_split_fork = nullptr;

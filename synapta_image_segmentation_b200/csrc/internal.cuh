@@ -12,7 +12,7 @@
 #define SYNSEG_EXPORT __attribute__((visibility("default")))
 
 #ifndef SYNSEG_OVERLAP_DEFAULT
-#define SYNSEG_OVERLAP_DEFAULT 2
+#define SYNSEG_OVERLAP_DEFAULT 3
 #endif
 
 #ifndef __CUDA_ARCH__

@@ -13,7 +13,7 @@
 // one (2k-1) pass) and the erode run on bit planes, and the labelling reads bits.  The bit planes of a
 // 50-page batch (53 MB each) stay in the 126 MB L2; the grey plane (420 MB) is re-read from HBM by the two stencils.
 // Stream plan: a batch is cut into page chunks that run as independent chains on the caller's stream and on side streams
-// owned by the context (fork / join through events; SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams, default 2 on 2), so
+// owned by the context (fork / join through events; SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams, default 3 on 3), so
 // the latency-bound union-find of one chunk overlaps the issue-bound stencils of another.
 //
 // synseg_grid_counts: per crop, grey -> Canny(50,150) -> OPEN(kw x 1, it=2) / OPEN(1 x kh, it=2)
@@ -125,7 +125,7 @@ static int detect_pages_impl(synseg_ctx *ctx, const synseg_img *rgb, const synse
     if (chunks >= 2 && B >= 2 * chunks) {
         // Page chunks as independent chains, dealt round-robin to the caller's stream and the context's side streams, each
         // stream with its own part of the arena: the latency-bound labelling of one chunk runs beside the issue- / HBM-bound
-        // front end of another (measured: 2.34 -> 2.18 ms per 50 pages with two chunks on two streams).  The side streams
+        // front end of another (measured: 2.34 -> 2.18 ms per 50 pages with two chunks on two streams in round 1; 1.47 -> 1.39 with two, 1.34 with three chunks on three streams now).  The side streams
         // fork from and join into the caller's stream through events, so the call stays asynchronous on that stream.
         SS_TRY(overlap_streams(ctx));
         const int ns = chunks < ctx->overlap_streams ? chunks : ctx->overlap_streams;

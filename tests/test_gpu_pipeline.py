@@ -66,7 +66,7 @@ def test_pipeline_odd_sizes_and_noise(ctx):
 
 def test_page_chunks_on_side_streams_equal_one_chain(ctx, monkeypatch):
     """synseg_detect_pages cuts a batch into chunks that run as independent chains on the caller's stream and the
-    context's side streams (SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams; default 2 on 2).  Every setting must give
+    context's side streams (SYNSEG_OVERLAP chunks on SYNSEG_STREAMS streams; default 3 on 3).  Every setting must give
     the tables of the single chain -- ragged last chunk, more chunks than streams, repeated calls on one context (the
     arena parts are re-used), a grey plane handed back -- and the cv2 chain's."""
     from synapta_image_segmentation_b200.ops import Context
