@@ -781,23 +781,24 @@ int run_union_find(synseg_ctx *ctx, const RowGeom &g, int G, int batch, int32_t 
     LAUNCH_G(G, rccl_init_kernel<16>, rccl_init_kernel<32>, row_grid(g, batch, 0, G), 0, st, g, L);
     SS_LAUNCH_CHECK(ctx, "ccl_init", st);
     if (g.bh > 1) {
-        // the union kernel always runs one warp per block row: two rows per warp made its divergent event loops and
-        // the atomics of adjacent rows collide (measured 0.23 -> 0.25 ms), unlike the purely analytic kernels
+        // The union kernel works on whole-warp block rows (G = 32), two consecutive rows per warp one after the other (rccl_merge2_kernel).
+        // Half-warp rows -- two rows of a warp side by side, as in the purely analytic kernels -- were slower here: divergent event loops,
+        // colliding atomics of adjacent rows (0.23 -> 0.25 ms in round 1, 0.119 against 0.109 ms now).  -DSYNSEG_MERGE1 selects the older
+        // kernel with one block row per warp (with -DSYNSEG_MERGE_G16 also its half-warp form for the labelling).
         RowGeom g32 = g;
         g32.nseg = cdiv(g.width, 64 * 32);
-        const dim3 grid = row_grid(g32, batch, 1, 32);
 #ifndef SYNSEG_MERGE1
         const dim3 grid2(cdiv(cdiv(g32.bh - 1, 2), ROWS_PER_CTA), batch);
         if (strong) rccl_merge2_kernel<true><<<grid2, 256, 0, st>>>(g32, L, *strong);
         else rccl_merge2_kernel<false><<<grid2, 256, 0, st>>>(g32, L, BitPlane{nullptr, 0, 0});
-        SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
-        return SYNSEG_OK;
-#endif
+#else
+        const dim3 grid = row_grid(g32, batch, 1, 32);
         if (strong) rccl_merge_kernel<true, 32><<<grid, 256, 0, st>>>(g32, L, *strong);
 #ifdef SYNSEG_MERGE_G16
         else if (G == 16) rccl_merge_kernel<false, 16><<<row_grid(g, batch, 1, 16), 256, 0, st>>>(g, L, BitPlane{nullptr, 0, 0});
 #endif
         else rccl_merge_kernel<false, 32><<<grid, 256, 0, st>>>(g32, L, BitPlane{nullptr, 0, 0});
+#endif
         SS_LAUNCH_CHECK(ctx, "ccl_merge", st);
     }
     return SYNSEG_OK;
