@@ -283,3 +283,27 @@ def test_decode_colors_row_layout():
     assert FeatureHints.decode_colors(row) == dict(mask_px=14900, dominant_colors=["#1ea03c", "#283cd2", "#c81e28"],
                                                    color_weights=[6400, 4500, 4000])
     assert FeatureHints.decode_colors(np.array([99, 0, 0, 0, 0, 0, 0], np.int64)) == dict(mask_px=99, dominant_colors=[], color_weights=[])
+
+
+def test_committed_ncu_traffic_table_feeds_the_bench_roofline():
+    """bench.py takes roofline.traffic / binding_resource / issue_slots of the dominant kernel from profiles/traffic.json: the
+    table must name the kernels of the page pipeline with the fields bench.py reads, for the 50-page launches the bench profiles."""
+    import json
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert tj["pages_per_launch"] == 50
+    for k in ("canny_rgb", "adaptive_mean", "bitmorph_h", "bitmorph_v", "ccl_merge", "ccl_final"):
+        e = tj["kernels"][k]
+        assert e["dram_read_bytes"] > 0 and e["dram_write_bytes"] >= 0 and isinstance(e["binding"], str) and e["warp_instructions"] > 0
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert '"issue_slots"' in src and '"cpu_baseline"' in src and '"roofline"' in src and '"e2e"' in src
+
+
+def test_variant_library_path_is_honoured(monkeypatch):
+    """SYNSEG_LIB (tuning: a variant built with SYNSEG_BUILD_TAG) replaces the path of the product library; unset, the in-tree one loads."""
+    import importlib
+    from synapta_image_segmentation_b200 import _lib
+    here = os.path.dirname(os.path.abspath(_lib.__file__))
+    monkeypatch.setenv("SYNSEG_LIB", "/nonexistent/libsynseg_x.so")
+    assert importlib.reload(_lib).LIB_PATH == "/nonexistent/libsynseg_x.so"
+    monkeypatch.delenv("SYNSEG_LIB")
+    assert importlib.reload(_lib).LIB_PATH == os.path.join(here, "libsynseg.so")
